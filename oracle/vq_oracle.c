@@ -1,0 +1,209 @@
+/*
+ * vq_oracle.c -- CPU restatement of the reference vector quantiser.  TEST INFRASTRUCTURE ONLY.
+ *
+ * This file is the parity checker for the CUDA path.  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load it; the product
+ * (vq_vae_gan_diffusion_b200/) never does.
+ *
+ * It restates /root/reference/network/vqvae/submodule/codebook.py::CodeBook.forward
+ * (codebook.py:47-111) and the autograd backward PyTorch derives from it, in plain C:
+ *
+ *   codebook.py:62-66   NCHW -> (N, D) rows, N = B*H*W in (b, h, w) order
+ *   codebook.py:70-79   d[n,k] = fl( fl(|z_n|^2 + |e_k|^2) - fl(2 * fl(z_n . e_k)) )     (fp32)
+ *   codebook.py:82      idx[n] = first index of the row minimum (torch.argmin)
+ *   codebook.py:85      e = E[idx]
+ *   codebook.py:96-103  loss = mean((e - z)^2 + beta * mean((e - z)^2))
+ *   codebook.py:106     z_q = fl(z + fl(e - z))            (straight-through value)
+ *   codebook.py:109     returned as NHWC memory viewed NCHW -> here written as (N, D) rows
+ *   backward            grad_z = g_out + g_loss * 2 (z - e) / (N D)
+ *                       grad_E[idx[n]] += g_loss * beta * 2 (e - z) / (N D)
+ *   histogram           bincount(idx, minlength=K)   (not in the reference; defined on its indices)
+ *
+ * Parity pinning: the reference ships no tests and no golden vectors.
+ * This restatement is pinned against outputs of the reference itself, generated in the build
+ * container by tests/golden/make_golden.py (imports /root/reference) and committed under
+ * tests/golden/.  See tests/test_oracle_golden.py.
+ *
+ * Accumulation order.  The reference's reductions run inside ATen/BLAS whose summation order
+ * is implementation defined (MKL sgemm on CPU, cuBLAS sgemm on GPU).  The oracle fixes ONE
+ * order -- the "canonical order" -- and the CUDA path reproduces exactly this order in its
+ * exact-fp32 re-rank, so CUDA-vs-oracle indices are bit-exact by construction, while
+ * oracle-vs-reference differences are confined to rows that are exact fp32 ties or lie within
+ * the rounding band of the reference formula (classified in tests/parity.py):
+ *
+ *   dot(x, y) over D terms: four partial sums, partial j accumulates the terms d == j (mod 4)
+ *   in ascending d with one fused multiply-add each; result = (p0 + p1) + (p2 + p3).
+ *   |x|^2 = dot(x, x).
+ *
+ * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define VQO_API __attribute__((visibility("default")))
+
+/* canonical-order dot product; x has element stride sx, y has element stride sy */
+static inline float vqo_dot(const float* x, int64_t sx, const float* y, int64_t sy, int D) {
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+    int d = 0;
+    for (; d + 3 < D; d += 4) {
+        p0 = fmaf(x[(d + 0) * sx], y[(d + 0) * sy], p0);
+        p1 = fmaf(x[(d + 1) * sx], y[(d + 1) * sy], p1);
+        p2 = fmaf(x[(d + 2) * sx], y[(d + 2) * sy], p2);
+        p3 = fmaf(x[(d + 3) * sx], y[(d + 3) * sy], p3);
+    }
+    if (d < D) { p0 = fmaf(x[d * sx], y[d * sy], p0); d++; }
+    if (d < D) { p1 = fmaf(x[d * sx], y[d * sy], p1); d++; }
+    if (d < D) { p2 = fmaf(x[d * sx], y[d * sy], p2); d++; }
+    return (p0 + p1) + (p2 + p3);
+}
+
+/* fp32 distance of the reference formula, codebook.py:70-79 */
+static inline float vqo_dist(float z2, float e2, float dot) {
+    volatile float s = z2 + e2;     /* fl(|z|^2 + |e|^2) */
+    volatile float t = 2.0f * dot;  /* fl(2 * dot) (exact) */
+    return s - t;
+}
+
+VQO_API int vq_oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+/* |row|^2 of a (R, D) row-major matrix in canonical order */
+VQO_API void vq_oracle_row_norms(const float* X, int64_t R, int D, float* out) {
+#pragma omp parallel for schedule(static)
+    for (int64_t r = 0; r < R; r++) out[r] = vqo_dot(X + r * D, 1, X + r * D, 1, D);
+}
+
+/*
+ * Full forward.  z_nchw is contiguous (B, D, HW).  Any output pointer may be NULL.
+ *   zq_nhwc  (N, D)   straight-through value fl(z + fl(e - z))
+ *   idx      (N)      int64 argmin, first minimum
+ *   loss     (1)      fp32
+ *   hist     (K)      int64 bincount(idx)
+ *   dist_min (N)      fp32 minimal distance (diagnostic)
+ *   tie_rows (1)      rows whose minimal fp32 distance is attained by >= 2 codes
+ */
+VQO_API int vq_oracle_forward(const float* z_nchw, int64_t B, int64_t HW, int D,
+                              const float* E, int K, float beta,
+                              float* zq_nhwc, int64_t* idx, float* loss, int64_t* hist,
+                              float* dist_min, uint64_t* tie_rows) {
+    if (B < 0 || HW < 0 || D <= 0 || K <= 0) return -1;
+    const int64_t N = B * HW;
+    float* e2 = (float*)malloc(sizeof(float) * (size_t)K);
+    int64_t* idx_local = idx ? idx : (int64_t*)malloc(sizeof(int64_t) * (size_t)(N > 0 ? N : 1));
+    if (!e2 || !idx_local) return -2;
+    vq_oracle_row_norms(E, K, D, e2);
+
+    uint64_t ties = 0;
+    double sq_sum = 0.0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : ties, sq_sum)
+    for (int64_t n = 0; n < N; n++) {
+        const int64_t b = n / HW, hw = n % HW;
+        const float* zr = z_nchw + b * (int64_t)D * HW + hw; /* element stride HW */
+        const float z2 = vqo_dot(zr, HW, zr, HW, D);
+        float best = INFINITY;
+        int64_t best_k = 0;
+        int n_best = 0;
+        for (int k = 0; k < K; k++) {
+            const float dot = vqo_dot(zr, HW, E + (int64_t)k * D, 1, D);
+            const float dist = vqo_dist(z2, e2[k], dot);
+            if (k == 0 || dist < best) { best = dist; best_k = k; n_best = 1; }
+            else if (dist == best) n_best++;
+        }
+        idx_local[n] = best_k;
+        if (dist_min) dist_min[n] = best;
+        if (n_best > 1) ties++;
+        const float* e = E + best_k * D;
+        for (int d = 0; d < D; d++) {
+            const float zv = zr[(int64_t)d * HW];
+            volatile float diff = e[d] - zv;               /* fl(e - z) */
+            if (zq_nhwc) zq_nhwc[n * D + d] = zv + diff;   /* fl(z + fl(e - z)), codebook.py:106 */
+            volatile float sq = diff * diff;
+            sq_sum += (double)sq;
+        }
+    }
+    if (tie_rows) *tie_rows = ties;
+    if (loss) {
+        /* mean(a + beta*mean(b)) with a == b elementwise, codebook.py:96-103 */
+        const double m = (N > 0) ? sq_sum / ((double)N * (double)D) : NAN;
+        *loss = (float)(m + (double)beta * m);
+    }
+    if (hist) {
+        memset(hist, 0, sizeof(int64_t) * (size_t)K);
+        for (int64_t n = 0; n < N; n++) hist[idx_local[n]]++;
+    }
+    free(e2);
+    if (!idx) free(idx_local);
+    return 0;
+}
+
+/*
+ * Distances of selected (row, code) pairs in canonical order -- lets the tests classify a
+ * disagreement without recomputing whole rows.
+ */
+VQO_API void vq_oracle_pair_dist(const float* z_nchw, int64_t B, int64_t HW, int D,
+                                 const float* E, const int64_t* rows, const int64_t* codes,
+                                 int64_t npairs, float* out) {
+    (void)B;
+    for (int64_t i = 0; i < npairs; i++) {
+        const int64_t n = rows[i], b = n / HW, hw = n % HW;
+        const float* zr = z_nchw + b * (int64_t)D * HW + hw;
+        const float* e = E + codes[i] * D;
+        out[i] = vqo_dist(vqo_dot(zr, HW, zr, HW, D), vqo_dot(e, 1, e, 1, D), vqo_dot(zr, HW, e, 1, D));
+    }
+}
+
+/*
+ * Backward of the reference forward as PyTorch autograd derives it.
+ *   gout     upstream gradient on z_q, logical shape (B, D, HW), element strides gs[3] = {b, d, hw};
+ *            may be NULL (treated as zero)
+ *   g_loss   upstream gradient on the scalar loss
+ *   n_global number of latents the loss mean ran over (= N on one device; the global N when the
+ *            batch is sharded, so that summed shard gradients equal the single-device gradient)
+ *   grad_z   (B, D, HW) contiguous NCHW
+ *   grad_E   (K, D), overwritten
+ */
+VQO_API int vq_oracle_backward(const float* gout, const int64_t* gs, float g_loss,
+                               const float* z_nchw, const int64_t* idx, const float* E,
+                               int64_t B, int64_t HW, int D, int K, float beta, int64_t n_global,
+                               float* grad_z, float* grad_E) {
+    const int64_t N = B * HW;
+    if (n_global <= 0) n_global = N;
+    const float coef = (float)(2.0 * (double)g_loss / ((double)n_global * (double)D));
+    const float coef_e = beta * coef;
+    if (grad_E) memset(grad_E, 0, sizeof(float) * (size_t)K * (size_t)D);
+    if (grad_z) {
+#pragma omp parallel for schedule(static)
+        for (int64_t n = 0; n < N; n++) {
+            const int64_t b = n / HW, hw = n % HW;
+            const float* e = E + idx[n] * D;
+            for (int d = 0; d < D; d++) {
+                const int64_t off = b * (int64_t)D * HW + (int64_t)d * HW + hw;
+                const float g = gout ? gout[b * gs[0] + d * gs[1] + hw * gs[2]] : 0.f;
+                grad_z[off] = fmaf(coef, z_nchw[off] - e[d], g);
+            }
+        }
+    }
+    if (grad_E) {
+        /* serial, ascending n: a deterministic summation order for the scatter-add */
+        for (int64_t n = 0; n < N; n++) {
+            const int64_t b = n / HW, hw = n % HW;
+            const float* e = E + idx[n] * D;
+            float* ge = grad_E + idx[n] * D;
+            for (int d = 0; d < D; d++)
+                ge[d] += coef_e * (e[d] - z_nchw[b * (int64_t)D * HW + (int64_t)d * HW + hw]);
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,78 @@
+"""Seeded synthetic inputs shared by the golden-vector generator, the oracle tests and the GPU parity tests.
+
+Inputs are regenerated from seeds (numpy PCG64) instead of being stored, so tests/golden/ only has to hold the
+reference's OUTPUTS.  Distributions follow SURVEY.md section 8(d):
+  "init"    E ~ U(-1/K, 1/K) (codebook.py:43-45), z ~ N(0,1)            -> many fp32 near-ties
+  "trained" E ~ N(0,1), z = E[randint(K)] + 0.3 N(0,1)                  -> well separated
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# name -> spec.  D is 256 everywhere the CUDA path runs (latent_dim of every reference config).
+CASES = {
+    # tiny, full arrays stored
+    "small_init":     dict(B=2, H=4, W=4, K=64, D=256, dist="init", seed=101),
+    "small_trained":  dict(B=2, H=4, W=4, K=64, D=256, dist="trained", seed=102),
+    # ragged: N and K are not multiples of any tile size
+    "ragged_init":    dict(B=3, H=5, W=7, K=100, D=256, dist="init", seed=103),
+    "ragged_trained": dict(B=3, H=5, W=7, K=333, D=256, dist="trained", seed=104),
+    # BASELINE.json configs[0]: VQGAN small on 28x28 -> encoder output 1x1, batch 200, K=1024
+    "cfg1_init":      dict(B=200, H=1, W=1, K=1024, D=256, dist="init", seed=105),
+    # BASELINE.json configs[1] at 1/8 batch: 16x16 latents, K=1024
+    "cfg2s_init":     dict(B=8, H=16, W=16, K=1024, D=256, dist="init", seed=106),
+    "cfg2s_trained":  dict(B=8, H=16, W=16, K=1024, D=256, dist="trained", seed=107),
+    # large-K tie census (configs[2]/[3] codebooks at reduced N)
+    "k8192_init":     dict(B=1, H=32, W=32, K=8192, D=256, dist="init", seed=108),
+    "k16384_trained": dict(B=1, H=16, W=32, K=16384, D=256, dist="trained", seed=109),
+    # edge cases of the domain
+    "dup_rows":       dict(B=2, H=8, W=8, K=96, D=256, dist="dup", seed=110),      # duplicated code rows -> lowest index
+    "exact_hit":      dict(B=2, H=8, W=8, K=128, D=256, dist="exact", seed=111),   # z equals a code -> distance 0
+    "zero_codebook":  dict(B=1, H=4, W=8, K=40, D=256, dist="zero", seed=112),     # every code ties -> index 0
+    # oracle-only known answer (D != 256)
+    "k4_d2":          dict(B=1, H=1, W=3, K=4, D=2, dist="kat", seed=0),
+}
+
+FULL_ARRAY_LIMIT = 1 << 15      # cases with N*D below this store z_q / grads whole, others store samples
+N_SAMPLES = 2048
+
+
+def make_inputs(spec: dict):
+    """-> z (B, D, H, W) fp32 C-contiguous, E (K, D) fp32, g_out_nhwc (B, H, W, D) fp32."""
+    B, H, W, K, D = spec["B"], spec["H"], spec["W"], spec["K"], spec["D"]
+    rng = np.random.default_rng(spec["seed"])
+    dist = spec["dist"]
+    N = B * H * W
+    if dist == "kat":
+        # hand-computed case: codes on the corners of a square, three latents
+        E = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0]], np.float32)
+        zf = np.array([[0.1, 0.2], [0.9, 0.2], [0.6, 0.9]], np.float32)      # -> codes 0, 1, 3
+        z = np.ascontiguousarray(zf.reshape(B, H, W, D).transpose(0, 3, 1, 2))
+        g = np.array([[1.0, -1.0], [0.5, 0.25], [-2.0, 4.0]], np.float32).reshape(B, H, W, D)
+        return z, E, g
+    if dist == "init":
+        E = rng.uniform(-1.0 / K, 1.0 / K, size=(K, D)).astype(np.float32)
+        zf = rng.standard_normal((N, D), dtype=np.float32)
+    elif dist == "trained":
+        E = rng.standard_normal((K, D), dtype=np.float32)
+        zf = E[rng.integers(0, K, size=N)] + np.float32(0.3) * rng.standard_normal((N, D), dtype=np.float32)
+    elif dist == "dup":
+        base = rng.standard_normal((K // 3, D), dtype=np.float32)
+        E = np.concatenate([base, base, base], axis=0)[:K]                      # rows k, k+K/3, k+2K/3 identical
+        zf = base[rng.integers(0, K // 3, size=N)] + np.float32(0.1) * rng.standard_normal((N, D), dtype=np.float32)
+    elif dist == "exact":
+        E = rng.standard_normal((K, D), dtype=np.float32)
+        zf = E[rng.integers(0, K, size=N)].copy()
+    elif dist == "zero":
+        E = np.zeros((K, D), np.float32)
+        zf = rng.standard_normal((N, D), dtype=np.float32)
+    else:
+        raise ValueError(dist)
+    z = np.ascontiguousarray(zf.reshape(B, H, W, D).transpose(0, 3, 1, 2)).astype(np.float32)
+    g = rng.standard_normal((B, H, W, D), dtype=np.float32)
+    return z, np.ascontiguousarray(E, dtype=np.float32), g
+
+
+def sample_positions(n_elems: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed + 7919)
+    return np.sort(rng.choice(n_elems, size=min(N_SAMPLES, n_elems), replace=False)).astype(np.int64)

@@ -1,0 +1,154 @@
+"""Pin the CPU oracle (oracle/vq_oracle.c and the numpy/BLAS port) against outputs of the reference itself.
+
+The golden files were produced by tests/golden/make_golden.py from the unmodified reference CodeBook
+(/root/reference/network/vqvae/submodule/codebook.py).  CPU-only; runs in seconds.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from cases import CASES, FULL_ARRAY_LIMIT, make_inputs, sample_positions
+from parity import assert_close, classify_index_mismatches
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def compare_floats(gold, key, arr, spec, mask_rows=None, D=None):
+    """arr against the golden whole array or its samples; rows in mask_rows (index disagreements) are skipped."""
+    arr = np.asarray(arr)
+    if key in gold.files:
+        ref = gold[key].reshape(arr.shape)
+        if mask_rows is not None and len(mask_rows):
+            keep = np.ones(arr.shape[0], bool)
+            keep[mask_rows] = False
+            arr, ref = arr[keep], ref[keep]
+        return assert_close(arr, ref, key)
+    pos = sample_positions(arr.size, spec["seed"])
+    got = arr.reshape(-1)[pos]
+    ref = gold[key + "_samples"]
+    scale = float(gold[key + "_absmax"])
+    if mask_rows is not None and len(mask_rows):
+        keep = ~np.isin(pos // D, mask_rows)
+        got, ref = got[keep], ref[keep]
+    err = float(np.abs(got.astype(np.float64) - ref).max() / max(scale, 1e-30))
+    assert err <= 1e-5, f"{key}: sampled relative error {err:.3e}"
+    return err
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_c_oracle_matches_reference(name, oracle):
+    spec = CASES[name]
+    gold = load(name)
+    z, E, g = make_inputs(spec)
+    D = spec["D"]
+    out = oracle.forward(z, E, beta=0.25)
+    ref_idx = gold["idx"].astype(np.int64)
+
+    cls = classify_index_mismatches(z, E, out["idx"], ref_idx, pair_dist=oracle.pair_dist)
+    assert cls["real"] == 0, f"real index mismatches vs reference: {cls}"
+    # disagreements can only come from rows the reference itself cannot decide exactly
+    assert cls["mismatch"] <= int(gold["ref_tie_rows"]) + int(gold["ref_ne_fp64"]) + 2, cls
+    bad = np.nonzero(out["idx"] != ref_idx)[0]
+
+    assert np.array_equal(out["hist"], np.bincount(out["idx"], minlength=spec["K"]))
+    # loss: every row contributes, mismatching rows are near-ties so the value agrees to ~1e-7
+    assert abs(float(out["loss"]) - float(gold["loss"])) <= 1e-5 * max(abs(float(gold["loss"])), 1e-30) + 1e-12
+    compare_floats(gold, "zq", out["zq_nhwc"], spec, bad, D)
+
+    g_view = np.transpose(g, (0, 3, 1, 2))                       # NHWC memory viewed NCHW (like the reference test)
+    grad_z, grad_E = oracle.backward(g_view, 1.0, z, ref_idx, E, beta=0.25)   # reference indices: float parity
+    B, H, W = spec["B"], spec["H"], spec["W"]
+    gz_rows = np.moveaxis(grad_z.reshape(B, D, H * W), 1, 2).reshape(-1, D)
+    if "grad_z" in gold.files:
+        assert_close(grad_z, gold["grad_z"], "grad_z")
+        assert_close(grad_E, gold["grad_E"], "grad_E")
+    else:
+        compare_floats(gold, "grad_z", grad_z, spec)
+        compare_floats(gold, "grad_E", grad_E, spec)
+    assert gz_rows.shape == (B * H * W, D)
+
+
+def test_known_answer_k4_d2(oracle):
+    """Hand-computed: codes on the unit square corners."""
+    spec = CASES["k4_d2"]
+    z, E, g = make_inputs(spec)
+    out = oracle.forward(z, E, beta=0.25)
+    assert out["idx"].tolist() == [0, 1, 3]
+    # sum (e-z)^2 = (0.01+0.04) + (0.01+0.04) + (0.16+0.01) = 0.27 ; mean over 6 = 0.045 ; *(1+0.25)
+    assert abs(float(out["loss"]) - 0.05625) < 1e-7
+    assert out["hist"].tolist() == [1, 1, 0, 1]
+    gold = load("k4_d2")
+    assert gold["idx"].tolist() == [0, 1, 3] and abs(float(gold["loss"]) - 0.05625) < 1e-7
+
+
+def test_duplicate_rows_lowest_index(oracle):
+    spec = CASES["dup_rows"]
+    z, E, _ = make_inputs(spec)
+    out = oracle.forward(z, E)
+    assert out["idx"].max() < spec["K"] // 3          # the first copy of every duplicated row wins
+    assert out["tie_rows"] == out["idx"].size
+    assert np.array_equal(out["idx"], load("dup_rows")["idx"])
+
+
+def test_exact_hit_zero_distance(oracle):
+    spec = CASES["exact_hit"]
+    z, E, _ = make_inputs(spec)
+    out = oracle.forward(z, E)
+    assert float(out["loss"]) == 0.0
+    rows = np.moveaxis(z.reshape(spec["B"], spec["D"], -1), 1, 2).reshape(-1, spec["D"])
+    assert np.array_equal(out["zq_nhwc"], rows)
+    assert np.array_equal(E[out["idx"]], rows)
+
+
+def test_zero_codebook_all_tie_index0(oracle):
+    spec = CASES["zero_codebook"]
+    z, E, _ = make_inputs(spec)
+    out = oracle.forward(z, E)
+    assert (out["idx"] == 0).all() and out["tie_rows"] == out["idx"].size
+    assert (load("zero_codebook")["idx"] == 0).all()
+
+
+@pytest.mark.parametrize("name", ["small_init", "cfg1_init", "cfg2s_trained", "k8192_init"])
+def test_blas_port_matches_reference(name, oracle):
+    """The numpy/BLAS port (the timed CPU baseline) follows the reference too."""
+    from oracle.vq_oracle import backward_blas, forward_blas
+    spec = CASES[name]
+    gold = load(name)
+    z, E, g = make_inputs(spec)
+    zq, idx, loss = forward_blas(z, E, 0.25)
+    cls = classify_index_mismatches(z, E, idx, gold["idx"].astype(np.int64), pair_dist=oracle.pair_dist)
+    assert cls["real"] == 0, cls
+    assert abs(float(loss) - float(gold["loss"])) <= 1e-5 * abs(float(gold["loss"]))
+    _, idx_only, _ = forward_blas(z, E, 0.25, indices_only=True)
+    assert np.array_equal(idx, idx_only)
+    gz, gE = backward_blas(g.reshape(-1, spec["D"]), 1.0, z, gold["idx"].astype(np.int64), E, 0.25)
+    gz_c, gE_c = oracle.backward(np.transpose(g, (0, 3, 1, 2)), 1.0, z, gold["idx"].astype(np.int64), E, 0.25)
+    B, D = spec["B"], spec["D"]
+    assert_close(gz, np.moveaxis(gz_c.reshape(B, D, -1), 1, 2).reshape(-1, D), "grad_z port vs C")
+    assert_close(gE, gE_c, "grad_E port vs C")
+
+
+def test_oracle_backward_n_global(oracle):
+    """Sharded backward with n_global equals the single-device gradient on the concatenated batch."""
+    spec = CASES["small_trained"]
+    z, E, g = make_inputs(spec)
+    out = oracle.forward(z, E)
+    gv = np.transpose(g, (0, 3, 1, 2))
+    gz, gE = oracle.backward(gv, 1.0, z, out["idx"], E)
+    N = out["idx"].size
+    half = spec["B"] // 2
+    hw = spec["H"] * spec["W"]
+    parts = []
+    gE_sum = np.zeros_like(gE)
+    for sl in (slice(0, half), slice(half, spec["B"])):
+        rows = slice(sl.start * hw, sl.stop * hw)
+        gzi, gEi = oracle.backward(gv[sl], 1.0, z[sl], out["idx"][rows], E, n_global=N)
+        parts.append(gzi)
+        gE_sum += gEi
+    assert_close(np.concatenate(parts, 0), gz, "sharded grad_z")
+    assert_close(gE_sum, gE, "sharded grad_E")
