@@ -1,0 +1,131 @@
+/*
+ * vq_b200.h -- C ABI of the B200-native vector-quantiser hot path (libvq_b200.so).
+ *
+ * The reference (hongrui16/VQ-VAE-GAN-Diffusion) is pure Python and has no FFI layer; its boundary for this
+ * path is the class network/vqvae/submodule/codebook.py::CodeBook (codebook.py:13-111).  This header is the
+ * C-ABI a binding for that class calls (see INTEGRATION.md for the ctypes stub a maintainer would add to the
+ * reference).  Each entry point names the reference lines it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all memory;
+ *   - no entry point allocates, frees or synchronises the device; all work is enqueued on `stream`;
+ *   - return value 0 = OK, otherwise a negative VQ_E_* code or a positive cudaError_t;
+ *     vq_last_error() gives a thread-local message;
+ *   - the library is re-entrant (forward runs on the caller's thread, backward on PyTorch's autograd thread);
+ *   - D (latent_dim) must be 256 -- the value of every reference config (configs/*.yml) -- else VQ_E_UNSUPPORTED;
+ *   - N = B*HW latents in (b, h, w) order, z is contiguous NCHW (B, D, HW).
+ *   - there is NO CPU fallback: on a device that is not sm_100 every compute entry point fails with
+ *     VQ_E_DEVICE.
+ */
+#ifndef VQ_B200_H_
+#define VQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* vq_stream_t; /* == cudaStream_t */
+
+#define VQ_OK             0
+#define VQ_E_INVALID     -1   /* bad argument (null pointer, negative size, misaligned pointer) */
+#define VQ_E_UNSUPPORTED -2   /* D != 256, K < 1, ... */
+#define VQ_E_WORKSPACE   -3   /* workspace too small */
+#define VQ_E_DEVICE      -4   /* current device is not sm_100 / driver entry point missing */
+
+/* stats[] slots written by vq_argmin / vq_forward (uint64 each, overwritten) */
+#define VQ_STAT_TIE_ROWS      0  /* rows whose minimal fp32 distance is attained by >= 2 codes */
+#define VQ_STAT_RERANK_ROWS   1  /* rows that needed the exact-fp32 re-rank (>= 2 candidates within the margin) */
+#define VQ_STAT_FALLBACK_ROWS 2  /* rows resolved by the full fp32 row scan (candidate list overflow) */
+#define VQ_STAT_CANDIDATES    3  /* total candidates that survived the margin filter */
+#define VQ_STAT_COUNT         4
+
+int         vq_abi_version(void);
+const char* vq_last_error(void);
+
+/* 0 if the CURRENT device can run the kernels (compute capability 10.0), else VQ_E_DEVICE. */
+int vq_device_check(void);
+
+/* Padded codebook rows: K rounded up to the code-tile size (256).  E_h holds K_pad*D fp16, e_norm2 K_pad floats. */
+int vq_padded_codes(int K);
+
+/* Bytes of scratch vq_argmin / vq_forward need for N latents. */
+int vq_workspace_bytes(int64_t N, int K, int D, size_t* out_host);
+
+/*
+ * Derived codebook state; call again whenever the weight changed.
+ * Replaces: torch.sum(self.codebook.weight**2, dim=1)  (codebook.py:74) and the operand conversion the
+ * reference's sgemm does implicitly.
+ *   E            (K, D) fp32  nn.Embedding weight (codebook.py:40)
+ *   E_h          (K_pad, D) fp16 tensor-core operand: E * 2^s with s chosen so max|E * 2^s| is in [2^14, 2^15)
+ *                (an exact scaling); rows >= K zero
+ *   e_norm2      (K_pad) fp32 |e_k|^2 in the oracle's canonical order, rows >= K = +inf
+ *   cb_scalars   (4) fp32: [0] max_k |e_k|^2, [1] max |E|, [2] 2^-s, [3] reserved
+ */
+int vq_prepare_codebook(const float* E, int K, int D, void* E_h, float* e_norm2, float* cb_scalars,
+                        vq_stream_t stream);
+
+/*
+ * Tokeniser mode: indices only.
+ * Replaces codebook.py:62-82 as reached from VQVAE.encode (network/vqvae/vqvae.py:139-146) by
+ * VQTransformer.encode_to_z (network/vqTransformer/vqTransformer.py:64-81) and VQDiffusion.encode_to_z
+ * (network/vqDiffusion/vqDiffusion.py:140-156), which discard z_q and the loss.
+ *   idx    (N) int64 -- torch.argmin semantics (first minimum) of the fp32 distance formula
+ *   stats  (VQ_STAT_COUNT) uint64, optional (may be NULL)
+ */
+int vq_argmin(const float* z_nchw, int64_t B, int64_t HW, int D,
+              const float* E, const void* E_h, const float* e_norm2, const float* cb_scalars, int K,
+              int64_t* idx, unsigned long long* stats,
+              void* workspace, size_t workspace_bytes, vq_stream_t stream);
+
+/*
+ * Training forward.  Replaces CodeBook.forward, codebook.py:47-111.
+ *   zq_nhwc (N, D) fp32 -- fl(z + fl(e - z)) in NHWC memory (the caller exposes it as the NCHW view the
+ *                          reference returns, codebook.py:109)
+ *   idx     (N) int64
+ *   loss    (1) fp32    -- mean((e-z)^2 + beta*mean((e-z)^2)), codebook.py:96-103
+ *   hist    (K) int64   -- bincount(idx, minlength=K); optional (may be NULL); overwritten
+ */
+int vq_forward(const float* z_nchw, int64_t B, int64_t HW, int D,
+               const float* E, const void* E_h, const float* e_norm2, const float* cb_scalars, int K,
+               float beta, float* zq_nhwc, int64_t* idx, float* loss, int64_t* hist,
+               unsigned long long* stats, void* workspace, size_t workspace_bytes, vq_stream_t stream);
+
+/*
+ * Backward of CodeBook.forward as autograd derives it:
+ *   grad_z = g_out + g_loss * 2 (z - e) / (n_global * D)              (contiguous NCHW)
+ *   grad_E[idx[n]] += g_loss * beta * 2 (e - z) / (n_global * D)      (dense (K, D), zeroed here first)
+ *   gout          upstream gradient on z_q, logical (B, D, HW); element strides gout_strides_host[3] =
+ *                 {b, d, hw}; may be NULL (no upstream gradient)
+ *   g_loss        upstream gradient on the scalar loss, as a host value; if g_loss_dev is non-NULL the value is
+ *                 read from that device scalar instead (lets an autograd backward run without a host sync)
+ *   n_global      latents the loss mean ran over; pass N on one device, the global N when the batch is sharded
+ *   grad_z_nchw   may be NULL (z does not require grad); grad_E may be NULL (frozen codebook)
+ */
+int vq_backward(const float* gout, const int64_t* gout_strides_host, float g_loss, const float* g_loss_dev,
+                const float* z_nchw, const int64_t* idx, const float* E,
+                int64_t B, int64_t HW, int D, int K, float beta, int64_t n_global,
+                float* grad_z_nchw, float* grad_E, vq_stream_t stream);
+
+/*
+ * Index -> embedding lookup in NCHW layout (the decode side: codebook(indices).reshape(B,h,w,D).permute(0,3,1,2),
+ * worker/vqganVqvaeWorker.py:459, network/vqTransformer/vqTransformer.py:98).
+ *   out_nchw (B, D, HW) fp32
+ */
+int vq_embed_nchw(const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K,
+                  float* out_nchw, vq_stream_t stream);
+
+/* Number of kernel launches the last call on this thread enqueued (for bench.py's gpu_launches). */
+int vq_last_launch_count(void);
+
+/* Debug: dump the approximate (fp16 tensor-core) scores e2[k] - 2 z.e for all (n, k); N*K_pad floats. */
+int vq_debug_scores(const float* z_nchw, int64_t B, int64_t HW, int D,
+                    const void* E_h, const float* e_norm2, const float* cb_scalars, int K,
+                    float* scores, void* workspace, size_t workspace_bytes, vq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQ_B200_H_ */

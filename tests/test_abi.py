@@ -1,0 +1,74 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol that
+include/vq_b200.h declares; host-side argument validation works without a GPU; the module refuses to run on CPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import vq_vae_gan_diffusion_b200 as vq
+from vq_vae_gan_diffusion_b200 import _native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "vq_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vq_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    path = _native.build()
+    assert os.path.exists(path)
+    L = ctypes.CDLL(path)
+    syms = declared_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/vq_b200.h but not exported"
+    assert set(syms) == set(_native.EXPORTED_SYMBOLS), "ctypes signatures out of sync with the header"
+    assert _native.lib().vq_abi_version() == 1
+
+
+def test_host_side_validation_without_gpu():
+    L = _native.lib()
+    assert L.vq_padded_codes(1) == 256 and L.vq_padded_codes(256) == 256 and L.vq_padded_codes(257) == 512
+    out = ctypes.c_size_t(0)
+    assert L.vq_workspace_bytes(1000, 1024, 256, ctypes.byref(out)) == 0 and out.value > 1000 * 256 * 2
+    small = out.value
+    assert L.vq_workspace_bytes(100000, 1024, 256, ctypes.byref(out)) == 0 and out.value > small
+    assert L.vq_workspace_bytes(1000, 1024, 128, ctypes.byref(out)) == -2          # VQ_E_UNSUPPORTED: D != 256
+    assert b"256" in L.vq_last_error()
+    assert L.vq_workspace_bytes(-1, 1024, 256, ctypes.byref(out)) == -1            # VQ_E_INVALID
+    # compute entry points reject bad arguments before touching the device
+    assert L.vq_argmin(None, 1, 1, 64, None, None, None, None, 16, None, None, None, 0, None) == -2
+    assert L.vq_forward(None, 4, 4, 256, None, None, None, None, 16, 0.25, None, None, None, None, None, None, 0, None) == -1
+
+
+def test_module_has_no_cpu_path():
+    cb = vq.CodeBook(32, 256)
+    assert list(cb.state_dict().keys()) == ["codebook.weight"]
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cb(torch.zeros(1, 256, 2, 2))
+    with pytest.raises(ValueError):
+        cb(torch.zeros(1, 256, 2))
+
+
+def test_constructor_matches_reference_rng_consumption():
+    """Same seed -> same weights as the reference constructor (nn.Embedding init, then uniform_(-1/K, 1/K))."""
+    torch.manual_seed(123)
+    cb = vq.CodeBook(num_codebook_vectors=48, latent_dim=256, beta=0.3)
+    torch.manual_seed(123)
+    emb = torch.nn.Embedding(48, 256)
+    emb.weight.data.uniform_(-1 / 48, 1 / 48)
+    assert torch.equal(cb.codebook.weight, emb.weight)
+    assert (cb.num_codebook_vectors, cb.latent_dim, cb.beta) == (48, 256, 0.3)
+
+
+def test_install_registers_reference_module_path():
+    import sys
+    vq.install()
+    from network.vqvae.submodule.codebook import CodeBook  # noqa: the reference's import line (vqvae.py:17)
+    assert CodeBook is vq.CodeBook
+    del sys.modules["network.vqvae.submodule.codebook"]

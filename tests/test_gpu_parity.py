@@ -1,0 +1,304 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Every call goes through the C-ABI of
+include/vq_b200.h (ctypes), either directly or via the CodeBook module; the checker is the CPU oracle and the
+golden vectors of the reference.  Nothing here reads /root/reference.
+
+Bars (north_star / SURVEY 8(c)): indices and histogram bit-exact against the oracle; z_q bit-exact (it is one
+IEEE add of one IEEE subtract); loss and gradients within 1e-5 relative; against the reference's golden
+indices every disagreement must be an exact tie or inside the rounding band, and is counted.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from cases import CASES, make_inputs, sample_positions
+from parity import assert_close, classify_index_mismatches, rel_err
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GPU_CASES = [n for n, s in CASES.items() if s["D"] == 256]
+
+
+@pytest.fixture(scope="module")
+def vq():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import vq_vae_gan_diffusion_b200 as m
+    assert os.path.exists(m._native.LIB_PATH), "libvq_b200.so must be built in-tree (no fallback)"
+    m._native.check(m._native.lib().vq_device_check(), "vq_device_check")
+    assert torch.backends.cuda.matmul.allow_tf32 is False
+    return m
+
+
+def run_module(vq, z_np, E_np, g_nhwc=None, beta=0.25, g_loss=1.0):
+    """forward (+ backward) through the CodeBook module on cuda:0 -> numpy dict."""
+    dev = torch.device("cuda:0")
+    K, D = E_np.shape
+    cb = vq.CodeBook(K, D, beta).to(dev)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(torch.from_numpy(E_np))
+    z = torch.from_numpy(z_np).to(dev).requires_grad_(True)
+    z_q, idx, loss = cb(z)
+    out = dict(z_q=z_q, idx=idx.cpu().numpy(), loss=float(loss.item()),
+               hist=cb.last_histogram.cpu().numpy(), stats=cb.stats_dict(),
+               zq_rows=z_q.detach().permute(0, 2, 3, 1).reshape(-1, D).cpu().numpy())
+    if g_nhwc is not None:
+        g = torch.from_numpy(g_nhwc).to(dev).permute(0, 3, 1, 2)          # NHWC memory viewed NCHW, like z_q
+        (g_loss * loss + (z_q * g).sum()).backward()
+        out["grad_z"] = z.grad.cpu().numpy()
+        out["grad_E"] = cb.codebook.weight.grad.cpu().numpy()
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("name", GPU_CASES)
+def test_forward_backward_vs_oracle(name, vq, oracle):
+    spec = CASES[name]
+    z, E, g = make_inputs(spec)
+    D, K = spec["D"], spec["K"]
+    got = run_module(vq, z, E, g)
+    ref = oracle.forward(z, E, beta=0.25)
+
+    assert got["idx"].dtype == np.int64 and got["idx"].shape == ref["idx"].shape
+    nbad = int((got["idx"] != ref["idx"]).sum())
+    assert nbad == 0, f"{nbad} indices differ from the oracle, first rows {np.nonzero(got['idx'] != ref['idx'])[0][:8]}"
+    assert np.array_equal(got["hist"], ref["hist"])
+    assert np.array_equal(got["hist"], np.bincount(got["idx"], minlength=K))
+    assert np.array_equal(got["zq_rows"], ref["zq_nhwc"]), "z_q must be bit-exact: fl(z + fl(e - z))"
+    assert abs(got["loss"] - float(ref["loss"])) <= 1e-6 * abs(float(ref["loss"])) + 1e-12
+    assert got["stats"]["tie_rows"] == ref["tie_rows"], (got["stats"], ref["tie_rows"])
+
+    gz, gE = oracle.backward(np.transpose(g, (0, 3, 1, 2)), 1.0, z, ref["idx"], E, beta=0.25)
+    assert_close(got["grad_z"], gz, "grad_z")
+    assert_close(got["grad_E"], gE, "grad_E")
+
+
+@pytest.mark.parametrize("name", GPU_CASES)
+def test_against_reference_golden(name, vq, oracle):
+    spec = CASES[name]
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    z, E, g = make_inputs(spec)
+    D = spec["D"]
+    got = run_module(vq, z, E, g)
+    ref_idx = gold["idx"].astype(np.int64)
+    cls = classify_index_mismatches(z, E, got["idx"], ref_idx, pair_dist=oracle.pair_dist)
+    assert cls["real"] == 0, cls
+    assert cls["mismatch"] <= int(gold["ref_tie_rows"]) + int(gold["ref_ne_fp64"]) + 2, cls
+    bad = np.nonzero(got["idx"] != ref_idx)[0]
+    assert abs(got["loss"] - float(gold["loss"])) <= 1e-5 * abs(float(gold["loss"])) + 1e-12
+    # z_q shape / strides exactly as the reference returned them
+    assert tuple(got["z_q"].shape) == tuple(gold["zq_shape"])
+    assert tuple(got["z_q"].stride()) == tuple(gold["zq_strides"])
+    assert got["z_q"].dtype == torch.float32 and got["z_q"].grad_fn is not None
+    keep = np.ones(got["zq_rows"].shape[0], bool)
+    keep[bad] = False
+    if "zq" in gold.files:
+        assert_close(got["zq_rows"][keep], gold["zq"][keep], "z_q vs reference")
+        if len(bad) == 0:
+            assert_close(got["grad_z"], gold["grad_z"], "grad_z vs reference")
+            assert_close(got["grad_E"], gold["grad_E"], "grad_E vs reference")
+    else:
+        for key, arr in (("zq", got["zq_rows"]), ("grad_z", got["grad_z"]), ("grad_E", got["grad_E"])):
+            if key != "zq" and len(bad):
+                continue
+            pos = sample_positions(arr.size, spec["seed"])
+            vals = arr.reshape(-1)[pos]
+            refv = gold[key + "_samples"]
+            if key == "zq":
+                m = ~np.isin(pos // D, bad)
+                vals, refv = vals[m], refv[m]
+            err = float(np.abs(vals.astype(np.float64) - refv).max() / max(float(gold[key + "_absmax"]), 1e-30))
+            assert err <= 1e-5, f"{key}: {err:.3e}"
+
+
+def test_tokeniser_mode_matches_forward(vq, oracle):
+    spec = CASES["cfg2s_init"]
+    z, E, _ = make_inputs(spec)
+    dev = torch.device("cuda:0")
+    cb = vq.CodeBook(spec["K"], spec["D"]).to(dev)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(torch.from_numpy(E))
+        zt = torch.from_numpy(z).to(dev)
+        idx_tok = cb.encode_indices(zt)
+        none_q, idx_kw, none_l = cb(zt, indices_only=True)
+        z_q, idx_fwd, loss = cb(zt)                      # no_grad full forward (what encode_to_z gets)
+    assert none_q is None and none_l is None
+    ref = oracle.forward(z, E)
+    assert np.array_equal(idx_tok.cpu().numpy(), ref["idx"])
+    assert torch.equal(idx_tok, idx_kw) and torch.equal(idx_tok, idx_fwd)
+    assert z_q.grad_fn is None and not loss.requires_grad
+
+
+def test_margin_bound_and_operands(vq):
+    """The rigorous error bound behind the candidate margin holds on hardware (incl. tensor-core accumulation)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "tools", "gpu_diag.py")], capture_output=True, text=True,
+                         timeout=600)
+    assert res.returncode == 0 and "DIAG OK" in res.stdout, res.stdout[-3000:] + res.stderr[-2000:]
+
+
+def test_module_contract(vq):
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    cb = vq.CodeBook(num_codebook_vectors=512, latent_dim=256, beta=0.25).to(dev)
+    assert list(cb.state_dict().keys()) == ["codebook.weight"]
+    assert isinstance(cb.codebook, torch.nn.Embedding) and cb.codebook.weight.shape == (512, 256)
+    assert float(cb.codebook.weight.abs().max()) <= 1.0 / 512
+    z = torch.randn(2, 256, 4, 4, device=dev, requires_grad=True)
+    z_q, idx, loss = cb(z)
+    assert z_q.shape == (2, 256, 4, 4) and z_q.stride() == (4 * 4 * 256, 1, 4 * 256, 256)
+    assert idx.shape == (32,) and idx.dtype == torch.int64 and loss.dim() == 0 and loss.dtype == torch.float32
+    # straight-through: d(sum z_q)/dz == 1 (+ loss term), codebook gets only the beta term
+    (z_q.sum() + loss).backward()
+    e = cb.codebook.weight.detach()[idx].reshape(2, 4, 4, 256).permute(0, 3, 1, 2)
+    exp_gz = 1.0 + 2.0 * (z.detach() - e) / z.numel()
+    assert rel_err(z.grad.cpu().numpy(), exp_gz.cpu().numpy()) < 1e-6
+    exp_gE = torch.zeros_like(cb.codebook.weight)
+    exp_gE.index_add_(0, idx, (0.25 * 2.0 * (e - z.detach()) / z.numel()).permute(0, 2, 3, 1).reshape(-1, 256))
+    assert rel_err(cb.codebook.weight.grad.cpu().numpy(), exp_gE.cpu().numpy()) < 1e-5
+
+    # derived state follows in-place weight updates (optimizer.step) and load_state_dict
+    opt = torch.optim.SGD(cb.parameters(), lr=10.0)
+    opt.step()
+    with torch.no_grad():
+        _, idx2, _ = cb(z.detach())
+        d = (z.detach().permute(0, 2, 3, 1).reshape(-1, 256)[:, None, :] - cb.codebook.weight[None]).pow(2).sum(-1)
+        assert (d.gather(1, idx2[:, None]).squeeze(1) <= d.min(dim=1).values * (1 + 1e-5) + 1e-6).all()
+    sd = {"codebook.weight": torch.randn(512, 256)}
+    cb.load_state_dict(sd)
+    with torch.no_grad():
+        _, idx3, _ = cb(z.detach())
+        d = (z.detach().permute(0, 2, 3, 1).reshape(-1, 256)[:, None, :] - cb.codebook.weight[None]).pow(2).sum(-1)
+        assert torch.equal(idx3, d.argmin(1)) or (d.gather(1, idx3[:, None]).squeeze(1) <= d.min(1).values * (1 + 1e-5)).all()
+
+    # frozen codebook (stage-2 models freeze the VQVAE, vqvae.py:103-104): grad only to z
+    for p in cb.parameters():
+        p.requires_grad_(False)
+    cb.zero_grad(set_to_none=True)
+    z2 = torch.randn(1, 256, 3, 5, device=dev, requires_grad=True)
+    zq2, _, l2 = cb(z2)
+    (zq2.sum() + l2).backward()
+    assert z2.grad is not None and cb.codebook.weight.grad is None
+
+    # stricter-than-reference input validation
+    with pytest.raises(ValueError):
+        cb(torch.randn(2, 128, 4, 4, device=dev))
+    with pytest.raises(ValueError):
+        cb(torch.randn(2, 256, device=dev))
+    with pytest.raises(RuntimeError):
+        cb(torch.randn(2, 256, 4, 4))
+    with pytest.raises(RuntimeError):
+        cb(torch.randn(2, 256, 4, 4, device=dev, dtype=torch.float64))
+
+
+def test_empty_and_noncontiguous_inputs(vq, oracle):
+    dev = torch.device("cuda:0")
+    cb = vq.CodeBook(64, 256).to(dev)
+    z_q, idx, loss = cb(torch.zeros(0, 256, 4, 4, device=dev))
+    assert z_q.shape == (0, 256, 4, 4) and idx.numel() == 0 and torch.isnan(loss)
+    # channels-last input (non-contiguous NCHW view)
+    spec = CASES["small_trained"]
+    z, E, _ = make_inputs(spec)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(torch.from_numpy(E))
+        zt = torch.from_numpy(z).to(dev).permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        assert not zt.is_contiguous()
+        _, idx, _ = cb(zt)
+    assert np.array_equal(idx.cpu().numpy(), oracle.forward(z, E)["idx"])
+
+
+def test_backward_gout_layouts(vq, oracle):
+    """Upstream gradient as NCHW-contiguous, channels-last and broadcast (stride 0) tensors."""
+    spec = CASES["ragged_trained"]
+    z, E, g = make_inputs(spec)
+    dev = torch.device("cuda:0")
+    cb = vq.CodeBook(spec["K"], spec["D"]).to(dev)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(torch.from_numpy(E))
+    ref = oracle.forward(z, E)
+    g_nchw = np.ascontiguousarray(np.transpose(g, (0, 3, 1, 2)))
+    gz_ref, gE_ref = oracle.backward(g_nchw, 0.5, z, ref["idx"], E)
+    for layout in ("nchw", "nhwc"):
+        zt = torch.from_numpy(z).to(dev).requires_grad_(True)
+        cb.zero_grad(set_to_none=True)
+        z_q, idx, loss = cb(zt)
+        gt = torch.from_numpy(g_nchw).to(dev)
+        if layout == "nhwc":
+            gt = gt.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+        torch.autograd.backward([z_q, loss], [gt, torch.tensor(0.5, device=dev)])
+        assert_close(zt.grad.cpu().numpy(), gz_ref, f"grad_z ({layout})")
+        assert_close(cb.codebook.weight.grad.cpu().numpy(), gE_ref, f"grad_E ({layout})")
+    # loss only (no upstream gradient on z_q), and z_q.sum() (broadcast ones)
+    zt = torch.from_numpy(z).to(dev).requires_grad_(True)
+    z_q, idx, loss = cb(zt)
+    loss.backward()
+    gz0, _ = oracle.backward(None, 1.0, z, ref["idx"], E)
+    assert_close(zt.grad.cpu().numpy(), gz0, "grad_z (loss only)")
+
+
+def test_embed_nchw(vq):
+    dev = torch.device("cuda:0")
+    W = torch.randn(300, 256, device=dev)
+    idx = torch.randint(0, 300, (3 * 5 * 7,), device=dev)
+    out = vq.vq_embed_nchw(idx, W, 3, 5, 7)
+    exp = W[idx].reshape(3, 5, 7, 256).permute(0, 3, 1, 2)
+    assert out.is_contiguous() and torch.equal(out, exp)
+
+
+@pytest.mark.parametrize("K,dist", [(16384, "init"), (16384, "trained"), (8192, "init")])
+def test_full_size_properties(K, dist, vq, oracle):
+    """BASELINE.json configs[2]/[3] at full size (B=256, 32x32 -> N=262144): size-independent properties plus an
+    oracle spot check on a row sample."""
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(1234)
+    B, D, H, W = 256, 256, 32, 32
+    N = B * H * W
+    if dist == "init":
+        E = (torch.rand(K, D, device=dev, generator=g) * 2 - 1) / K
+        z = torch.randn(B, D, H, W, device=dev, generator=g)
+    else:
+        E = torch.randn(K, D, device=dev, generator=g)
+        pick = torch.randint(0, K, (N,), device=dev, generator=g)
+        z = (E[pick] + 0.3 * torch.randn(N, D, device=dev, generator=g)).reshape(B, H, W, D).permute(0, 3, 1, 2).contiguous()
+    cb = vq.CodeBook(K, D).to(dev)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(E)
+    zt = z.clone().requires_grad_(True)
+    z_q, idx, loss = cb(zt)
+    gout = torch.randn(B, H, W, D, device=dev, generator=g).permute(0, 3, 1, 2)
+    (loss + (z_q * gout).sum()).backward()
+    hist = cb.last_histogram
+    stats = cb.stats_dict()
+    assert int(hist.sum()) == N and torch.equal(hist, torch.bincount(idx, minlength=K))
+    assert int(idx.min()) >= 0 and int(idx.max()) < K
+    assert stats["fallback_rows"] <= N // 1000, stats
+    zrows = z.permute(0, 2, 3, 1).reshape(N, D)
+    e = E[idx]
+    # loss identity (1 + beta) * mean((e - z)^2)
+    exp_loss = 1.25 * float(((e - zrows).double() ** 2).mean())
+    assert abs(float(loss) - exp_loss) <= 1e-5 * exp_loss
+    # z_q value and straight-through gradient identities
+    assert torch.equal(z_q.permute(0, 2, 3, 1).reshape(N, D), zrows + (e - zrows))
+    exp_gz = gout + (2.0 / (N * D)) * (z - e.reshape(B, H, W, D).permute(0, 3, 1, 2))
+    assert rel_err(zt.grad[:8].cpu().numpy(), exp_gz[:8].cpu().numpy()) <= 1e-5
+    # codebook gradient: column sums equal beta * 2/(ND) * sum(e - z)  (linearity), and rows of unused codes are zero
+    gE = cb.codebook.weight.grad
+    exp_colsum = (0.25 * 2.0 / (N * D)) * (e - zrows).double().sum(0)
+    assert rel_err(gE.double().sum(0).cpu().numpy(), exp_colsum.cpu().numpy()) <= 1e-4
+    assert float(gE[hist == 0].abs().max() if (hist == 0).any() else 0.0) == 0.0
+    if dist == "trained":
+        assert float((idx == pick).double().mean()) > 0.999      # the planted code wins
+    # idempotence: quantising the chosen codes returns codes at distance 0 from them
+    with torch.no_grad():
+        sub = e[:4096].reshape(4, 32, 32, D).permute(0, 3, 1, 2).contiguous()
+        idx2 = cb.encode_indices(sub)
+        assert torch.equal(E[idx2], e[:4096])
+    # oracle spot check: 1024 sampled rows, full K
+    rows = torch.randperm(N, device=dev, generator=g)[:1024].sort().values
+    zs = zrows[rows].reshape(1024, 1, 1, D).permute(0, 3, 1, 2).contiguous().cpu().numpy()
+    ref = oracle.forward(zs, E.cpu().numpy(), want_zq=False)
+    assert np.array_equal(idx[rows].cpu().numpy(), ref["idx"])

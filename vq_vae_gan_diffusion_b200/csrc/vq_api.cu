@@ -1,0 +1,387 @@
+// vq_api.cu -- C-ABI entry points of libvq_b200.so (declared in include/vq_b200.h).
+//
+// Host side only: argument checks, workspace carving, TMA descriptor encoding and kernel launches.  Nothing here
+// allocates device memory or synchronises; every launch goes to the caller's stream.  There is no CPU fallback:
+// on anything but an sm_100 device the compute entry points return VQ_E_DEVICE.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/vq_b200.h"
+#include "vq_argmin_sm100.cuh"
+#include "vq_backward.cuh"
+#include "vq_common.cuh"
+#include "vq_prep.cuh"
+#include "vq_select.cuh"
+
+#define VQ_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define VQ_CUDA(expr)                                                                            \
+    do {                                                                                         \
+        cudaError_t e_ = (expr);                                                                 \
+        if (e_ != cudaSuccess) return fail((int)e_, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define VQ_LAUNCH_CHECK(name)                                                                    \
+    do {                                                                                         \
+        cudaError_t e_ = cudaGetLastError();                                                     \
+        if (e_ != cudaSuccess) return fail((int)e_, "launch of %s failed: %s", name, cudaGetErrorString(e_)); \
+        g_launches++;                                                                            \
+    } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// ---- per-device info (SM count, capability), cached
+struct DevInfo { int sms = 0; int cc = 0; bool attrs_set = false; };
+DevInfo g_dev[64];
+std::mutex g_mu;
+
+int device_info(DevInfo** out) {
+    int dev = 0;
+    VQ_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(VQ_E_DEVICE, "device ordinal %d out of range", dev);
+    std::lock_guard<std::mutex> lk(g_mu);
+    DevInfo& d = g_dev[dev];
+    if (d.sms == 0) {
+        int major = 0, minor = 0, sms = 0;
+        VQ_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+        VQ_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+        VQ_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        d.cc = major * 10 + minor;
+        d.sms = sms;
+    }
+    if (d.cc != 100)
+        return fail(VQ_E_DEVICE, "vq_b200 kernels are built for sm_100a only; current device is sm_%d (no fallback)", d.cc);
+    if (!d.attrs_set) {
+        VQ_CUDA(cudaFuncSetAttribute(vq::vq_argmin_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)vq::kGemmSmemBytes));
+        VQ_CUDA(cudaFuncSetAttribute(vq::vq_argmin_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)vq::kGemmSmemBytes));
+        VQ_CUDA(cudaFuncSetAttribute(vq::vq_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(2 * vq::kD * (vq::kSelRows + 1) * sizeof(float))));
+        d.attrs_set = true;
+    }
+    *out = &d;
+    return VQ_OK;
+}
+
+// ---- TMA descriptors.  cuTensorMapEncodeTiled is resolved through the runtime so the library has no link-time
+// dependency on libcuda (it must load on the GPU-less build box).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+int get_encode(EncodeTiledFn* out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess)
+            return fail(VQ_E_DEVICE, "cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    *out = g_encode;
+    return VQ_OK;
+}
+
+// (rows, 256) fp16 row-major matrix, box = (box_rows, 64 elements = 128 bytes), SWIZZLE_128B
+int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int box_rows) {
+    EncodeTiledFn enc;
+    int rc = get_encode(&enc);
+    if (rc != VQ_OK) return rc;
+    cuuint64_t dims[2] = {(cuuint64_t)vq::kD, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)vq::kD * 2};
+    cuuint32_t box[2] = {(cuuint32_t)vq::kDChunk, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VQ_E_INVALID, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return VQ_OK;
+}
+
+// ---- workspace layout
+struct Workspace {
+    __half* z_h;            // (N_pad, D)
+    float* z2;              // (N)
+    float* z_inv_scale;     // (N)
+    int32_t* out_cnt;       // (N)
+    int32_t* out_q;         // (N, kOutCap)
+    double* loss_partial;   // (ceil(N/32))
+    unsigned int* blocks_done;   // (1) + padding; zeroed by vq_forward
+    unsigned long long* stats;   // (VQ_STAT_COUNT) internal copy when the caller passes none
+    size_t bytes;
+};
+
+Workspace carve(void* base, int64_t N) {
+    Workspace w;
+    const int64_t n_pad = round_up(N > 0 ? N : 1, vq::kRowTile);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        void* p = base ? static_cast<char*>(base) + off : nullptr;
+        off += (size_t)round_up((int64_t)bytes, 256);
+        return p;
+    };
+    w.z_h = static_cast<__half*>(take((size_t)n_pad * vq::kD * 2));
+    w.z2 = static_cast<float*>(take((size_t)n_pad * 4));
+    w.z_inv_scale = static_cast<float*>(take((size_t)n_pad * 4));
+    w.out_cnt = static_cast<int32_t*>(take((size_t)n_pad * 4));
+    w.out_q = static_cast<int32_t*>(take((size_t)n_pad * vq::kOutCap * 4));
+    w.loss_partial = static_cast<double*>(take((size_t)(n_pad / vq::kSelRows) * 8));
+    w.blocks_done = static_cast<unsigned int*>(take(256));
+    w.stats = static_cast<unsigned long long*>(take(256));
+    w.bytes = off;
+    return w;
+}
+
+int check_common(const void* z, int64_t B, int64_t HW, int D, int K) {
+    if (D != vq::kD) return fail(VQ_E_UNSUPPORTED, "latent_dim D=%d is not supported (kernels are specialised for D=256)", D);
+    if (K < 1) return fail(VQ_E_UNSUPPORTED, "K=%d", K);
+    if (B < 0 || HW < 0) return fail(VQ_E_INVALID, "negative shape B=%lld HW=%lld", (long long)B, (long long)HW);
+    if (B * HW >= (int64_t)1 << 31) return fail(VQ_E_UNSUPPORTED, "N=%lld latents exceed 2^31", (long long)(B * HW));
+    if (B * HW > 0 && z == nullptr) return fail(VQ_E_INVALID, "null z pointer");
+    return VQ_OK;
+}
+
+// shared front half of vq_argmin / vq_forward / vq_debug_scores: prep z + GEMM with fused candidate argmin
+int run_gemm(const float* z, int64_t N, int64_t HW, const void* E_h, const float* e2, const float* cb, int K,
+             const Workspace& w, float* dbg_scores, cudaStream_t st) {
+    DevInfo* dev;
+    int rc = device_info(&dev);
+    if (rc != VQ_OK) return rc;
+    const int64_t n_pad = round_up(N, vq::kRowTile);
+    const int k_pad = vq_padded_codes(K);
+
+    vq::vq_prep_z_kernel<<<(unsigned)(n_pad / vq::kSelRows), vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2,
+                                                                                        w.z_inv_scale);
+    VQ_LAUNCH_CHECK("vq_prep_z_kernel");
+
+    CUtensorMap tm_z, tm_e;
+    rc = make_tmap(&tm_z, w.z_h, n_pad, vq::kRowTile);
+    if (rc != VQ_OK) return rc;
+    rc = make_tmap(&tm_e, E_h, k_pad, vq::kCodeTile);
+    if (rc != VQ_OK) return rc;
+
+    vq::GemmParams gp;
+    gp.e2 = e2;
+    gp.cb = cb;
+    gp.z2 = w.z2;
+    gp.z_inv_scale = w.z_inv_scale;
+    gp.N = N;
+    gp.k_tiles = k_pad / vq::kCodeTile;
+    gp.row_tiles = (int)(n_pad / vq::kRowTile);
+    gp.out_cnt = w.out_cnt;
+    gp.out_q = w.out_q;
+    gp.dbg_scores = dbg_scores;
+    const int grid = gp.row_tiles < dev->sms ? gp.row_tiles : dev->sms;
+    if (dbg_scores)
+        vq::vq_argmin_gemm_kernel<true><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(tm_z, tm_e, gp);
+    else
+        vq::vq_argmin_gemm_kernel<false><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(tm_z, tm_e, gp);
+    VQ_LAUNCH_CHECK("vq_argmin_gemm_kernel");
+    return VQ_OK;
+}
+
+int check_ws(void* ws, size_t ws_bytes, int64_t N, Workspace* w) {
+    *w = carve(ws, N);
+    if (ws == nullptr) return fail(VQ_E_INVALID, "null workspace");
+    if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(VQ_E_INVALID, "workspace must be 256-byte aligned");
+    if (ws_bytes < w->bytes)
+        return fail(VQ_E_WORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, w->bytes);
+    return VQ_OK;
+}
+
+}  // namespace
+
+VQ_EXPORT int vq_abi_version(void) { return 1; }
+VQ_EXPORT const char* vq_last_error(void) { return g_err; }
+VQ_EXPORT int vq_last_launch_count(void) { return g_launches; }
+
+VQ_EXPORT int vq_device_check(void) {
+    DevInfo* d;
+    return device_info(&d);
+}
+
+VQ_EXPORT int vq_padded_codes(int K) { return (int)round_up(K > 0 ? K : 1, vq::kCodeTile); }
+
+VQ_EXPORT int vq_workspace_bytes(int64_t N, int K, int D, size_t* out) {
+    if (out == nullptr) return fail(VQ_E_INVALID, "null out pointer");
+    if (D != vq::kD) return fail(VQ_E_UNSUPPORTED, "latent_dim D=%d is not supported (D must be 256)", D);
+    if (N < 0 || K < 1) return fail(VQ_E_INVALID, "bad shape N=%lld K=%d", (long long)N, K);
+    *out = carve(nullptr, N).bytes;
+    return VQ_OK;
+}
+
+VQ_EXPORT int vq_prepare_codebook(const float* E, int K, int D, void* E_h, float* e_norm2, float* cb_scalars,
+                                  vq_stream_t stream) {
+    g_launches = 0;
+    if (D != vq::kD) return fail(VQ_E_UNSUPPORTED, "latent_dim D=%d is not supported (D must be 256)", D);
+    if (K < 1) return fail(VQ_E_UNSUPPORTED, "K=%d", K);
+    if (!E || !E_h || !e_norm2 || !cb_scalars) return fail(VQ_E_INVALID, "null pointer");
+    DevInfo* dev;
+    int rc = device_info(&dev);
+    if (rc != VQ_OK) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const int k_pad = vq_padded_codes(K);
+    VQ_CUDA(cudaMemsetAsync(cb_scalars, 0, 4 * sizeof(float), st));
+    vq::vq_codebook_norms_kernel<<<k_pad / vq::kSelRows, vq::kPrepThreads, 0, st>>>(E, K, k_pad, e_norm2, cb_scalars);
+    VQ_LAUNCH_CHECK("vq_codebook_norms_kernel");
+    vq::vq_codebook_convert_kernel<<<k_pad / vq::kSelRows, vq::kPrepThreads, 0, st>>>(E, K, k_pad,
+                                                                                      static_cast<__half*>(E_h), cb_scalars);
+    VQ_LAUNCH_CHECK("vq_codebook_convert_kernel");
+    return VQ_OK;
+}
+
+static int forward_impl(bool training, const float* z, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
+                        const float* e2, const float* cb, int K, float beta, float* zq, int64_t* idx, float* loss,
+                        int64_t* hist, unsigned long long* stats, void* ws, size_t ws_bytes, vq_stream_t stream) {
+    g_launches = 0;
+    int rc = check_common(z, B, HW, D, K);
+    if (rc != VQ_OK) return rc;
+    if (!E || !E_h || !e2 || !cb) return fail(VQ_E_INVALID, "null codebook pointer");
+    const int64_t N = B * HW;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (stats) VQ_CUDA(cudaMemsetAsync(stats, 0, VQ_STAT_COUNT * sizeof(unsigned long long), st));
+    if (training && hist) VQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)K * sizeof(int64_t), st));
+    if (N == 0) {
+        // torch.mean over an empty tensor is NaN (codebook.py:96)
+        if (training && loss) {
+            const float nanv = __builtin_nanf("");
+            VQ_CUDA(cudaMemcpyAsync(loss, &nanv, sizeof(float), cudaMemcpyHostToDevice, st));
+        }
+        return VQ_OK;
+    }
+    if (!idx) return fail(VQ_E_INVALID, "null idx pointer");
+    if (training && (!zq || !loss)) return fail(VQ_E_INVALID, "null zq/loss pointer");
+    Workspace w;
+    rc = check_ws(ws, ws_bytes, N, &w);
+    if (rc != VQ_OK) return rc;
+
+    rc = run_gemm(z, N, HW, E_h, e2, cb, K, w, nullptr, st);
+    if (rc != VQ_OK) return rc;
+
+    vq::SelectParams sp;
+    sp.z = z; sp.E = E; sp.e2 = e2; sp.z2 = w.z2;
+    sp.out_cnt = w.out_cnt; sp.out_q = w.out_q;
+    sp.N = N; sp.HW = HW; sp.K = K; sp.beta = beta;
+    sp.idx = idx; sp.zq = zq;
+    sp.hist = reinterpret_cast<unsigned long long*>(hist);
+    sp.loss_partial = w.loss_partial; sp.blocks_done = w.blocks_done; sp.loss = loss;
+    sp.stats = stats;
+    const unsigned grid = (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows);
+    if (training) {
+        VQ_CUDA(cudaMemsetAsync(w.blocks_done, 0, sizeof(unsigned int), st));
+        vq::vq_select_kernel<true><<<grid, vq::kSelThreads, 0, st>>>(sp);
+    } else {
+        vq::vq_select_kernel<false><<<grid, vq::kSelThreads, 0, st>>>(sp);
+    }
+    VQ_LAUNCH_CHECK("vq_select_kernel");
+    return VQ_OK;
+}
+
+VQ_EXPORT int vq_argmin(const float* z_nchw, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
+                        const float* e_norm2, const float* cb_scalars, int K, int64_t* idx, unsigned long long* stats,
+                        void* workspace, size_t workspace_bytes, vq_stream_t stream) {
+    return forward_impl(false, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, 0.0f, nullptr, idx, nullptr, nullptr,
+                        stats, workspace, workspace_bytes, stream);
+}
+
+VQ_EXPORT int vq_forward(const float* z_nchw, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
+                         const float* e_norm2, const float* cb_scalars, int K, float beta, float* zq_nhwc, int64_t* idx,
+                         float* loss, int64_t* hist, unsigned long long* stats, void* workspace, size_t workspace_bytes,
+                         vq_stream_t stream) {
+    return forward_impl(true, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, beta, zq_nhwc, idx, loss, hist, stats,
+                        workspace, workspace_bytes, stream);
+}
+
+VQ_EXPORT int vq_debug_scores(const float* z_nchw, int64_t B, int64_t HW, int D, const void* E_h, const float* e_norm2,
+                              const float* cb_scalars, int K, float* scores, void* workspace, size_t workspace_bytes,
+                              vq_stream_t stream) {
+    g_launches = 0;
+    int rc = check_common(z_nchw, B, HW, D, K);
+    if (rc != VQ_OK) return rc;
+    if (!E_h || !e_norm2 || !cb_scalars || !scores) return fail(VQ_E_INVALID, "null pointer");
+    const int64_t N = B * HW;
+    if (N == 0) return VQ_OK;
+    Workspace w;
+    rc = check_ws(workspace, workspace_bytes, N, &w);
+    if (rc != VQ_OK) return rc;
+    return run_gemm(z_nchw, N, HW, E_h, e_norm2, cb_scalars, K, w, scores, reinterpret_cast<cudaStream_t>(stream));
+}
+
+VQ_EXPORT int vq_backward(const float* gout, const int64_t* gout_strides, float g_loss, const float* g_loss_dev,
+                          const float* z_nchw,
+                          const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K, float beta,
+                          int64_t n_global, float* grad_z, float* grad_E, vq_stream_t stream) {
+    g_launches = 0;
+    int rc = check_common(z_nchw, B, HW, D, K);
+    if (rc != VQ_OK) return rc;
+    const int64_t N = B * HW;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (grad_E) VQ_CUDA(cudaMemsetAsync(grad_E, 0, (size_t)K * D * sizeof(float), st));
+    if (N == 0 || (!grad_z && !grad_E)) return VQ_OK;
+    if (!idx || !E) return fail(VQ_E_INVALID, "null idx/E pointer");
+    if (gout && !gout_strides) return fail(VQ_E_INVALID, "gout given without strides");
+    DevInfo* dev;
+    rc = device_info(&dev);
+    if (rc != VQ_OK) return rc;
+    if (n_global <= 0) n_global = N;
+
+    vq::BackwardParams bp;
+    bp.gout = gout;
+    bp.gs_b = gout ? gout_strides[0] : 0;
+    bp.gs_d = gout ? gout_strides[1] : 0;
+    bp.gs_hw = gout ? gout_strides[2] : 0;
+    bp.z = z_nchw; bp.idx = idx; bp.E = E;
+    bp.N = N; bp.HW = HW; bp.K = K;
+    bp.g_loss = g_loss;
+    bp.g_loss_dev = g_loss_dev;
+    bp.inv_nd = 1.0 / ((double)n_global * (double)D);
+    bp.beta = beta;
+    bp.grad_z = grad_z; bp.grad_E = grad_E;
+    const unsigned grid = (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows);
+    const size_t tile = (size_t)vq::kD * (vq::kSelRows + 1) * sizeof(float);
+    // channels-last upstream gradient (d contiguous; the layout of the z_q we returned) is staged through shared
+    // memory so its reads are coalesced too; any other layout is read in place, lanes over hw.
+    const bool cl = gout != nullptr && bp.gs_d == 1 && !(bp.gs_hw == 1 && HW > 1);
+    if (cl) vq::vq_backward_kernel<true><<<grid, vq::kBwdThreads, 2 * tile, st>>>(bp);
+    else    vq::vq_backward_kernel<false><<<grid, vq::kBwdThreads, tile, st>>>(bp);
+    VQ_LAUNCH_CHECK("vq_backward_kernel");
+    return VQ_OK;
+}
+
+VQ_EXPORT int vq_embed_nchw(const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K, float* out,
+                            vq_stream_t stream) {
+    g_launches = 0;
+    if (D != vq::kD) return fail(VQ_E_UNSUPPORTED, "latent_dim D=%d is not supported (D must be 256)", D);
+    if (B < 0 || HW < 0 || K < 1) return fail(VQ_E_INVALID, "bad shape");
+    const int64_t N = B * HW;
+    if (N == 0) return VQ_OK;
+    if (!idx || !E || !out) return fail(VQ_E_INVALID, "null pointer");
+    DevInfo* dev;
+    int rc = device_info(&dev);
+    if (rc != VQ_OK) return rc;
+    const unsigned grid = (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows);
+    vq::vq_embed_nchw_kernel<<<grid, vq::kBwdThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(idx, E, N, HW, K, out);
+    VQ_LAUNCH_CHECK("vq_embed_nchw_kernel");
+    return VQ_OK;
+}

@@ -1,0 +1,61 @@
+// vq_common.cuh -- constants and small device helpers shared by all kernels of the VQ hot path.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace vq {
+
+constexpr int kD = 256;             // latent_dim of every reference config (configs/*.yml: latent_channels 256)
+constexpr int kRowTile = 128;       // latents per GEMM tile  (UMMA M, one TMEM lane per latent)
+constexpr int kCodeTile = 256;      // codes per GEMM tile    (UMMA N)
+constexpr int kDChunk = 64;         // 16-bit elements per 128-byte swizzle row
+constexpr int kNumDChunks = kD / kDChunk;
+constexpr int kQuad = 4;            // candidate granularity: 4 consecutive codes
+constexpr int kRingCap = 16;        // per-row candidate ring (shared memory) inside the GEMM epilogue
+constexpr int kOutCap = 8;          // surviving candidate quads handed to the exact stage, per row
+constexpr int kSelRows = 32;        // latents per CTA in the fp32 kernels (prep / select / backward)
+
+// Tensor-core operands are fp16 scaled by exact powers of two so that the largest magnitude lands in
+// [2^14, 2^15): per latent row for z, per tensor for the codebook.  exponent_of() returns ex with |x| < 2^ex.
+constexpr int kOperandTopExp = 15;
+__device__ __forceinline__ int exponent_of(float maxabs) {
+    int ex;
+    (void)frexpf(maxabs, &ex);                 // maxabs = m * 2^ex, m in [0.5, 1)
+    if (!(maxabs > 0.0f) || !(maxabs < INFINITY)) ex = 0;   // zero / inf / nan rows: scale 1 (handled downstream)
+    return max(-100, min(100, ex));
+}
+__device__ __forceinline__ float pow2f(int e) { return __int_as_float((e + 127) << 23); }   // -126 <= e <= 127
+
+// Canonical-order dot product pieces (oracle/vq_oracle.c: vqo_dot): partial j sums the terms d == j (mod 4)
+// in ascending d with one fma each; the result is (p0 + p1) + (p2 + p3).
+__device__ __forceinline__ float combine4(float p) {
+    // p holds partial j on lane (4*g + j); returns (p0+p1)+(p2+p3) on all four lanes (fp add is commutative).
+    float q = __fadd_rn(p, __shfl_xor_sync(0xffffffffu, p, 1));
+    return __fadd_rn(q, __shfl_xor_sync(0xffffffffu, q, 2));
+}
+
+// Reference distance formula in fp32, codebook.py:70-79: fl( fl(|z|^2 + |e|^2) - fl(2 * dot) ).
+__device__ __forceinline__ float ref_distance(float z2, float e2, float dot) {
+    return __fsub_rn(__fadd_rn(z2, e2), __fmul_rn(2.0f, dot));
+}
+
+// Rigorous bound eps on | (score_approx + |z|^2) - d_oracle | valid for every code of a row, and the candidate
+// margin derived from it.  score_approx = e2[k] - 2 * (fp16(z) . fp16(e_k)) with fp32 accumulation in the tensor
+// core; d_oracle = ref_distance() with a canonical-order fp32 dot.  With a = |z| * max_k |e_k| (Cauchy-Schwarz
+// bound of sum |z_d e_d|) and r = |z|^2 + max|e|^2 + 2a (bounds every intermediate magnitude):
+//   fp16 rounding of both operands (unit roundoff 2^-11, + subnormal slack)   2 (2^-10 + 2^-22 + 2^-35) a
+//   tensor-core fp32 accumulation over D = 256 products                       <= 2^-13 a (budget, checked on HW)
+//   oracle's own fp32 dot                                                     2 D 2^-24 a = 2^-15 a
+//   fp32 roundings of the two formulas and of the threshold add               <= 2^-22 r
+//   => eps <= (2^-9 + 2^-12) a + 2^-22 r
+// The oracle's argmin k* then satisfies score[k*] <= min_k score + 2 eps.  See DESIGN.md "candidate margin".
+__device__ __forceinline__ float candidate_margin(float z2, float e2max) {
+    const float a = sqrtf(z2) * sqrtf(e2max) * 1.000001f;
+    const float r = z2 + e2max + 2.0f * a;
+    const float eps = a * (0.001953125f + 0.000244140625f) + r * 2.384185791015625e-07f;
+    return 2.0f * eps * 1.0625f + 1e-37f;
+}
+
+}  // namespace vq
