@@ -1,0 +1,387 @@
+#!/usr/bin/env python
+"""bench.py -- VQ latents/sec (fwd+bwd) of the CodeBook hot path on B200, with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg4]
+
+A "step" is one pass of the hot path over one batch of synthetic latents: CodeBook forward (operand prep,
+tcgen05 distance GEMM with fused candidate argmin, exact fp32 select + gather + loss + histogram) followed by the
+backward (straight-through grad_z + scatter-add grad_E), plus -- for N > 1 -- the codebook-gradient all-reduce.
+The derived codebook state is rebuilt every step, as it is in training where the optimizer changes the weight.
+
+Default workload = BASELINE.json configs[3] ("cfg4"): K=16384, D=256, batch 256 of 32x32 latents PER GPU (weak
+scaling), the configuration the north-star target (>= 60 % of tensor-pipe peak on the fused distance-argmin) is
+quoted on.  Inputs (268 MB of z + 268 MB of g_out per GPU) exceed the 126 MB L2, so no L2 flush is needed.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same step driven from pinned host
+buffers (H2D of z and g_out, D2H of loss and indices inside the timed region), `roofline` = the distance-GEMM kernel
+against the measured bf16 tensor peak, `cpu_baseline` = the numpy/BLAS port of the reference timed on this box's
+host cores on a bounded row sample.
+
+--impl reference: the reference arm.  The reference is pure Python/PyTorch and cannot travel to the GPU box, so this
+arm times the oracle port (oracle/vq_oracle.py: forward_blas/backward_blas, same ATen-style op sequence, BLAS
+sgemm on all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B per GPU, H, W, K, mode)     D = 256 everywhere
+    "cfg1": dict(B=200, H=1, W=1, K=1024, desc="configs[0] VQGAN small, 28x28 -> 1x1 latents, K=1024"),
+    "cfg2": dict(B=64, H=16, W=16, K=1024, desc="configs[1] taming-default K=1024, batch 64 of 16x16 latents"),
+    "cfg3": dict(B=256, H=32, W=32, K=8192, desc="configs[2] VQVAE K=8192, batch 256 of 32x32 latents"),
+    "cfg4": dict(B=256, H=32, W=32, K=16384, desc="configs[3] large codebook K=16384, batch 256 of 32x32 latents per GPU"),
+    "cfg5": dict(B=64, H=32, W=32, K=2048, desc="configs[4] tokeniser path, 512x512 -> 32x32 latents, indices only", tokenizer=True),
+}
+D = 256
+BETA = 0.25
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(bf16_tflops=float(p["bf16_tflops"]), bf16_tflops_sustained=float(p.get("bf16_tflops_sustained", 0)),
+                    hbm_gbs=float(p["hbm_gbs"]), source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        try:
+            proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                     "--format=csv,noheader,nounits", "-lms", "100"],
+                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        try:
+            while not self._stop.is_set():
+                line = proc.stdout.readline()
+                if not line:
+                    break
+                self.samples.append((time.time(), line.strip()))
+        finally:
+            proc.terminate()
+
+    def start(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t:
+            self._t.join(timeout=2)
+
+    def summary(self, t0: float, t1: float):
+        import statistics
+        mhz, reasons, mx = [], set(), None
+        for ts, line in self.samples:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                mx = float(parts[1])
+                if t0 - 0.05 <= ts <= t1 + 0.15:
+                    mhz.append(float(parts[0]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(mhz)}
+
+
+def make_latents(torch, dev, B, H, W, K, distribution, seed):
+    g = torch.Generator(device=dev).manual_seed(seed)
+    N = B * H * W
+    if distribution == "init":
+        torch.manual_seed(0)
+        E = (torch.rand(K, D, device=dev, generator=g) * 2 - 1) / K          # U(-1/K, 1/K), codebook.py:43-45
+        z = torch.randn(B, D, H, W, device=dev, generator=g)
+    else:
+        E = torch.randn(K, D, device=dev, generator=g)
+        pick = torch.randint(0, K, (N,), device=dev, generator=g)
+        z = (E[pick] + 0.3 * torch.randn(N, D, device=dev, generator=g)).reshape(B, H, W, D).permute(0, 3, 1, 2).contiguous()
+    g_out = torch.randn(B, H, W, D, device=dev, generator=g).permute(0, 3, 1, 2)   # NHWC memory, like z_q itself
+    return E, z, g_out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_port_step(z_np, E_np, g_np, tokenizer):
+    """One fwd(+bwd) of the torch-CPU port of the reference (oracle/vq_oracle.py: torch_cpu_step): the same ATen op
+    sequence the reference issues, on all host threads."""
+    import torch
+    from oracle.vq_oracle import torch_cpu_step
+    z = torch.from_numpy(z_np)
+    E = torch.from_numpy(E_np)
+    g = None if tokenizer else torch.from_numpy(g_np).view(z.shape[0], 1, 1, -1).permute(0, 3, 1, 2)
+    return torch_cpu_step(z, E, g, BETA, indices_only=tokenizer)[1]
+
+
+def time_cpu_port(wl, distribution, sample_rows, budget_s, reps_min=1):
+    """numpy/BLAS port of the reference on a bounded row sample of the workload -> latents/s."""
+    import numpy as np
+    K = wl["K"]
+    rng = np.random.default_rng(1234)
+    n = min(sample_rows, wl["B"] * wl["H"] * wl["W"])
+    if distribution == "init":
+        E = rng.uniform(-1.0 / K, 1.0 / K, size=(K, D)).astype(np.float32)
+        zf = rng.standard_normal((n, D), dtype=np.float32)
+    else:
+        E = rng.standard_normal((K, D), dtype=np.float32)
+        zf = E[rng.integers(0, K, size=n)] + np.float32(0.3) * rng.standard_normal((n, D), dtype=np.float32)
+    z = np.ascontiguousarray(zf.reshape(n, 1, 1, D).transpose(0, 3, 1, 2))
+    g = rng.standard_normal((n, D), dtype=np.float32)
+    tok = bool(wl.get("tokenizer"))
+    cpu_port_step(z[:256], E, g[:256], tok)                 # warm-up (BLAS thread pool, page faults)
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < reps_min or (time.perf_counter() - t_start < budget_s and len(times) < 20):
+        t0 = time.perf_counter()
+        cpu_port_step(z, E, g, tok)
+        times.append(time.perf_counter() - t0)
+    best = min(times)
+    return n / best, best, n, len(times)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    sample = 16384 if wl["K"] >= 8192 else 65536
+    n_total = wl["B"] * wl["H"] * wl["W"]
+    sample = min(sample, n_total)
+    # warm-up passes then K timed steps, each a bounded sample
+    for _ in range(max(args.warmup, 1)):
+        time_cpu_port(wl, args.distribution, min(sample, 2048), 0.0)
+    per_step = []
+    for _ in range(args.steps):
+        v, t, n, _ = time_cpu_port(wl, args.distribution, sample, 0.0)
+        per_step.append(t)
+    ms = 1e3 * sum(per_step) / len(per_step)
+    value = sample / (ms / 1e3)
+    line = {
+        "impl": "reference", "metric": "vq_latents_per_sec_fwd_bwd" if not wl.get("tokenizer") else "vq_latents_per_sec_tokenize",
+        "value": value, "unit": "latents/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": args.workload + ": " + wl["desc"], "K": wl["K"], "D": D,
+                                        "distribution": args.distribution, "sample_rows_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "latents/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} of {n_total} latents per step (rows are independent), torch-CPU port of codebook.py (same ATen ops)"},
+        "e2e": {"value": value, "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg4", choices=list(WORKLOADS))
+    ap.add_argument("--distribution", default="init", choices=["init", "trained"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import vq_vae_gan_diffusion_b200 as vq
+    from vq_vae_gan_diffusion_b200 import _native
+    from vq_vae_gan_diffusion_b200.dist import DataParallelVQ
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device: the VQ hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _native.check(_native.lib().vq_device_check(), "vq_device_check")
+
+    wl = WORKLOADS[args.workload]
+    B, H, W, K = wl["B"], wl["H"], wl["W"], wl["K"]
+    tok = bool(wl.get("tokenizer"))
+    N = B * H * W
+    E, z, g_out = make_latents(torch, dev, B, H, W, K, args.distribution, 1234 + rank)
+    cb = vq.CodeBook(K, D, BETA).to(dev)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(E)
+    dp = DataParallelVQ(cb) if world > 1 else None
+    z_req = z.clone().requires_grad_(not tok)
+    g_loss = torch.ones((), device=dev)
+
+    def step(zin, gin):
+        cb._derived_key = None                      # the optimizer changed the weight: rebuild derived state
+        if tok:
+            return cb.encode_indices(zin), None
+        cb.codebook.weight.grad = None
+        zin.grad = None
+        z_q, idx, loss = (dp or cb)(zin)
+        torch.autograd.backward([z_q, loss], [gin, g_loss])
+        if dp is not None:
+            dp.wait()
+        return idx, loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(z_req, g_out)
+    barrier()
+    launches = 2 + cb._launches + (0 if tok else cb._launches_bwd)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    _native.profile_enable(True)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_wall0 = time.time()
+    ev0.record()
+    for _ in range(args.steps):
+        step(z_req, g_out)
+    ev1.record()
+    barrier()
+    t_wall1 = time.time()
+    gemm_ms = _native.profile_collect()
+    _native.profile_enable(False)
+    ms_total = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    if rank == 0:
+        time.sleep(0.15)
+        sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
+    stats = cb.stats_dict()
+
+    # ---- end to end: host buffers in, loss + indices out, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        z_host = z.cpu().pin_memory()
+        # upstream gradient in channels-last memory (the layout of z_q, which is what flows back from post_quant_conv)
+        g_host = None if tok else g_out.permute(0, 2, 3, 1).contiguous().cpu().pin_memory()
+        idx_host = torch.empty(N, dtype=torch.int64).pin_memory()
+        loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+        z_dev = torch.empty_like(z).requires_grad_(not tok)
+        g_dev_nhwc = None if tok else torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
+        g_dev = None if tok else g_dev_nhwc.permute(0, 3, 1, 2)
+
+        def e2e_step():
+            with torch.no_grad():
+                z_dev.copy_(z_host, non_blocking=True)
+                if not tok:
+                    g_dev_nhwc.copy_(g_host, non_blocking=True)
+            idx, loss = step(z_dev, g_dev)
+            idx_host.copy_(idx, non_blocking=True)
+            if loss is not None:
+                loss_host.copy_(loss.detach(), non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_e2e = max(3, min(args.steps, 10))
+        e0.record()
+        for _ in range(n_e2e):
+            e2e_step()
+        e1.record()
+        barrier()
+        te = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ms_e2e = float(te.item()) / n_e2e
+        h2d = z_host.numel() * 4 + (0 if tok else g_host.numel() * 4)
+        d2h = N * 8 + (0 if tok else 4)
+        e2e = {"value": N * world / (ms_e2e / 1e3), "unit": "latents/s", "ms_per_step": ms_e2e,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = load_peaks()
+    gemm_avg = sum(gemm_ms) / len(gemm_ms) if gemm_ms else None
+    flops = 2.0 * N * K * D                                         # algorithmic: the z.E^T contraction only
+    roofline = None
+    if gemm_avg:
+        ach = flops / (gemm_avg / 1e3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "vq_argmin_gemm_kernel", "achieved": ach, "peak": peaks["bf16_tflops"],
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+                    "kernel_ms": gemm_avg, "kernel_share_of_step": gemm_avg / ms_step,
+                    "peak_source": peaks["source"] + ", burst", "peak_sustained": peaks["bf16_tflops_sustained"],
+                    "frac_of_sustained": ach / peaks["bf16_tflops_sustained"] if peaks["bf16_tflops_sustained"] else None,
+                    "algorithmic_flops_per_launch": flops}
+        # whole-step HBM view (fwd+bwd algorithmic bytes per latent: 5136 B; tokeniser: 1032 B) for context
+        bytes_per_latent = 1032 if tok else 5136
+        roofline["step_hbm_gbs_algorithmic"] = N * bytes_per_latent / (ms_step / 1e3) / 1e9
+        roofline["hbm_peak_gbs"] = peaks["hbm_gbs"]
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        sample = 16384 if K >= 8192 else min(N, 65536)
+        v, tbest, n, reps = time_cpu_port(wl, args.distribution, sample, budget_s=12.0)
+        cpu_baseline = {"value": v, "unit": "latents/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"best of {reps} passes over {n} of {N} latents (rows independent; torch-CPU port "
+                                  f"of codebook.py fwd{'' if tok else '+bwd'}), {tbest*1e3:.0f} ms per pass"}
+
+    line = {
+        "metric": "vq_latents_per_sec_fwd_bwd" if not tok else "vq_latents_per_sec_tokenize",
+        "value": N * world / (ms_step / 1e3), "unit": "latents/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (distance GEMM operands f16, f32 accumulate; exact f32 re-rank)",
+        "data": "synthetic",
+        "config": {"workload": args.workload + ": " + wl["desc"], "K": K, "D": D, "latents_per_gpu": N,
+                   "distribution": args.distribution, "l2": "inputs (2 x 268 MB per GPU) larger than the 126 MB L2"
+                   if N * D * 4 > 130e6 else "inputs smaller than L2, no flush (launch-latency-bound workload)",
+                   "parallelism": f"dp{world} (batch-sharded latents, replicated codebook, grad_E all-reduce)"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "select_stats_last_step": stats,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

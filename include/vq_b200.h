@@ -120,6 +120,14 @@ int vq_embed_nchw(const int64_t* idx, const float* E, int64_t B, int64_t HW, int
 /* Number of kernel launches the last call on this thread enqueued (for bench.py's gpu_launches). */
 int vq_last_launch_count(void);
 
+/*
+ * Timing of the distance-GEMM kernel for the roofline report.  vq_profile_enable(1) makes vq_argmin / vq_forward
+ * calls ON THIS THREAD bracket that kernel with CUDA events on the caller's stream (up to 512 calls);
+ * vq_profile_collect, called after the caller synchronised, returns the elapsed milliseconds per call and resets.
+ */
+int vq_profile_enable(int on);
+int vq_profile_collect(float* ms_host, int cap, int* n_host);
+
 /* Debug: dump the approximate (fp16 tensor-core) scores e2[k] - 2 z.e for all (n, k); N*K_pad floats. */
 int vq_debug_scores(const float* z_nchw, int64_t B, int64_t HW, int D,
                     const void* E_h, const float* e_norm2, const float* cb_scalars, int K,

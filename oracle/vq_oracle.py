@@ -175,3 +175,34 @@ def backward_blas(gout_nhwc, g_loss: float, z: np.ndarray, idx: np.ndarray, E: n
     grad_E = np.zeros_like(E)
     np.add.at(grad_E, idx, (-np.float32(beta) * coef) * diff)
     return grad_z, grad_E
+
+
+# ----------------------------------------------------------------------------------------------
+# torch-CPU port (what bench.py times as the CPU baseline): the same ATen op sequence the reference
+# issues -- one sgemm, elementwise passes over the (N, K) matrix, argmin, embedding lookup, two means,
+# autograd backward -- so that its cost on the host cores is the reference's cost.
+# ----------------------------------------------------------------------------------------------
+
+def torch_cpu_step(z, E, g_out=None, beta: float = 0.25, indices_only: bool = False):
+    """z (B, D, H, W) and E (K, D) CPU torch tensors.  Returns (z_q NCHW view, idx, loss, grad_z, grad_E);
+    the last two are None without g_out.  Restates codebook.py:62-111 + loss.backward()."""
+    import torch
+    D = E.shape[1]
+    need_grad = g_out is not None and not indices_only
+    zin = z.detach().clone().requires_grad_(need_grad)
+    W = E.detach().clone().requires_grad_(need_grad)
+    with torch.set_grad_enabled(need_grad):
+        rows = zin.permute(0, 2, 3, 1).contiguous()                  # codebook.py:62
+        flat = rows.view(-1, D)                                      # codebook.py:64-66
+        dist = (flat ** 2).sum(dim=1, keepdim=True) + (W ** 2).sum(dim=1) - 2 * torch.matmul(flat, W.t())   # :70-79
+        idx = torch.argmin(dist, dim=1)                              # codebook.py:82
+        if indices_only:
+            return None, idx, None, None, None
+        q = torch.nn.functional.embedding(idx, W).view(rows.shape)   # codebook.py:85
+        loss = torch.mean((q.detach() - rows) ** 2 + beta * torch.mean((q - rows.detach()) ** 2))   # :96-103
+        q = rows + (q - rows).detach()                               # codebook.py:106
+        z_q = q.permute(0, 3, 1, 2)                                  # codebook.py:109
+    if not need_grad:
+        return z_q, idx, loss, None, None
+    (loss + (z_q * g_out).sum()).backward()
+    return z_q.detach(), idx, loss.detach(), zin.grad, W.grad

@@ -74,6 +74,8 @@ _SIGNATURES = {
     "vq_forward": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vq_backward": (_int, [_vp, ctypes.POINTER(_i64), _f32, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _f32, _i64, _vp, _vp, _vp]),
     "vq_embed_nchw": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _vp]),
+    "vq_profile_enable": (_int, [_int]),
+    "vq_profile_collect": (_int, [ctypes.POINTER(_f32), _int, ctypes.POINTER(_int)]),
     "vq_debug_scores": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _int, _vp, _vp, _sz, _vp]),
 }
 
@@ -103,6 +105,18 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = lib().vq_last_error().decode(errors="replace")
         raise VQNativeError(f"{what} failed (rc={rc}): {msg}")
+
+
+def profile_enable(on: bool) -> None:
+    check(lib().vq_profile_enable(1 if on else 0), "vq_profile_enable")
+
+
+def profile_collect():
+    """Milliseconds of the distance-GEMM kernel for each profiled call since the last collect (host sync)."""
+    buf = (_f32 * 512)()
+    n = _int(0)
+    check(lib().vq_profile_collect(buf, 512, ctypes.byref(n)), "vq_profile_collect")
+    return [float(buf[i]) for i in range(n.value)]
 
 
 def padded_codes(K: int) -> int:

@@ -48,6 +48,17 @@ int fail(int code, const char* fmt, ...) {
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// ---- optional timing of the distance-GEMM kernel (bench.py's roofline): a ring of event pairs recorded on the
+// caller's stream around that one launch; read back after the caller has synchronised.
+constexpr int kProfCap = 512;
+struct Prof {
+    bool on = false;
+    int n = 0;
+    cudaEvent_t ev[kProfCap][2];
+    int created = 0;
+};
+thread_local Prof g_prof;
+
 // ---- per-device info (SM count, capability), cached
 struct DevInfo { int sms = 0; int cc = 0; bool attrs_set = false; };
 DevInfo g_dev[64];
@@ -193,11 +204,24 @@ int run_gemm(const float* z, int64_t N, int64_t HW, const void* E_h, const float
     gp.out_q = w.out_q;
     gp.dbg_scores = dbg_scores;
     const int grid = gp.row_tiles < dev->sms ? gp.row_tiles : dev->sms;
+    const bool prof = g_prof.on && g_prof.n < kProfCap;
+    if (prof) {
+        while (g_prof.created <= g_prof.n) {
+            VQ_CUDA(cudaEventCreate(&g_prof.ev[g_prof.created][0]));
+            VQ_CUDA(cudaEventCreate(&g_prof.ev[g_prof.created][1]));
+            g_prof.created++;
+        }
+        VQ_CUDA(cudaEventRecord(g_prof.ev[g_prof.n][0], st));
+    }
     if (dbg_scores)
         vq::vq_argmin_gemm_kernel<true><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(tm_z, tm_e, gp);
     else
         vq::vq_argmin_gemm_kernel<false><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(tm_z, tm_e, gp);
     VQ_LAUNCH_CHECK("vq_argmin_gemm_kernel");
+    if (prof) {
+        VQ_CUDA(cudaEventRecord(g_prof.ev[g_prof.n][1], st));
+        g_prof.n++;
+    }
     return VQ_OK;
 }
 
@@ -215,6 +239,24 @@ int check_ws(void* ws, size_t ws_bytes, int64_t N, Workspace* w) {
 VQ_EXPORT int vq_abi_version(void) { return 1; }
 VQ_EXPORT const char* vq_last_error(void) { return g_err; }
 VQ_EXPORT int vq_last_launch_count(void) { return g_launches; }
+
+VQ_EXPORT int vq_profile_enable(int on) {
+    g_prof.on = on != 0;
+    g_prof.n = 0;
+    return VQ_OK;
+}
+
+VQ_EXPORT int vq_profile_collect(float* ms_host, int cap, int* n_host) {
+    if (!ms_host || !n_host) return fail(VQ_E_INVALID, "null pointer");
+    int n = g_prof.n < cap ? g_prof.n : cap;
+    for (int i = 0; i < n; i++) {
+        VQ_CUDA(cudaEventSynchronize(g_prof.ev[i][1]));
+        VQ_CUDA(cudaEventElapsedTime(&ms_host[i], g_prof.ev[i][0], g_prof.ev[i][1]));
+    }
+    *n_host = n;
+    g_prof.n = 0;
+    return VQ_OK;
+}
 
 VQ_EXPORT int vq_device_check(void) {
     DevInfo* d;
