@@ -135,10 +135,12 @@ struct Workspace {
     __half* z_h;            // (N_pad, D)
     float* z2;              // (N)
     float* z_inv_scale;     // (N)
-    int32_t* out_cnt;       // (N)
-    int32_t* out_q;         // (N, kOutCap)
+    int32_t* out_cnt;       // (N, 2) one count per epilogue group
+    uint32_t* out_q;        // (N, kOutCap) candidate entries (chunk << 8 | quad mask)
     double* loss_partial;   // (ceil(N/32))
     unsigned int* blocks_done;   // (1) + padding; zeroed by vq_forward
+    int32_t* fb_rows;            // (2N) rows needing the exact full scan (a row may be listed once per group)
+    int32_t* fb_count;           // (1)
     unsigned long long* stats;   // (VQ_STAT_COUNT) internal copy when the caller passes none
     size_t bytes;
 };
@@ -155,10 +157,12 @@ Workspace carve(void* base, int64_t N) {
     w.z_h = static_cast<__half*>(take((size_t)n_pad * vq::kD * 2));
     w.z2 = static_cast<float*>(take((size_t)n_pad * 4));
     w.z_inv_scale = static_cast<float*>(take((size_t)n_pad * 4));
-    w.out_cnt = static_cast<int32_t*>(take((size_t)n_pad * 4));
-    w.out_q = static_cast<int32_t*>(take((size_t)n_pad * vq::kOutCap * 4));
+    w.out_cnt = static_cast<int32_t*>(take((size_t)n_pad * 2 * 4));
+    w.out_q = static_cast<uint32_t*>(take((size_t)n_pad * vq::kOutCap * 4));
     w.loss_partial = static_cast<double*>(take((size_t)(n_pad / vq::kSelRows) * 8));
     w.blocks_done = static_cast<unsigned int*>(take(256));
+    w.fb_rows = static_cast<int32_t*>(take((size_t)n_pad * 2 * 4));
+    w.fb_count = static_cast<int32_t*>(take(256));
     w.stats = static_cast<unsigned long long*>(take(256));
     w.bytes = off;
     return w;
@@ -202,8 +206,11 @@ int run_gemm(const float* z, int64_t N, int64_t HW, const void* E_h, const float
     gp.row_tiles = (int)(n_pad / vq::kRowTile);
     gp.out_cnt = w.out_cnt;
     gp.out_q = w.out_q;
+    gp.fb_rows = w.fb_rows;
+    gp.fb_count = w.fb_count;
     gp.dbg_scores = dbg_scores;
     const int grid = gp.row_tiles < dev->sms ? gp.row_tiles : dev->sms;
+    VQ_CUDA(cudaMemsetAsync(w.fb_count, 0, sizeof(int32_t), st));
     const bool prof = g_prof.on && g_prof.n < kProfCap;
     if (prof) {
         while (g_prof.created <= g_prof.n) {
@@ -320,6 +327,21 @@ static int forward_impl(bool training, const float* z, int64_t B, int64_t HW, in
 
     rc = run_gemm(z, N, HW, E_h, e2, cb, K, w, nullptr, st);
     if (rc != VQ_OK) return rc;
+
+    {   // rows whose candidate list overflowed (rare): exact scan, one CTA per row; a no-op when the worklist is empty
+        vq::FallbackParams fp;
+        fp.z = z; fp.E = E; fp.e2 = e2; fp.z2 = w.z2;
+        fp.fb_rows = w.fb_rows; fp.fb_count = w.fb_count;
+        fp.HW = HW; fp.K = K;
+        fp.out_cnt = w.out_cnt; fp.out_q = w.out_q; fp.stats = stats;
+        DevInfo* dev;
+        rc = device_info(&dev);
+        if (rc != VQ_OK) return rc;
+        const int64_t want = (N + 31) / 32;
+        const unsigned fgrid = (unsigned)(want < 2 * dev->sms ? want : 2 * dev->sms);
+        vq::vq_fallback_kernel<<<fgrid, vq::kFbThreads, 0, st>>>(fp);
+        VQ_LAUNCH_CHECK("vq_fallback_kernel");
+    }
 
     vq::SelectParams sp;
     sp.z = z; sp.E = E; sp.e2 = e2; sp.z2 = w.z2;

@@ -2,19 +2,26 @@
 //
 // Computes, for every latent row n, the approximate scores  s[n,k] = |e_k|^2 - 2 * fp16(z_n) . fp16(e_k)
 // (the k-dependent part of codebook.py:70-79) on the 5th-gen tensor cores and reduces them IN THE EPILOGUE to a
-// short list of candidate "quads" (4 consecutive codes) whose minimum is within margin[n] of the row minimum,
-// so the N x K distance matrix never leaves the SM.  vq_select_kernel (vq_select.cuh) recomputes the distances of
-// the surviving quads exactly in fp32 and takes the first minimum.
+// short list of candidate entries -- a 32-code chunk plus a bit mask of its "quads" (4 consecutive codes) whose
+// minimum is within margin[n] of the running row minimum -- so the N x K distance matrix never leaves the SM.
+// vq_select_kernel (vq_select.cuh) recomputes the distances of the surviving quads exactly in fp32 and takes the
+// first minimum.
 //
-// CTA = 6 warps, persistent over row tiles (128 latents each):
+// CTA = 10 warps, persistent over row tiles (128 latents each):
 //   warp 0      TMA producer: A = z tile (4 chunks of [128 x 64] fp16, SWIZZLE_128B) once per row tile,
-//               B = codebook tile ([256 codes x 64] fp16 per stage) through a 4-stage ring.
+//               B = codebook tile ([256 codes x 64] fp16 per stage) through a 4-stage ring, and the |e|^2 slice of
+//               every code tile (1 KiB bulk copy) into a double buffer.
 //   warp 1      TMEM allocator + MMA issuer: per code tile 16 x tcgen05.mma (M128 N256 K16) into one of two
-//               256-column fp32 accumulators (double buffered: the epilogue of tile j overlaps the MMAs of j+1).
-//   warps 2..5  epilogue: thread <-> TMEM lane <-> latent row; tcgen05.ld 32 columns at a time, one FFMA per
-//               element for the score, a 3-input-min tree per 32-column chunk whose 4-wide partial minima are the
-//               quad minima, and a short slow path that pushes quads within the running threshold into a
-//               per-row ring in shared memory.
+//               256-column fp32 accumulators (the epilogue of tile j overlaps the MMAs of tile j+1).
+//   warps 2..5  epilogue group 0: columns [0, 128) of every accumulator tile
+//   warps 6..9  epilogue group 1: columns [128, 256)
+//               thread <-> TMEM lane <-> latent row; tcgen05.ld 32 columns at a time (prefetched one chunk ahead,
+//               like the |e|^2 values), one FFMA per element for the score, a 3-input-min tree per chunk whose
+//               4-wide partial minima are the quad minima, and a short slow path that pushes (chunk, quad mask)
+//               into a per-(row, group) ring in shared memory.  The accumulator buffer is released as soon as its
+//               last columns are in registers.  A buffer cycles MMA -> drain -> MMA, so the tensor pipe stays busy
+//               only while drain + hand-off latency <= one MMA tile time; splitting the columns over two warps per
+//               SM sub-partition halves the drain and lets the two hide each other's latencies.
 #pragma once
 #include <cuda.h>
 
@@ -24,25 +31,37 @@
 namespace vq {
 
 constexpr int kStagesB = 4;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiGroups = 2;
+constexpr int kGroupCols = kCodeTile / kEpiGroups;           // 128 accumulator columns per epilogue group
+constexpr int kChunk = 32;                                   // codes per tcgen05.ld / per candidate entry
+constexpr int kGemmThreads = 64 + kEpiGroups * 128;         // 320
 constexpr uint32_t kBytesAChunk = kRowTile * kDChunk * 2;    // 16 KiB
 constexpr uint32_t kBytesBStage = kCodeTile * kDChunk * 2;   // 32 KiB
+constexpr uint32_t kBytesE2Tile = kCodeTile * 4;             // 1 KiB
 constexpr uint32_t kTmemCols = 512;
+constexpr int kOutPerGroup = kOutCap / kEpiGroups;           // candidate entries a group may hand over per row
+constexpr int kMaxQuadsPerGroup = 16;                        // ... and quads (the exact stage lists <= 32 per row)
 
 struct GemmSmem {
     alignas(1024) uint8_t a[kNumDChunks][kBytesAChunk];      // 64 KiB
     alignas(1024) uint8_t b[kStagesB][kBytesBStage];         // 128 KiB
-    int32_t ring_q[kRingCap][kRowTile];                      // 8 KiB   quad ids,    [slot][row]: conflict-free
-    float ring_s[kRingCap][kRowTile];                        // 8 KiB   quad minima
+    alignas(16) float e2s[2][kCodeTile];                     // 2 KiB   |e|^2 of the code tile in accumulator buffer b
+    uint32_t ring_q[kEpiGroups][kRingCap][kRowTile];         // 12 KiB  (chunk << 8 | quad mask), [slot][row]
+    float ring_s[kEpiGroups][kRingCap][kRowTile];            // 12 KiB  chunk minima
+    float m_part[2][kEpiGroups][kRowTile];                   // 2 KiB   per-group running minima (double buffered)
+    int32_t c_part[2][kEpiGroups][kRowTile];                 // 2 KiB   per-group push counts
     alignas(8) uint64_t a_full[kNumDChunks];
     uint64_t a_empty[kNumDChunks];
     uint64_t b_full[kStagesB];
     uint64_t b_empty[kStagesB];
     uint64_t t_full[2];
     uint64_t t_empty[2];
+    uint64_t e2_full[2];
+    uint64_t e2_empty[2];
     uint32_t tmem_base;
 };
 constexpr size_t kGemmSmemBytes = sizeof(GemmSmem) + 1024;   // + slack for manual 1024 B alignment
+static_assert(kGemmSmemBytes <= 232448, "exceeds the 227 KiB of shared memory a CTA can opt into");
 
 struct GemmParams {
     const float* e2;           // (K_pad) |e_k|^2, +inf on pad rows
@@ -52,8 +71,10 @@ struct GemmParams {
     int64_t N;
     int k_tiles;               // K_pad / 256
     int row_tiles;             // N_pad / 128
-    int32_t* out_cnt;          // (N)  surviving quads, or -1: list unusable -> exact scan of the whole row
-    int32_t* out_q;            // (N, kOutCap) quad ids (code / 4)
+    int32_t* out_cnt;          // (N, 2) candidate entries per epilogue group, or -1: list unusable -> exact row scan
+    uint32_t* out_q;           // (N, kOutCap) entries (chunk << 8 | quad mask); group g owns slots [g*8, g*8+8)
+    int32_t* fb_rows;          // (2N) worklist of the rows flagged -1 (for vq_fallback_kernel)
+    int32_t* fb_count;         // (1)  its length, zeroed before launch
     float* dbg_scores;         // (N, K_pad) or null
 };
 
@@ -61,6 +82,10 @@ __device__ __forceinline__ float min3(float a, float b, float c) {
     float r;
     asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
     return r;
+}
+
+__device__ __forceinline__ void epi_barrier() {               // the 256 epilogue threads only
+    asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
 template <bool kDebugScores>
@@ -78,7 +103,12 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
         tma_prefetch_desc(&tmap_e);
         for (int i = 0; i < kNumDChunks; i++) { mbar_init(&s.a_full[i], 1); mbar_init(&s.a_empty[i], 1); }
         for (int i = 0; i < kStagesB; i++) { mbar_init(&s.b_full[i], 1); mbar_init(&s.b_empty[i], 1); }
-        for (int i = 0; i < 2; i++) { mbar_init(&s.t_full[i], 1); mbar_init(&s.t_empty[i], 4); }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&s.t_full[i], 1);
+            mbar_init(&s.t_empty[i], 4 * kEpiGroups);
+            mbar_init(&s.e2_full[i], 1);
+            mbar_init(&s.e2_empty[i], 4 * kEpiGroups);
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -95,7 +125,7 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
         if (lane == 0) {
             const uint64_t pol_keep = policy_evict_last();    // codebook tiles are re-read by every CTA
             const uint64_t pol_stream = policy_evict_first(); // z tiles are read exactly once
-            uint32_t stage = 0, b_phase = 0, a_phase = 0;
+            uint32_t stage = 0, b_phase = 0, a_phase = 0, buf = 0, e_phase = 0;
             for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x) {
                 for (int kt = 0; kt < p.k_tiles; kt++) {
                     for (int dc = 0; dc < kNumDChunks; dc++) {
@@ -109,6 +139,13 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                         tma_load_2d_hint(s.b[stage], &tmap_e, dc * kDChunk, kt * kCodeTile, &s.b_full[stage], pol_keep);
                         if (++stage == kStagesB) { stage = 0; b_phase ^= 1; }
                     }
+                    // |e|^2 of this code tile, issued after its operand stages so that waiting for the epilogue to
+                    // release the buffer (two tiles back) never delays an operand load
+                    mbar_wait(&s.e2_empty[buf], e_phase ^ 1);
+                    mbar_expect_tx(&s.e2_full[buf], kBytesE2Tile);
+                    bulk_load_1d(s.e2s[buf], p.e2 + (int64_t)kt * kCodeTile, kBytesE2Tile, &s.e2_full[buf]);
+                    buf ^= 1;
+                    if (buf == 0) e_phase ^= 1;
                 }
                 a_phase ^= 1;
             }
@@ -146,14 +183,21 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        const int grp = (warp - 2) >> 2;                    // which half of the accumulator columns
         const int quarter = warp & 3;                       // TMEM lanes [32*quarter, 32*quarter + 32)
         const int trow = quarter * 32 + lane;               // row inside the tile == TMEM lane
-        const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+        const uint32_t col0 = grp * kGroupCols;
+        const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + col0;
+        const uint32_t e2_sa[2] = {smem_u32(&s.e2s[0][col0]), smem_u32(&s.e2s[1][col0])};
+        const uint32_t ring_q_sa = smem_u32(&s.ring_q[grp][0][trow]);
+        const uint32_t ring_s_sa = smem_u32(&s.ring_s[grp][0][trow]);
+        constexpr uint32_t kSlotStride = kRowTile * 4;
         const float e2max = __ldg(p.cb + 0);
         const float e_inv = __ldg(p.cb + 2);
-        uint32_t buf = 0, t_phase = 0;
-        for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x) {
+        uint32_t buf = 0, phase = 0;
+        int rti = 0;
+        for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x, rti++) {
             const int64_t row = (int64_t)rt * kRowTile + trow;
             const bool row_ok = row < p.N;
             const float margin = candidate_margin(row_ok ? __ldg(p.z2 + row) : 0.0f, e2max);
@@ -161,84 +205,104 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
             const float cscale = -2.0f * (row_ok ? __ldg(p.z_inv_scale + row) : 1.0f) * e_inv;
             float m_run = INFINITY, thr = INFINITY, lost_min = INFINITY;
             int cnt = 0;
+            uint32_t slot_off = 0;
 
             for (int kt = 0; kt < p.k_tiles; kt++) {
-                mbar_wait(&s.t_full[buf], t_phase);
+                mbar_wait(&s.t_full[buf], phase);
+                mbar_wait(&s.e2_full[buf], phase);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + lane_addr + buf * kCodeTile;
-                const float4* e2v = reinterpret_cast<const float4*>(p.e2 + (int64_t)kt * kCodeTile);
+                const uint32_t taddr = t_lane + buf * kCodeTile;
+                const uint32_t e2a = e2_sa[buf];
 
                 uint32_t acc[2][32];
+                float4 ev[2][8];
                 tmem_ld32(taddr, acc[0]);
-#pragma unroll 1
-                for (int c2 = 0; c2 < kCodeTile / 64; c2++) {
 #pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int c = 2 * c2 + h;
-                        tmem_ld_wait();
-                        // prefetch the next 32 columns into the other register buffer while this one is reduced
-                        if (c + 1 < kCodeTile / 32) tmem_ld32(taddr + (c + 1) * 32, acc[h ^ 1]);
-                        float sc[32];
+                for (int q = 0; q < 8; q++) ev[0][q] = lds128(e2a + q * 16);
 #pragma unroll
-                        for (int q = 0; q < 8; q++) {
-                            const float4 e = __ldg(e2v + c * 8 + q);
-                            sc[4 * q + 0] = __fmaf_rn(cscale, __uint_as_float(acc[h][4 * q + 0]), e.x);
-                            sc[4 * q + 1] = __fmaf_rn(cscale, __uint_as_float(acc[h][4 * q + 1]), e.y);
-                            sc[4 * q + 2] = __fmaf_rn(cscale, __uint_as_float(acc[h][4 * q + 2]), e.z);
-                            sc[4 * q + 3] = __fmaf_rn(cscale, __uint_as_float(acc[h][4 * q + 3]), e.w);
-                        }
-                        if (kDebugScores) {
-                            if (row_ok) {
-                                float* dst = p.dbg_scores + row * ((int64_t)p.k_tiles * kCodeTile) + kt * kCodeTile + c * 32;
+                for (int c = 0; c < kGroupCols / kChunk; c++) {
+                    const int h = c & 1;
+                    tmem_ld_wait();
+                    if (c + 1 < kGroupCols / kChunk) {
+                        // prefetch the next chunk (accumulators and |e|^2) while this one is reduced
+                        tmem_ld32(taddr + (c + 1) * kChunk, acc[h ^ 1]);
 #pragma unroll
-                                for (int i = 0; i < 32; i++) dst[i] = sc[i];
-                            }
-                        }
-                        // quad minima (4 consecutive codes) and the chunk minimum: 3-input min tree
-                        float m8[8];
-#pragma unroll
-                        for (int q = 0; q < 8; q++)
-                            m8[q] = fminf(min3(sc[4 * q], sc[4 * q + 1], sc[4 * q + 2]), sc[4 * q + 3]);
-                        const float cm = min3(min3(m8[0], m8[1], m8[2]), min3(m8[3], m8[4], m8[5]), fminf(m8[6], m8[7]));
-                        if (cm <= thr) {
-                            // slow path: this chunk holds a quad within the running threshold
-                            m_run = fminf(m_run, cm);
-                            thr = m_run + margin;
-                            const int qbase = (kt * kCodeTile + c * 32) / kQuad;
-#pragma unroll
-                            for (int q = 0; q < 8; q++) {
-                                if (m8[q] <= thr) {
-                                    const int slot = cnt & (kRingCap - 1);
-                                    if (cnt >= kRingCap) lost_min = fminf(lost_min, s.ring_s[slot][trow]);
-                                    s.ring_q[slot][trow] = qbase + q;
-                                    s.ring_s[slot][trow] = m8[q];
-                                    cnt++;
-                                }
-                            }
-                        }
+                        for (int q = 0; q < 8; q++) ev[h ^ 1][q] = lds128(e2a + (c + 1) * kChunk * 4 + q * 16);
+                    } else {
+                        // everything this warp needs from the buffer is in registers: release it to the MMA / TMA now
+                        tc_fence_before();
                         __syncwarp();
+                        if (lane == 0) {
+                            mbar_arrive(&s.t_empty[buf]);
+                            mbar_arrive(&s.e2_empty[buf]);
+                        }
                     }
+                    float sc[32];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) {
+                        sc[4 * q + 0] = __fmaf_rn(cscale, __uint_as_float(acc[h][4 * q + 0]), ev[h][q].x);
+                        sc[4 * q + 1] = __fmaf_rn(cscale, __uint_as_float(acc[h][4 * q + 1]), ev[h][q].y);
+                        sc[4 * q + 2] = __fmaf_rn(cscale, __uint_as_float(acc[h][4 * q + 2]), ev[h][q].z);
+                        sc[4 * q + 3] = __fmaf_rn(cscale, __uint_as_float(acc[h][4 * q + 3]), ev[h][q].w);
+                    }
+                    if (kDebugScores) {
+                        if (row_ok) {
+                            float* dst = p.dbg_scores + row * ((int64_t)p.k_tiles * kCodeTile) + kt * kCodeTile + col0 + c * kChunk;
+#pragma unroll
+                            for (int i = 0; i < 32; i++) dst[i] = sc[i];
+                        }
+                    }
+                    // quad minima (4 consecutive codes) and the chunk minimum: 3-input min tree
+                    float m8[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                        m8[q] = fminf(min3(sc[4 * q], sc[4 * q + 1], sc[4 * q + 2]), sc[4 * q + 3]);
+                    const float cm = min3(min3(m8[0], m8[1], m8[2]), min3(m8[3], m8[4], m8[5]), fminf(m8[6], m8[7]));
+                    if (cm <= thr) {
+                        // slow path: this chunk holds a quad within the running threshold -> one ring entry
+                        m_run = fminf(m_run, cm);
+                        thr = m_run + margin;
+                        uint32_t entry = (uint32_t)(kt * (kCodeTile / kChunk) + grp * (kGroupCols / kChunk) + c) << 8;
+#pragma unroll
+                        for (int q = 0; q < 8; q++) entry |= (m8[q] <= thr) ? (1u << q) : 0u;
+                        if (cnt >= kRingCap) lost_min = fminf(lost_min, lds_f32(ring_s_sa + slot_off));
+                        sts_u32(ring_q_sa + slot_off, entry);
+                        sts_f32(ring_s_sa + slot_off, cm);
+                        cnt++;
+                        slot_off = (slot_off + kSlotStride == kRingCap * kSlotStride) ? 0u : slot_off + kSlotStride;
+                    }
+                    __syncwarp();
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&s.t_empty[buf]);
                 buf ^= 1;
-                if (buf == 0) t_phase ^= 1;
+                if (buf == 0) phase ^= 1;
             }
 
-            // hand the quads that survive the FINAL threshold to the exact stage
+            // combine the two groups' running minima, then hand the entries that survive the FINAL threshold to the
+            // exact stage (each group filters its own ring into its half of the output slots)
+            const int pb = rti & 1;
+            s.m_part[pb][grp][trow] = m_run;
+            s.c_part[pb][grp][trow] = cnt;
+            epi_barrier();
+            const float m_fin = fminf(m_run, s.m_part[pb][grp ^ 1][trow]);
+            const int cnt_all = cnt + s.c_part[pb][grp ^ 1][trow];
             if (row_ok) {
-                int n_out = 0;
-                bool bad = (cnt == 0) || (lost_min <= thr);      // nothing recorded (NaN row) or a survivor was overwritten
+                const float thr_fin = m_fin + margin;
+                int n_out = 0, n_quads = 0;
+                // nothing recorded at all (NaN row: group 0 reports) or a possible survivor was overwritten
+                bool bad = (cnt_all == 0 && grp == 0) || (lost_min <= thr_fin);
                 const int live = min(cnt, kRingCap);
+                uint32_t* dst = p.out_q + row * kOutCap + grp * kOutPerGroup;
                 for (int i = 0; i < live && !bad; i++) {
-                    if (s.ring_s[i][trow] <= thr) {
-                        if (n_out < kOutCap) p.out_q[row * kOutCap + n_out] = s.ring_q[i][trow];
+                    if (lds_f32(ring_s_sa + i * kSlotStride) <= thr_fin) {
+                        const uint32_t entry = lds_u32(ring_q_sa + i * kSlotStride);
+                        n_quads += __popc(entry & 0xffu);
+                        if (n_out < kOutPerGroup && n_quads <= kMaxQuadsPerGroup) dst[n_out] = entry;
                         else bad = true;
                         n_out++;
                     }
                 }
-                p.out_cnt[row] = bad ? -1 : n_out;
+                p.out_cnt[row * kEpiGroups + grp] = bad ? -1 : n_out;
+                if (bad) p.fb_rows[atomicAdd(p.fb_count, 1)] = (int32_t)row;
             }
             __syncwarp();
         }

@@ -13,8 +13,8 @@ constexpr int kCodeTile = 256;      // codes per GEMM tile    (UMMA N)
 constexpr int kDChunk = 64;         // 16-bit elements per 128-byte swizzle row
 constexpr int kNumDChunks = kD / kDChunk;
 constexpr int kQuad = 4;            // candidate granularity: 4 consecutive codes
-constexpr int kRingCap = 16;        // per-row candidate ring (shared memory) inside the GEMM epilogue
-constexpr int kOutCap = 8;          // surviving candidate quads handed to the exact stage, per row
+constexpr int kRingCap = 12;        // candidate ring per (row, epilogue group) in shared memory inside the GEMM epilogue
+constexpr int kOutCap = 16;         // surviving candidate quads handed to the exact stage, per row (half per group)
 constexpr int kSelRows = 32;        // latents per CTA in the fp32 kernels (prep / select / backward)
 
 // Tensor-core operands are fp16 scaled by exact powers of two so that the largest magnitude lands in

@@ -1,27 +1,36 @@
-// vq_select.cuh -- exact fp32 decision + fused forward tail.
+// vq_select.cuh -- exact fp32 decision + fused forward tail, and the exact full-row fallback.
 //
 // vq_select_kernel<kForward>: one CTA = 32 latents (8 warps, 4 rows per warp).
 //   1. load the fp32 z tile once (coalesced along hw) into shared memory
-//   2. per row: recompute the distances of the candidate quads handed over by the GEMM epilogue with the
-//      reference's fp32 formula (codebook.py:70-79) in the oracle's canonical accumulation order and take the
-//      first minimum (torch.argmin semantics, codebook.py:82); out_cnt < 0 -> exact scan of the whole row
+//   2. expand the candidate entries (32-code chunk + quad mask) written by the GEMM epilogue into quads, then
+//      recompute the distance of every candidate code with the reference's fp32 formula (codebook.py:70-79) in
+//      the oracle's canonical accumulation order -- one thread per (row, code): a warp pass covers 4 rows x 8 codes,
+//      each thread streaming its code row with 128-bit loads into the four canonical partial sums -- and take the
+//      first minimum (torch.argmin semantics, codebook.py:82)
 //   3. kForward only: gather e = E[idx] (codebook.py:85), write z_q = fl(z + fl(e - z)) as NHWC rows
 //      (codebook.py:106-109), accumulate sum (e - z)^2 for the loss (codebook.py:96-103) and the usage histogram.
-// HBM traffic per latent: read z 4D (+ 36 B of candidates), write idx 8 (+ z_q 4D when kForward).
+// HBM traffic per latent: read z 4D (+ 72 B of candidates), write idx 8 (+ z_q 4D when kForward).
+//
+// vq_fallback_kernel: the (rare) rows whose candidate ring overflowed in the GEMM epilogue get an exact scan of the
+// whole codebook, one 1024-thread CTA per row, one thread per code; the winner is written back as a one-quad
+// candidate entry so vq_select_kernel finishes the row like any other.
 #pragma once
 #include "vq_common.cuh"
 
 namespace vq {
 
 constexpr int kSelThreads = 256;
+constexpr int kSelWarps = kSelThreads / 32;
+constexpr int kMaxQuads = 32;           // quads per row the exact stage evaluates (GEMM hands over <= 16 per group)
+constexpr int kFbThreads = 1024;
 
 struct SelectParams {
     const float* z;            // (B, D, HW) fp32
     const float* E;            // (K, D) fp32
     const float* e2;           // (K_pad)
     const float* z2;           // (N)
-    const int32_t* out_cnt;    // (N)
-    const int32_t* out_q;      // (N, kOutCap)
+    const int32_t* out_cnt;    // (N, 2)
+    const uint32_t* out_q;     // (N, kOutCap)
     int64_t N, HW;
     int K;
     float beta;
@@ -34,22 +43,30 @@ struct SelectParams {
     unsigned long long* stats; // (VQ_STAT_COUNT) or null
 };
 
-// lexicographic (distance, index) minimum across the warp -> first minimum
-__device__ __forceinline__ void warp_argmin(float& d, int& k) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const float d2 = __shfl_xor_sync(0xffffffffu, d, o);
-        const int k2 = __shfl_xor_sync(0xffffffffu, k, o);
-        if (d2 < d || (d2 == d && k2 < k)) { d = d2; k = k2; }
+// canonical-order distance of latent row (shared tile column r) to code k; one thread does the whole dot product
+__device__ __forceinline__ float exact_distance_tile(const float (*t)[kSelRows + 1], int r, const float* __restrict__ E,
+                                                     const float* __restrict__ e2, int k, float z2) {
+    const float4* e4 = reinterpret_cast<const float4*>(E + (int64_t)k * kD);
+    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+#pragma unroll 8
+    for (int q = 0; q < kD / 4; q++) {
+        const float4 e = __ldg(e4 + q);
+        p0 = __fmaf_rn(t[4 * q + 0][r], e.x, p0);
+        p1 = __fmaf_rn(t[4 * q + 1][r], e.y, p1);
+        p2 = __fmaf_rn(t[4 * q + 2][r], e.z, p2);
+        p3 = __fmaf_rn(t[4 * q + 3][r], e.w, p3);
     }
+    const float dot = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
+    return ref_distance(z2, __ldg(e2 + k), dot);
 }
 
 template <bool kForward>
 __global__ void __launch_bounds__(kSelThreads)
 vq_select_kernel(const SelectParams p) {
     __shared__ float t[kD][kSelRows + 1];
+    __shared__ int qlist[kSelWarps][4][kMaxQuads];
     __shared__ int idx_s[kSelRows];
-    __shared__ double red_s[kSelThreads / 32];
+    __shared__ double red_s[kSelWarps];
     __shared__ bool is_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -66,57 +83,81 @@ vq_select_kernel(const SelectParams p) {
             t[d][lane] = ok ? __ldg(src + (int64_t)d * p.HW) : 0.0f;
         }
     }
+
+    // 2a. expand this warp's candidate entries into quads (independent of the z tile)
+    int nq[4];
+    unsigned resolved_mask = 0;                               // rows decided by vq_fallback_kernel (stats counted there)
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const int64_t n = n0 + warp * 4 + rr;
+        nq[rr] = 0;
+        if (n >= p.N) continue;                               // warp-uniform
+        const int c0 = __ldg(p.out_cnt + 2 * n), c1 = __ldg(p.out_cnt + 2 * n + 1);
+        const bool resolved = (c0 == -2);
+        if (resolved) resolved_mask |= 1u << rr;
+        const int g = lane >> 3, i = lane & 7;                // slot = lane: group g owns slots [8g, 8g + 8)
+        const bool valid = resolved ? (lane == 0) : (lane < kOutCap && i < (g ? c1 : c0));
+        const uint32_t e = valid ? __ldg(p.out_q + n * kOutCap + lane) : 0u;
+        const int pc = __popc(e & 0xffu);
+        int incl = pc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        int pos = incl - pc;
+        uint32_t bits = e & 0xffu;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (pos < kMaxQuads) qlist[warp][rr][pos] = (int)(e >> 8) * 8 + b;
+            pos++;
+        }
+        nq[rr] = min(kMaxQuads, __shfl_sync(0xffffffffu, incl, 31));
+    }
     __syncthreads();
 
-    // 2. decide the index of rows 4*warp .. 4*warp+3.  lane = 4*g + j: code slot g of the pass, partial sum j.
-    const int j = lane & 3, g = lane >> 2;
-    unsigned long long st_tie = 0, st_rerank = 0, st_fallback = 0, st_cand = 0;
-    for (int rr = 0; rr < 4; rr++) {
+    // 2b. exact distances: lane = 8*rr + c -> row rr of this warp, code slot c (two quads per pass and row)
+    {
+        const int rr = lane >> 3, c = lane & 7;
         const int r = warp * 4 + rr;
         const int64_t n = n0 + r;
-        if (n >= p.N) break;                                  // warp-uniform
-        const float z2 = __ldg(p.z2 + n);
-        const int nq = __ldg(p.out_cnt + n);
-        const bool scan_all = (nq <= 0 || nq > kOutCap);
-        const int my_q = (!scan_all && lane < nq) ? __ldg(p.out_q + n * kOutCap + lane) : 0;
-        const int total = scan_all ? p.K : nq * kQuad;        // codes to evaluate (some may be >= K: skipped)
-
+        const bool row_ok = n < p.N;
+        const int my_nq = (rr == 0) ? nq[0] : (rr == 1) ? nq[1] : (rr == 2) ? nq[2] : nq[3];
+        const int max_nq = max(max(nq[0], nq[1]), max(nq[2], nq[3]));
+        const float z2 = row_ok ? __ldg(p.z2 + n) : 0.0f;
+        const unsigned seg = 0xffu << (rr * 8);
         float best_d = INFINITY;
         int best_k = 0x7fffffff, n_at_min = 0;
-        for (int base = 0; base < total; base += 8) {
-            const int slot = base + g;                        // code slot of this lane group
-            const int qsrc = __shfl_sync(0xffffffffu, my_q, (slot / kQuad) & 31);
-            int k = scan_all ? slot : qsrc * kQuad + (slot % kQuad);
-            if (slot >= total || k >= p.K) k = -1;
-            float acc = 0.0f;
-            if (k >= 0) {
-                const float* e = p.E + (int64_t)k * kD + j;
-#pragma unroll 8
-                for (int q = 0; q < kD / 4; q++) acc = __fmaf_rn(t[4 * q + j][r], __ldg(e + 4 * q), acc);
-            }
-            const float dot = combine4(acc);
-            const float dist = (k >= 0) ? ref_distance(z2, __ldg(p.e2 + k), dot) : INFINITY;
+        for (int base = 0; base < max_nq; base += 2) {
+            const int tq = base + (c >> 2);
+            int k = (tq < my_nq) ? qlist[warp][rr][tq] * kQuad + (c & 3) : -1;
+            if (k >= p.K) k = -1;                              // pad codes of the last chunk
+            float dist = INFINITY;
+            if (k >= 0) dist = exact_distance_tile(t, r, p.E, p.e2, k, z2);
+            // first minimum within the row's 8 lanes (lexicographic on (distance, index))
             float pd = dist;
             int pk = (k >= 0) ? k : 0x7fffffff;
-            warp_argmin(pd, pk);
-            const int eq = __popc(__ballot_sync(0xffffffffu, j == 0 && k >= 0 && dist == pd));
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                const float d2 = __shfl_xor_sync(0xffffffffu, pd, o);
+                const int k2 = __shfl_xor_sync(0xffffffffu, pk, o);
+                if (d2 < pd || (d2 == pd && k2 < pk)) { pd = d2; pk = k2; }
+            }
+            const int eq = __popc(__ballot_sync(0xffffffffu, k >= 0 && dist == pd) & seg);
             if (pd < best_d) { best_d = pd; best_k = pk; n_at_min = eq; }
             else if (pd == best_d) { n_at_min += eq; best_k = min(best_k, pk); }
         }
         if (best_k == 0x7fffffff) best_k = 0;                 // every distance NaN: torch.argmin -> 0 as well
-        if (n_at_min > 1) st_tie++;
-        if (scan_all) st_fallback++; else if (nq > 1) st_rerank++;
-        st_cand += scan_all ? (unsigned long long)p.K : (unsigned long long)nq;
-        if (lane == 0) {
+        if (row_ok && c == 0) {
             idx_s[r] = best_k;
             p.idx[n] = (int64_t)best_k;
+            if (p.stats != nullptr && !((resolved_mask >> rr) & 1u)) {
+                if (n_at_min > 1) atomicAdd(p.stats + 0, 1ull);
+                if (my_nq > 1) atomicAdd(p.stats + 1, 1ull);
+                atomicAdd(p.stats + 3, (unsigned long long)my_nq);
+            }
         }
-    }
-    if (p.stats != nullptr && lane == 0) {
-        if (st_tie) atomicAdd(p.stats + 0, st_tie);
-        if (st_rerank) atomicAdd(p.stats + 1, st_rerank);
-        if (st_fallback) atomicAdd(p.stats + 2, st_fallback);
-        if (st_cand) atomicAdd(p.stats + 3, st_cand);
     }
     if (!kForward) return;
 
@@ -148,7 +189,7 @@ vq_select_kernel(const SelectParams p) {
     __syncthreads();
     if (tid == 0) {
         double sum = 0.0;
-        for (int w = 0; w < kSelThreads / 32; w++) sum += red_s[w];
+        for (int w = 0; w < kSelWarps; w++) sum += red_s[w];
         p.loss_partial[blockIdx.x] = sum;
         __threadfence();
         is_last = (atomicAdd(p.blocks_done, 1u) == gridDim.x - 1);
@@ -165,10 +206,90 @@ vq_select_kernel(const SelectParams p) {
         __syncthreads();
         if (tid == 0) {
             double tot = 0.0;
-            for (int w = 0; w < kSelThreads / 32; w++) tot += red_s[w];
+            for (int w = 0; w < kSelWarps; w++) tot += red_s[w];
             const double m = tot / ((double)p.N * (double)kD);
             *p.loss = (float)(m + (double)p.beta * m);       // mean(a + beta*mean(b)), a == b elementwise
             *p.blocks_done = 0;                              // re-arm for the next call on this workspace
+        }
+    }
+}
+
+struct FallbackParams {
+    const float* z;
+    const float* E;
+    const float* e2;
+    const float* z2;
+    const int32_t* fb_rows;
+    const int32_t* fb_count;
+    int64_t HW;
+    int K;
+    int32_t* out_cnt;
+    uint32_t* out_q;
+    unsigned long long* stats;
+};
+
+// merge (distance, first index, multiplicity) triples: lexicographic minimum, multiplicities of equal minima add up
+__device__ __forceinline__ void merge_min(float& d, int& k, int& c, float d2, int k2, int c2) {
+    if (d2 < d) { d = d2; k = k2; c = c2; }
+    else if (d2 == d) { c += c2; k = min(k, k2); }
+}
+
+__global__ void __launch_bounds__(kFbThreads)
+vq_fallback_kernel(const FallbackParams p) {
+    __shared__ float4 zr4[kD / 4];
+    __shared__ float sd[kFbThreads / 32];
+    __shared__ int sk[kFbThreads / 32], sn[kFbThreads / 32];
+    __shared__ int claimed;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int count = __ldg(p.fb_count);
+    for (int i = blockIdx.x; i < count; i += gridDim.x) {
+        const int64_t n = __ldg(p.fb_rows + i);
+        const int64_t b = n / p.HW, hw = n % p.HW;
+        __syncthreads();
+        // a row can be listed twice (once per epilogue group): the first CTA to get here claims it
+        if (tid == 0) claimed = (atomicExch(p.out_cnt + 2 * n, -2) != -2);
+        if (tid < kD) reinterpret_cast<float*>(zr4)[tid] = __ldg(p.z + (b * kD + tid) * p.HW + hw);
+        __syncthreads();
+        if (!claimed) continue;
+        const float z2 = __ldg(p.z2 + n);
+        float best_d = INFINITY;
+        int best_k = 0x7fffffff, n_at_min = 0;
+        for (int k = tid; k < p.K; k += kFbThreads) {          // ascending k per thread: first minimum kept
+            const float4* e4 = reinterpret_cast<const float4*>(p.E + (int64_t)k * kD);
+            float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
+#pragma unroll 8
+            for (int q = 0; q < kD / 4; q++) {
+                const float4 e = __ldg(e4 + q);
+                const float4 zv = zr4[q];
+                p0 = __fmaf_rn(zv.x, e.x, p0);
+                p1 = __fmaf_rn(zv.y, e.y, p1);
+                p2 = __fmaf_rn(zv.z, e.z, p2);
+                p3 = __fmaf_rn(zv.w, e.w, p3);
+            }
+            const float dist = ref_distance(z2, __ldg(p.e2 + k), __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3)));
+            merge_min(best_d, best_k, n_at_min, dist, k, 1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float d2 = __shfl_xor_sync(0xffffffffu, best_d, o);
+            const int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
+            const int c2 = __shfl_xor_sync(0xffffffffu, n_at_min, o);
+            merge_min(best_d, best_k, n_at_min, d2, k2, c2);
+        }
+        if (lane == 0) { sd[warp] = best_d; sk[warp] = best_k; sn[warp] = n_at_min; }
+        __syncthreads();
+        if (tid == 0) {
+            float d = sd[0];
+            int k = sk[0], cnt = sn[0];
+            for (int w = 1; w < kFbThreads / 32; w++) merge_min(d, k, cnt, sd[w], sk[w], sn[w]);
+            if (k == 0x7fffffff) k = 0;                          // every distance NaN: torch.argmin -> 0 as well
+            // one-quad candidate entry; out_cnt[2n] already holds -2 (claimed above)
+            p.out_q[n * kOutCap] = ((uint32_t)(k >> 5) << 8) | (1u << ((k >> 2) & 7));
+            if (p.stats != nullptr) {
+                if (cnt > 1) atomicAdd(p.stats + 0, 1ull);
+                atomicAdd(p.stats + 2, 1ull);
+                atomicAdd(p.stats + 3, (unsigned long long)(p.K / kQuad));
+            }
         }
     }
 }
