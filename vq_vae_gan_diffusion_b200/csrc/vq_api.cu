@@ -85,8 +85,11 @@ int device_info(DevInfo** out) {
                                      (int)vq::kGemmSmemBytes));
         VQ_CUDA(cudaFuncSetAttribute(vq::vq_argmin_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)vq::kGemmSmemBytes));
-        VQ_CUDA(cudaFuncSetAttribute(vq::vq_backward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(2 * vq::kD * (vq::kSelRows + 1) * sizeof(float))));
+        const int bwd_smem = (int)(2 * vq::kBwdTileBytes);
+        VQ_CUDA(cudaFuncSetAttribute(vq::vq_backward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
+        VQ_CUDA(cudaFuncSetAttribute(vq::vq_backward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
+        VQ_CUDA(cudaFuncSetAttribute(vq::vq_backward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
+        VQ_CUDA(cudaFuncSetAttribute(vq::vq_backward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
         d.attrs_set = true;
     }
     *out = &d;
@@ -186,8 +189,14 @@ int run_gemm(const float* z, int64_t N, int64_t HW, const void* E_h, const float
     const int64_t n_pad = round_up(N, vq::kRowTile);
     const int k_pad = vq_padded_codes(K);
 
-    vq::vq_prep_z_kernel<<<(unsigned)(n_pad / vq::kSelRows), vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2,
-                                                                                        w.z_inv_scale);
+    // 16-byte tile accesses need 32-latent tiles that are hw-contiguous and 16-byte aligned
+    const bool vec = (HW % vq::kSelRows == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
+    if (vec)
+        vq::vq_prep_z_kernel<true><<<(unsigned)(n_pad / vq::kSelRows), vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h,
+                                                                                                  w.z2, w.z_inv_scale);
+    else
+        vq::vq_prep_z_kernel<false><<<(unsigned)(n_pad / vq::kSelRows), vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h,
+                                                                                                   w.z2, w.z_inv_scale);
     VQ_LAUNCH_CHECK("vq_prep_z_kernel");
 
     CUtensorMap tm_z, tm_e;
@@ -352,11 +361,14 @@ static int forward_impl(bool training, const float* z, int64_t B, int64_t HW, in
     sp.loss_partial = w.loss_partial; sp.blocks_done = w.blocks_done; sp.loss = loss;
     sp.stats = stats;
     const unsigned grid = (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows);
+    const bool vec = (HW % vq::kSelRows == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
     if (training) {
         VQ_CUDA(cudaMemsetAsync(w.blocks_done, 0, sizeof(unsigned int), st));
-        vq::vq_select_kernel<true><<<grid, vq::kSelThreads, 0, st>>>(sp);
+        if (vec) vq::vq_select_kernel<true, true><<<grid, vq::kSelThreads, 0, st>>>(sp);
+        else     vq::vq_select_kernel<true, false><<<grid, vq::kSelThreads, 0, st>>>(sp);
     } else {
-        vq::vq_select_kernel<false><<<grid, vq::kSelThreads, 0, st>>>(sp);
+        if (vec) vq::vq_select_kernel<false, true><<<grid, vq::kSelThreads, 0, st>>>(sp);
+        else     vq::vq_select_kernel<false, false><<<grid, vq::kSelThreads, 0, st>>>(sp);
     }
     VQ_LAUNCH_CHECK("vq_select_kernel");
     return VQ_OK;
@@ -423,12 +435,19 @@ VQ_EXPORT int vq_backward(const float* gout, const int64_t* gout_strides, float 
     bp.beta = beta;
     bp.grad_z = grad_z; bp.grad_E = grad_E;
     const unsigned grid = (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows);
-    const size_t tile = (size_t)vq::kD * (vq::kSelRows + 1) * sizeof(float);
-    // channels-last upstream gradient (d contiguous; the layout of the z_q we returned) is staged through shared
-    // memory so its reads are coalesced too; any other layout is read in place, lanes over hw.
+    const size_t smem = 2 * vq::kBwdTileBytes;
+    // channels-last upstream gradient (d contiguous; the layout of the z_q we returned) is read lanes-over-d, an
+    // hw-contiguous one like z; 16-byte tile accesses need hw-contiguous, 16-byte aligned 32-latent tiles
     const bool cl = gout != nullptr && bp.gs_d == 1 && !(bp.gs_hw == 1 && HW > 1);
-    if (cl) vq::vq_backward_kernel<true><<<grid, vq::kBwdThreads, 2 * tile, st>>>(bp);
-    else    vq::vq_backward_kernel<false><<<grid, vq::kBwdThreads, tile, st>>>(bp);
+    const bool vec = (HW % vq::kSelRows == 0) && ((reinterpret_cast<uintptr_t>(z_nchw) & 15) == 0) &&
+                     (grad_z == nullptr || (reinterpret_cast<uintptr_t>(grad_z) & 15) == 0);
+    if (vec) {
+        if (cl) vq::vq_backward_kernel<true, true><<<grid, vq::kBwdThreads, smem, st>>>(bp);
+        else    vq::vq_backward_kernel<true, false><<<grid, vq::kBwdThreads, smem, st>>>(bp);
+    } else {
+        if (cl) vq::vq_backward_kernel<false, true><<<grid, vq::kBwdThreads, smem, st>>>(bp);
+        else    vq::vq_backward_kernel<false, false><<<grid, vq::kBwdThreads, smem, st>>>(bp);
+    }
     VQ_LAUNCH_CHECK("vq_backward_kernel");
     return VQ_OK;
 }
@@ -445,7 +464,11 @@ VQ_EXPORT int vq_embed_nchw(const int64_t* idx, const float* E, int64_t B, int64
     int rc = device_info(&dev);
     if (rc != VQ_OK) return rc;
     const unsigned grid = (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows);
-    vq::vq_embed_nchw_kernel<<<grid, vq::kBwdThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(idx, E, N, HW, K, out);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if ((HW % vq::kSelRows == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0))
+        vq::vq_embed_nchw_kernel<true><<<grid, vq::kBwdThreads, 0, st>>>(idx, E, N, HW, K, out);
+    else
+        vq::vq_embed_nchw_kernel<false><<<grid, vq::kBwdThreads, 0, st>>>(idx, E, N, HW, K, out);
     VQ_LAUNCH_CHECK("vq_embed_nchw_kernel");
     return VQ_OK;
 }

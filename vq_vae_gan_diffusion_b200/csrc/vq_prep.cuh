@@ -19,26 +19,21 @@ constexpr int kCbMaxAbs = 1;     // max |E[k][d]|
 constexpr int kCbInvScale = 2;   // 2^(ex_E - 15): inverse of the fp16 operand scale
 
 // One CTA = 32 consecutive latents.  Tile held in shared memory as t[d][row] (+1 pad).
+template <bool kVec>
 __global__ void __launch_bounds__(kPrepThreads)
 vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_pad,
                  __half* __restrict__ z_h, float* __restrict__ z2, float* __restrict__ z_inv_scale) {
-    __shared__ float t[kD][kSelRows + 1];
+    __shared__ TileRow t[kD];
     __shared__ float scale_s[kSelRows];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n0 = (int64_t)blockIdx.x * kSelRows;
 
-    // load: lane = latent row (consecutive hw -> coalesced when HW >= 32), warp strides over d
-    {
-        const int64_t n = n0 + lane;
-        const bool ok = n < N;
-        const int64_t b = ok ? n / HW : 0, hw = ok ? n % HW : 0;
-        const float* src = z + (b * kD) * HW + hw;
-#pragma unroll 8
-        for (int i = 0; i < kD / 8; i++) {
-            const int d = warp + 8 * i;
-            t[d][lane] = ok ? __ldg(src + (int64_t)d * HW) : 0.0f;
-        }
+    if (kVec && n0 >= N) {                                   // pad rows of the last GEMM row tile: zero operand rows
+        for (int i = tid; i < kSelRows * kD / 2; i += kPrepThreads)
+            if (n0 * kD / 2 + i < n_pad * kD / 2) reinterpret_cast<__half2*>(z_h + n0 * kD)[i] = __floats2half2_rn(0.f, 0.f);
+        return;
     }
+    load_tile_nchw<kVec, false>(t, z, n0, N, HW, warp, lane);
     __syncthreads();
 
     // |z|^2 in canonical order and max|z|: 4 threads per row, thread j owns the terms d == j (mod 4)

@@ -44,7 +44,7 @@ struct SelectParams {
 };
 
 // canonical-order distance of latent row (shared tile column r) to code k; one thread does the whole dot product
-__device__ __forceinline__ float exact_distance_tile(const float (*t)[kSelRows + 1], int r, const float* __restrict__ E,
+__device__ __forceinline__ float exact_distance_tile(const TileRow* t, int r, const float* __restrict__ E,
                                                      const float* __restrict__ e2, int k, float z2) {
     const float4* e4 = reinterpret_cast<const float4*>(E + (int64_t)k * kD);
     float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
@@ -60,29 +60,22 @@ __device__ __forceinline__ float exact_distance_tile(const float (*t)[kSelRows +
     return ref_distance(z2, __ldg(e2 + k), dot);
 }
 
-template <bool kForward>
+template <bool kForward, bool kVec>
 __global__ void __launch_bounds__(kSelThreads)
 vq_select_kernel(const SelectParams p) {
-    __shared__ float t[kD][kSelRows + 1];
+    __shared__ TileRow t[kD];
     __shared__ int qlist[kSelWarps][4][kMaxQuads];
     __shared__ int idx_s[kSelRows];
     __shared__ double red_s[kSelWarps];
+    __shared__ unsigned int st_s[4];                          // per-CTA counters (same-address global atomics are slow)
     __shared__ bool is_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n0 = (int64_t)blockIdx.x * kSelRows;
+    if (tid < 4) st_s[tid] = 0;
 
-    {   // 1. z tile
-        const int64_t n = n0 + lane;
-        const bool ok = n < p.N;
-        const int64_t b = ok ? n / p.HW : 0, hw = ok ? n % p.HW : 0;
-        const float* src = p.z + (b * kD) * p.HW + hw;
-#pragma unroll 8
-        for (int i = 0; i < kD / 8; i++) {
-            const int d = warp + 8 * i;
-            t[d][lane] = ok ? __ldg(src + (int64_t)d * p.HW) : 0.0f;
-        }
-    }
+    // 1. z tile
+    load_tile_nchw<kVec, false>(t, p.z, n0, p.N, p.HW, warp, lane);
 
     // 2a. expand this warp's candidate entries into quads (independent of the z tile)
     int nq[4];
@@ -153,33 +146,44 @@ vq_select_kernel(const SelectParams p) {
             idx_s[r] = best_k;
             p.idx[n] = (int64_t)best_k;
             if (p.stats != nullptr && !((resolved_mask >> rr) & 1u)) {
-                if (n_at_min > 1) atomicAdd(p.stats + 0, 1ull);
-                if (my_nq > 1) atomicAdd(p.stats + 1, 1ull);
-                atomicAdd(p.stats + 3, (unsigned long long)my_nq);
+                if (n_at_min > 1) atomicAdd(&st_s[0], 1u);
+                if (my_nq > 1) atomicAdd(&st_s[1], 1u);
+                atomicAdd(&st_s[3], (unsigned)my_nq);
             }
         }
     }
+    __syncthreads();
+    if (p.stats != nullptr && tid < 4 && st_s[tid] != 0) atomicAdd(p.stats + tid, (unsigned long long)st_s[tid]);
     if (!kForward) return;
 
-    // 3. forward tail
-    __syncthreads();
+    // 3. forward tail: all four code rows of this warp are requested before the first one is consumed
     float sq = 0.0f;
-    for (int rr = 0; rr < 4; rr++) {
-        const int r = warp * 4 + rr;
-        const int64_t n = n0 + r;
-        if (n >= p.N) break;
-        const int k = idx_s[r];
-        const float* e = p.E + (int64_t)k * kD;
-        float* out = p.zq + n * kD;
+    {
+        float ev[4][kD / 32];
+        int kk[4];
 #pragma unroll
-        for (int i = 0; i < kD / 32; i++) {
-            const int d = lane + 32 * i;
-            const float zv = t[d][r];
-            const float diff = __fsub_rn(__ldg(e + d), zv);    // fl(e - z)
-            __stcs(out + d, __fadd_rn(zv, diff));              // fl(z + fl(e - z)), codebook.py:106
-            sq = __fmaf_rn(diff, diff, sq);
+        for (int rr = 0; rr < 4; rr++) {
+            const int r = warp * 4 + rr;
+            kk[rr] = (n0 + r < p.N) ? idx_s[r] : -1;
+            const float* e = p.E + (int64_t)max(kk[rr], 0) * kD;
+#pragma unroll
+            for (int i = 0; i < kD / 32; i++) ev[rr][i] = (kk[rr] >= 0) ? __ldg(e + lane + 32 * i) : 0.0f;
         }
-        if (p.hist != nullptr && lane == 0) atomicAdd(p.hist + k, 1ull);
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++) {
+            if (kk[rr] < 0) continue;
+            const int r = warp * 4 + rr;
+            float* out = p.zq + (n0 + r) * kD;
+#pragma unroll
+            for (int i = 0; i < kD / 32; i++) {
+                const int d = lane + 32 * i;
+                const float zv = t[d][r];
+                const float diff = __fsub_rn(ev[rr][i], zv);       // fl(e - z)
+                __stcs(out + d, __fadd_rn(zv, diff));              // fl(z + fl(e - z)), codebook.py:106
+                sq = __fmaf_rn(diff, diff, sq);
+            }
+            if (p.hist != nullptr && lane == 0) atomicAdd(p.hist + kk[rr], 1ull);
+        }
     }
     // loss: fp32 per thread (<= 32 terms), fp64 from there on; fixed-order final sum by the last CTA
     double v = (double)sq;
