@@ -40,14 +40,15 @@ constexpr uint32_t kBytesBStage = kCodeTile * kDChunk * 2;   // 32 KiB
 constexpr uint32_t kBytesE2Tile = kCodeTile * 4;             // 1 KiB
 constexpr uint32_t kTmemCols = 512;
 constexpr int kOutPerGroup = kOutCap / kEpiGroups;           // candidate entries a group may hand over per row
-constexpr int kMaxQuadsPerGroup = 16;                        // ... and quads (the exact stage lists <= 32 per row)
+constexpr int kMaxCodesPerGroup = 32;                        // ... and codes (the exact stage lists <= 64 per row)
 
 struct GemmSmem {
     alignas(1024) uint8_t a[kNumDChunks][kBytesAChunk];      // 64 KiB
     alignas(1024) uint8_t b[kStagesB][kBytesBStage];         // 128 KiB
     alignas(16) float e2s[2][kCodeTile];                     // 2 KiB   |e|^2 of the code tile in accumulator buffer b
-    uint32_t ring_q[kEpiGroups][kRingCap][kRowTile];         // 12 KiB  (chunk << 8 | quad mask), [slot][row]
-    float ring_s[kEpiGroups][kRingCap][kRowTile];            // 12 KiB  chunk minima
+    uint32_t ring_q[kEpiGroups][kRingCap][kRowTile];         // 8 KiB   chunk ids, [slot][row]: conflict-free
+    uint32_t ring_m[kEpiGroups][kRingCap][kRowTile];         // 8 KiB   32-bit masks of the chunk's candidate codes
+    float ring_s[kEpiGroups][kRingCap][kRowTile];            // 8 KiB   chunk minima
     float m_part[2][kEpiGroups][kRowTile];                   // 2 KiB   per-group running minima (double buffered)
     int32_t c_part[2][kEpiGroups][kRowTile];                 // 2 KiB   per-group push counts
     alignas(8) uint64_t a_full[kNumDChunks];
@@ -72,7 +73,7 @@ struct GemmParams {
     int k_tiles;               // K_pad / 256
     int row_tiles;             // N_pad / 128
     int32_t* out_cnt;          // (N, 2) candidate entries per epilogue group, or -1: list unusable -> exact row scan
-    uint32_t* out_q;           // (N, kOutCap) entries (chunk << 8 | quad mask); group g owns slots [g*8, g*8+8)
+    uint32_t* out_q;           // (N, kOutCap, 2) entries (chunk id, 32-bit code mask); group g owns slots [g*8, g*8+8)
     int32_t* fb_rows;          // (2N) worklist of the rows flagged -1 (for vq_fallback_kernel)
     int32_t* fb_count;         // (1)  its length, zeroed before launch
     float* dbg_scores;         // (N, K_pad) or null
@@ -191,6 +192,7 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
         const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16) + col0;
         const uint32_t e2_sa[2] = {smem_u32(&s.e2s[0][col0]), smem_u32(&s.e2s[1][col0])};
         const uint32_t ring_q_sa = smem_u32(&s.ring_q[grp][0][trow]);
+        const uint32_t ring_m_sa = smem_u32(&s.ring_m[grp][0][trow]);
         const uint32_t ring_s_sa = smem_u32(&s.ring_s[grp][0][trow]);
         constexpr uint32_t kSlotStride = kRowTile * 4;
         const float e2max = __ldg(p.cb + 0);
@@ -259,14 +261,21 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                         m8[q] = fminf(min3(sc[4 * q], sc[4 * q + 1], sc[4 * q + 2]), sc[4 * q + 3]);
                     const float cm = min3(min3(m8[0], m8[1], m8[2]), min3(m8[3], m8[4], m8[5]), fminf(m8[6], m8[7]));
                     if (cm <= thr) {
-                        // slow path: this chunk holds a quad within the running threshold -> one ring entry
+                        // slow path: this chunk holds a code within the running threshold -> one ring entry with the
+                        // mask of all such codes (only quads whose minimum passes are looked into)
                         m_run = fminf(m_run, cm);
                         thr = m_run + margin;
-                        uint32_t entry = (uint32_t)(kt * (kCodeTile / kChunk) + grp * (kGroupCols / kChunk) + c) << 8;
+                        uint32_t cmask = 0;
 #pragma unroll
-                        for (int q = 0; q < 8; q++) entry |= (m8[q] <= thr) ? (1u << q) : 0u;
+                        for (int q = 0; q < 8; q++) {
+                            if (m8[q] <= thr) {
+                                cmask |= ((sc[4 * q + 0] <= thr ? 1u : 0u) | (sc[4 * q + 1] <= thr ? 2u : 0u) |
+                                          (sc[4 * q + 2] <= thr ? 4u : 0u) | (sc[4 * q + 3] <= thr ? 8u : 0u)) << (4 * q);
+                            }
+                        }
                         if (cnt >= kRingCap) lost_min = fminf(lost_min, lds_f32(ring_s_sa + slot_off));
-                        sts_u32(ring_q_sa + slot_off, entry);
+                        sts_u32(ring_q_sa + slot_off, (uint32_t)(kt * (kCodeTile / kChunk) + grp * (kGroupCols / kChunk) + c));
+                        sts_u32(ring_m_sa + slot_off, cmask);
                         sts_f32(ring_s_sa + slot_off, cm);
                         cnt++;
                         slot_off = (slot_off + kSlotStride == kRingCap * kSlotStride) ? 0u : slot_off + kSlotStride;
@@ -287,16 +296,17 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
             const int cnt_all = cnt + s.c_part[pb][grp ^ 1][trow];
             if (row_ok) {
                 const float thr_fin = m_fin + margin;
-                int n_out = 0, n_quads = 0;
+                int n_out = 0, n_codes = 0;
                 // nothing recorded at all (NaN row: group 0 reports) or a possible survivor was overwritten
                 bool bad = (cnt_all == 0 && grp == 0) || (lost_min <= thr_fin);
                 const int live = min(cnt, kRingCap);
-                uint32_t* dst = p.out_q + row * kOutCap + grp * kOutPerGroup;
+                uint2* dst = reinterpret_cast<uint2*>(p.out_q) + row * kOutCap + grp * kOutPerGroup;
                 for (int i = 0; i < live && !bad; i++) {
                     if (lds_f32(ring_s_sa + i * kSlotStride) <= thr_fin) {
-                        const uint32_t entry = lds_u32(ring_q_sa + i * kSlotStride);
-                        n_quads += __popc(entry & 0xffu);
-                        if (n_out < kOutPerGroup && n_quads <= kMaxQuadsPerGroup) dst[n_out] = entry;
+                        const uint32_t chunk = lds_u32(ring_q_sa + i * kSlotStride);
+                        const uint32_t cmask = lds_u32(ring_m_sa + i * kSlotStride);
+                        n_codes += __popc(cmask);
+                        if (n_out < kOutPerGroup && n_codes <= kMaxCodesPerGroup) dst[n_out] = make_uint2(chunk, cmask);
                         else bad = true;
                         n_out++;
                     }

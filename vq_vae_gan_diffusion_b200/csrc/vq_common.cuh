@@ -13,7 +13,7 @@ constexpr int kCodeTile = 256;      // codes per GEMM tile    (UMMA N)
 constexpr int kDChunk = 64;         // 16-bit elements per 128-byte swizzle row
 constexpr int kNumDChunks = kD / kDChunk;
 constexpr int kQuad = 4;            // candidate granularity: 4 consecutive codes
-constexpr int kRingCap = 12;        // candidate ring per (row, epilogue group) in shared memory inside the GEMM epilogue
+constexpr int kRingCap = 8;      // candidate ring per (row, epilogue group) in shared memory inside the GEMM epilogue
 constexpr int kOutCap = 16;         // surviving candidate quads handed to the exact stage, per row (half per group)
 constexpr int kSelRows = 32;        // latents per CTA in the fp32 kernels (prep / select / backward)
 

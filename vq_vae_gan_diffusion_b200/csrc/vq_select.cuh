@@ -21,8 +21,10 @@ namespace vq {
 
 constexpr int kSelThreads = 256;
 constexpr int kSelWarps = kSelThreads / 32;
-constexpr int kMaxQuads = 32;           // quads per row the exact stage evaluates (GEMM hands over <= 16 per group)
-constexpr int kFbThreads = 1024;
+constexpr int kMaxCands = 64;           // codes per row the exact stage evaluates (GEMM hands over <= 32 per group)
+constexpr int kFbThreads = 256;
+constexpr int kFbParts = 16;            // CTAs sharing the exact scan of one overflowed row
+constexpr int kFbMaxRows = 4096;        // worklist entries that get the split treatment
 
 struct SelectParams {
     const float* z;            // (B, D, HW) fp32
@@ -64,7 +66,7 @@ template <bool kForward, bool kVec>
 __global__ void __launch_bounds__(kSelThreads)
 vq_select_kernel(const SelectParams p) {
     __shared__ TileRow t[kD];
-    __shared__ int qlist[kSelWarps][4][kMaxQuads];
+    __shared__ int clist[kSelWarps][4][kMaxCands];            // candidate codes of each row of each warp
     __shared__ int idx_s[kSelRows];
     __shared__ double red_s[kSelWarps];
     __shared__ unsigned int st_s[4];                          // per-CTA counters (same-address global atomics are slow)
@@ -90,8 +92,9 @@ vq_select_kernel(const SelectParams p) {
         if (resolved) resolved_mask |= 1u << rr;
         const int g = lane >> 3, i = lane & 7;                // slot = lane: group g owns slots [8g, 8g + 8)
         const bool valid = resolved ? (lane == 0) : (lane < kOutCap && i < (g ? c1 : c0));
-        const uint32_t e = valid ? __ldg(p.out_q + n * kOutCap + lane) : 0u;
-        const int pc = __popc(e & 0xffu);
+        uint2 e = make_uint2(0u, 0u);                         // (chunk id, mask of candidate codes in the chunk)
+        if (valid) e = __ldg(reinterpret_cast<const uint2*>(p.out_q) + n * kOutCap + lane);
+        const int pc = __popc(e.y);
         int incl = pc;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -99,14 +102,14 @@ vq_select_kernel(const SelectParams p) {
             if (lane >= o) incl += v;
         }
         int pos = incl - pc;
-        uint32_t bits = e & 0xffu;
+        uint32_t bits = e.y;
         while (bits) {
             const int b = __ffs(bits) - 1;
             bits &= bits - 1;
-            if (pos < kMaxQuads) qlist[warp][rr][pos] = (int)(e >> 8) * 8 + b;
+            if (pos < kMaxCands) clist[warp][rr][pos] = (int)e.x * 32 + b;
             pos++;
         }
-        nq[rr] = min(kMaxQuads, __shfl_sync(0xffffffffu, incl, 31));
+        nq[rr] = min(kMaxCands, __shfl_sync(0xffffffffu, incl, 31));
     }
     __syncthreads();
 
@@ -122,9 +125,8 @@ vq_select_kernel(const SelectParams p) {
         const unsigned seg = 0xffu << (rr * 8);
         float best_d = INFINITY;
         int best_k = 0x7fffffff, n_at_min = 0;
-        for (int base = 0; base < max_nq; base += 2) {
-            const int tq = base + (c >> 2);
-            int k = (tq < my_nq) ? qlist[warp][rr][tq] * kQuad + (c & 3) : -1;
+        for (int base = 0; base < max_nq; base += 8) {
+            int k = (base + c < my_nq) ? clist[warp][rr][base + c] : -1;
             if (k >= p.K) k = -1;                              // pad codes of the last chunk
             float dist = INFINITY;
             if (k >= 0) dist = exact_distance_tile(t, r, p.E, p.e2, k, z2);
@@ -229,6 +231,8 @@ struct FallbackParams {
     int K;
     int32_t* out_cnt;
     uint32_t* out_q;
+    float4* part;              // (kFbMaxRows, kFbParts) partial (distance, index, multiplicity) results
+    unsigned int* arrive;      // (kFbMaxRows) arrival counters, zero on entry, re-armed by the kernel
     unsigned long long* stats;
 };
 
@@ -238,30 +242,37 @@ __device__ __forceinline__ void merge_min(float& d, int& k, int& c, float d2, in
     else if (d2 == d) { c += c2; k = min(k, k2); }
 }
 
+// Work item = (worklist entry i, part): the codebook of an overflowed row is split over kFbParts CTAs so that even a
+// handful of such rows is scanned by the whole chip; the last part to arrive merges the partial minima.  Entries
+// beyond kFbMaxRows (a degenerate codebook: every row overflows) are scanned by one CTA each.
 __global__ void __launch_bounds__(kFbThreads)
 vq_fallback_kernel(const FallbackParams p) {
     __shared__ float4 zr4[kD / 4];
     __shared__ float sd[kFbThreads / 32];
     __shared__ int sk[kFbThreads / 32], sn[kFbThreads / 32];
-    __shared__ int claimed;
+    __shared__ int is_final;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int count = __ldg(p.fb_count);
-    for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    const int64_t items = (int64_t)count * kFbParts;
+    const int per_part = (p.K + kFbParts - 1) / kFbParts;
+    for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
+        const int i = (int)(w / kFbParts), part = (int)(w % kFbParts);
+        const bool split = i < kFbMaxRows;
+        if (!split && part != 0) continue;                       // block-uniform
         const int64_t n = __ldg(p.fb_rows + i);
         const int64_t b = n / p.HW, hw = n % p.HW;
         __syncthreads();
-        // a row can be listed twice (once per epilogue group): the first CTA to get here claims it
-        if (tid == 0) claimed = (atomicExch(p.out_cnt + 2 * n, -2) != -2);
         if (tid < kD) reinterpret_cast<float*>(zr4)[tid] = __ldg(p.z + (b * kD + tid) * p.HW + hw);
         __syncthreads();
-        if (!claimed) continue;
         const float z2 = __ldg(p.z2 + n);
+        const int k_lo = split ? part * per_part : 0;
+        const int k_hi = split ? min(p.K, k_lo + per_part) : p.K;
         float best_d = INFINITY;
         int best_k = 0x7fffffff, n_at_min = 0;
-        for (int k = tid; k < p.K; k += kFbThreads) {          // ascending k per thread: first minimum kept
+        for (int k = k_lo + tid; k < k_hi; k += kFbThreads) {    // ascending k per thread: first minimum kept
             const float4* e4 = reinterpret_cast<const float4*>(p.E + (int64_t)k * kD);
             float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
-#pragma unroll 8
+#pragma unroll 16
             for (int q = 0; q < kD / 4; q++) {
                 const float4 e = __ldg(e4 + q);
                 const float4 zv = zr4[q];
@@ -285,14 +296,31 @@ vq_fallback_kernel(const FallbackParams p) {
         if (tid == 0) {
             float d = sd[0];
             int k = sk[0], cnt = sn[0];
-            for (int w = 1; w < kFbThreads / 32; w++) merge_min(d, k, cnt, sd[w], sk[w], sn[w]);
-            if (k == 0x7fffffff) k = 0;                          // every distance NaN: torch.argmin -> 0 as well
-            // one-quad candidate entry; out_cnt[2n] already holds -2 (claimed above)
-            p.out_q[n * kOutCap] = ((uint32_t)(k >> 5) << 8) | (1u << ((k >> 2) & 7));
-            if (p.stats != nullptr) {
-                if (cnt > 1) atomicAdd(p.stats + 0, 1ull);
-                atomicAdd(p.stats + 2, 1ull);
-                atomicAdd(p.stats + 3, (unsigned long long)(p.K / kQuad));
+            for (int v = 1; v < kFbThreads / 32; v++) merge_min(d, k, cnt, sd[v], sk[v], sn[v]);
+            bool final_part = !split;
+            if (split) {
+                p.part[(int64_t)i * kFbParts + part] = make_float4(d, __int_as_float(k), __int_as_float(cnt), 0.0f);
+                __threadfence();
+                final_part = (atomicAdd(p.arrive + i, 1u) == kFbParts - 1);
+                if (final_part) {
+                    __threadfence();
+                    d = INFINITY; k = 0x7fffffff; cnt = 0;
+                    for (int q = 0; q < kFbParts; q++) {
+                        const float4 r = __ldcg(p.part + (int64_t)i * kFbParts + q);
+                        merge_min(d, k, cnt, r.x, __float_as_int(r.y), __float_as_int(r.z));
+                    }
+                    p.arrive[i] = 0;                             // re-arm for the next call on this workspace
+                }
+            }
+            // a row can be listed twice (once per epilogue group): the first finisher publishes and counts it
+            if (final_part && atomicExch(p.out_cnt + 2 * n, -2) != -2) {
+                if (k == 0x7fffffff) k = 0;                      // every distance NaN: torch.argmin -> 0 as well
+                reinterpret_cast<uint2*>(p.out_q)[n * kOutCap] = make_uint2((uint32_t)(k >> 5), 1u << (k & 31));
+                if (p.stats != nullptr) {
+                    if (cnt > 1) atomicAdd(p.stats + 0, 1ull);
+                    atomicAdd(p.stats + 2, 1ull);
+                    atomicAdd(p.stats + 3, (unsigned long long)p.K);
+                }
             }
         }
     }
