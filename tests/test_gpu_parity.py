@@ -240,6 +240,27 @@ def test_backward_gout_layouts(vq, oracle):
     assert_close(zt.grad.cpu().numpy(), gz0, "grad_z (loss only)")
 
 
+def test_degenerate_codebook_mass_fallback(vq, oracle):
+    """Every row overflows its candidate list (identical codes): the exact fallback decides all of them, including
+    the worklist tail beyond the split-scan capacity; torch.argmin semantics -> lowest index of the tied minimum."""
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(7)
+    K, B, H, W = 300, 2, 64, 72                              # N = 9216 > 4096 split rows; HW % 32 == 0
+    base = rng.standard_normal((3, 256)).astype(np.float32)
+    E = np.repeat(base, K // 3, axis=0)                       # 3 distinct codes, each repeated 100 times
+    z = rng.standard_normal((B, 256, H, W)).astype(np.float32)
+    cb = vq.CodeBook(K, 256).to(dev)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(torch.from_numpy(E))
+        z_q, idx, loss = cb(torch.from_numpy(z).to(dev))
+    st = cb.stats_dict()
+    ref = oracle.forward(z, E, want_zq=False)
+    assert np.array_equal(idx.cpu().numpy(), ref["idx"])
+    assert set(np.unique(ref["idx"]).tolist()) <= {0, 100, 200}
+    assert st["tie_rows"] == ref["tie_rows"] == B * H * W
+    assert st["fallback_rows"] == B * H * W
+
+
 def test_embed_nchw(vq):
     dev = torch.device("cuda:0")
     W = torch.randn(300, 256, device=dev)

@@ -144,8 +144,8 @@ struct Workspace {
     unsigned int* blocks_done;   // (1) + padding; zeroed by vq_forward
     int32_t* fb_rows;            // (2N) rows needing the exact full scan (a row may be listed once per group)
     int32_t* fb_count;           // (1)
-    float4* fb_part;             // (kFbMaxRows, kFbParts)
-    unsigned int* fb_arrive;     // (kFbMaxRows)
+    float4* fb_part;             // (kFbMaxGroups * kFbGroup, kFbMaxParts)
+    unsigned int* fb_arrive;     // (kFbMaxGroups)
     unsigned long long* stats;   // (VQ_STAT_COUNT) internal copy when the caller passes none
     size_t bytes;
 };
@@ -168,8 +168,8 @@ Workspace carve(void* base, int64_t N) {
     w.blocks_done = static_cast<unsigned int*>(take(256));
     w.fb_rows = static_cast<int32_t*>(take((size_t)n_pad * 2 * 4));
     w.fb_count = static_cast<int32_t*>(take(256));
-    w.fb_part = static_cast<float4*>(take((size_t)vq::kFbMaxRows * vq::kFbParts * sizeof(float4)));
-    w.fb_arrive = static_cast<unsigned int*>(take((size_t)vq::kFbMaxRows * sizeof(unsigned int)));
+    w.fb_part = static_cast<float4*>(take((size_t)vq::kFbMaxGroups * vq::kFbGroup * vq::kFbMaxParts * sizeof(float4)));
+    w.fb_arrive = static_cast<unsigned int*>(take((size_t)vq::kFbMaxGroups * sizeof(unsigned int)));
     w.stats = static_cast<unsigned long long*>(take(256));
     w.bytes = off;
     return w;
@@ -348,11 +348,14 @@ static int forward_impl(bool training, const float* z, int64_t B, int64_t HW, in
         fp.HW = HW; fp.K = K;
         fp.out_cnt = w.out_cnt; fp.out_q = w.out_q; fp.stats = stats;
         fp.part = w.fb_part; fp.arrive = w.fb_arrive;
-        VQ_CUDA(cudaMemsetAsync(w.fb_arrive, 0, (size_t)vq::kFbMaxRows * sizeof(unsigned int), st));
+        VQ_CUDA(cudaMemsetAsync(w.fb_arrive, 0, (size_t)vq::kFbMaxGroups * sizeof(unsigned int), st));
+        // code blocks: one code per thread when that needs <= kFbMaxParts blocks, else proportionally larger blocks
+        fp.per_part = vq::kFbThreads * (int)((K + (int64_t)vq::kFbThreads * vq::kFbMaxParts - 1) / ((int64_t)vq::kFbThreads * vq::kFbMaxParts));
+        fp.parts = (K + fp.per_part - 1) / fp.per_part;
         DevInfo* dev;
         rc = device_info(&dev);
         if (rc != VQ_OK) return rc;
-        const int64_t want = (N + 1) / 2 * vq::kFbParts;
+        const int64_t want = ((N + vq::kFbGroup - 1) / vq::kFbGroup) * fp.parts;
         const unsigned fgrid = (unsigned)(want < 4 * dev->sms ? want : 4 * dev->sms);
         vq::vq_fallback_kernel<<<fgrid, vq::kFbThreads, 0, st>>>(fp);
         VQ_LAUNCH_CHECK("vq_fallback_kernel");

@@ -23,8 +23,9 @@ constexpr int kSelThreads = 256;
 constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kMaxCands = 64;           // codes per row the exact stage evaluates (GEMM hands over <= 32 per group)
 constexpr int kFbThreads = 256;
-constexpr int kFbParts = 16;            // CTAs sharing the exact scan of one overflowed row
-constexpr int kFbMaxRows = 4096;        // worklist entries that get the split treatment
+constexpr int kFbGroup = 8;             // overflowed rows scanned together (they share every code-row load)
+constexpr int kFbMaxGroups = 512;       // row groups whose scan is split over code blocks (4096 rows)
+constexpr int kFbMaxParts = 256;        // code blocks per group
 
 struct SelectParams {
     const float* z;            // (B, D, HW) fp32
@@ -231,8 +232,9 @@ struct FallbackParams {
     int K;
     int32_t* out_cnt;
     uint32_t* out_q;
-    float4* part;              // (kFbMaxRows, kFbParts) partial (distance, index, multiplicity) results
-    unsigned int* arrive;      // (kFbMaxRows) arrival counters, zero on entry, re-armed by the kernel
+    float4* part;              // (kFbMaxGroups * kFbGroup, parts) partial (distance, index, multiplicity) results
+    unsigned int* arrive;      // (kFbMaxGroups) arrival counters, zero on entry, re-armed by the kernel
+    int parts, per_part;       // code blocks per group and codes per block (multiple of kFbThreads)
     unsigned long long* stats;
 };
 
@@ -242,78 +244,118 @@ __device__ __forceinline__ void merge_min(float& d, int& k, int& c, float d2, in
     else if (d2 == d) { c += c2; k = min(k, k2); }
 }
 
-// Work item = (worklist entry i, part): the codebook of an overflowed row is split over kFbParts CTAs so that even a
-// handful of such rows is scanned by the whole chip; the last part to arrive merges the partial minima.  Entries
-// beyond kFbMaxRows (a degenerate codebook: every row overflows) are scanned by one CTA each.
+// Work item = (group of kFbGroup worklist entries, block of codes): one thread per code streams its code row once
+// with 128-bit loads and applies it to all rows of the group (held in shared memory), so the codebook traffic of the
+// fallback is 1/kFbGroup of a row-by-row scan and a handful of overflowed rows is spread over the whole chip.  The
+// last code block of a group to arrive merges the per-block minima.  Groups beyond kFbMaxGroups (a degenerate
+// codebook: every row overflows) are scanned block after block by a single CTA each.
 __global__ void __launch_bounds__(kFbThreads)
 vq_fallback_kernel(const FallbackParams p) {
-    __shared__ float4 zr4[kD / 4];
-    __shared__ float sd[kFbThreads / 32];
-    __shared__ int sk[kFbThreads / 32], sn[kFbThreads / 32];
+    __shared__ float4 zr4[kFbGroup][kD / 4];
+    __shared__ float sd[kFbGroup][kFbThreads / 32];
+    __shared__ int sk[kFbGroup][kFbThreads / 32], sn[kFbGroup][kFbThreads / 32];
+    __shared__ int64_t row_s[kFbGroup];
     __shared__ int is_final;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int count = __ldg(p.fb_count);
-    const int64_t items = (int64_t)count * kFbParts;
-    const int per_part = (p.K + kFbParts - 1) / kFbParts;
+    const int groups = (count + kFbGroup - 1) / kFbGroup;
+    const int parts = p.parts, per_part = p.per_part;
+    const int64_t items = (int64_t)groups * parts;
     for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
-        const int i = (int)(w / kFbParts), part = (int)(w % kFbParts);
-        const bool split = i < kFbMaxRows;
-        if (!split && part != 0) continue;                       // block-uniform
-        const int64_t n = __ldg(p.fb_rows + i);
-        const int64_t b = n / p.HW, hw = n % p.HW;
+        const int g = (int)(w / parts), part0 = (int)(w % parts);
+        const bool split = g < kFbMaxGroups;
+        if (!split && part0 != 0) continue;                      // block-uniform
         __syncthreads();
-        if (tid < kD) reinterpret_cast<float*>(zr4)[tid] = __ldg(p.z + (b * kD + tid) * p.HW + hw);
+        if (tid < kFbGroup) row_s[tid] = (g * kFbGroup + tid < count) ? (int64_t)__ldg(p.fb_rows + g * kFbGroup + tid) : -1;
         __syncthreads();
-        const float z2 = __ldg(p.z2 + n);
-        const int k_lo = split ? part * per_part : 0;
-        const int k_hi = split ? min(p.K, k_lo + per_part) : p.K;
-        float best_d = INFINITY;
-        int best_k = 0x7fffffff, n_at_min = 0;
-        for (int k = k_lo + tid; k < k_hi; k += kFbThreads) {    // ascending k per thread: first minimum kept
-            const float4* e4 = reinterpret_cast<const float4*>(p.E + (int64_t)k * kD);
-            float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
-#pragma unroll 16
-            for (int q = 0; q < kD / 4; q++) {
-                const float4 e = __ldg(e4 + q);
-                const float4 zv = zr4[q];
-                p0 = __fmaf_rn(zv.x, e.x, p0);
-                p1 = __fmaf_rn(zv.y, e.y, p1);
-                p2 = __fmaf_rn(zv.z, e.z, p2);
-                p3 = __fmaf_rn(zv.w, e.w, p3);
+        for (int r = 0; r < kFbGroup; r++) {
+            const int64_t n = row_s[r];
+            if (tid < kD) reinterpret_cast<float*>(zr4[r])[tid] = (n >= 0) ? __ldg(p.z + ((n / p.HW) * kD + tid) * p.HW + n % p.HW) : 0.0f;
+        }
+        __syncthreads();
+        float z2[kFbGroup], best_d[kFbGroup];
+        int best_k[kFbGroup], n_at_min[kFbGroup];
+#pragma unroll
+        for (int r = 0; r < kFbGroup; r++) {
+            z2[r] = (row_s[r] >= 0) ? __ldg(p.z2 + row_s[r]) : 0.0f;
+            best_d[r] = INFINITY; best_k[r] = 0x7fffffff; n_at_min[r] = 0;
+        }
+        const int part_lo = split ? part0 : 0, part_hi = split ? part0 + 1 : parts;
+        for (int part = part_lo; part < part_hi; part++) {
+            const int k_hi = min(p.K, (part + 1) * per_part);
+            for (int k = part * per_part + tid; k < k_hi; k += kFbThreads) {   // ascending k per thread
+                const float4* e4 = reinterpret_cast<const float4*>(p.E + (int64_t)k * kD);
+                float acc[kFbGroup][4];
+#pragma unroll
+                for (int r = 0; r < kFbGroup; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+#pragma unroll 4
+                for (int q = 0; q < kD / 4; q++) {
+                    const float4 e = __ldg(e4 + q);
+#pragma unroll
+                    for (int r = 0; r < kFbGroup; r++) {
+                        const float4 zv = zr4[r][q];
+                        acc[r][0] = __fmaf_rn(zv.x, e.x, acc[r][0]);
+                        acc[r][1] = __fmaf_rn(zv.y, e.y, acc[r][1]);
+                        acc[r][2] = __fmaf_rn(zv.z, e.z, acc[r][2]);
+                        acc[r][3] = __fmaf_rn(zv.w, e.w, acc[r][3]);
+                    }
+                }
+                const float e2k = __ldg(p.e2 + k);
+#pragma unroll
+                for (int r = 0; r < kFbGroup; r++) {
+                    const float dot = __fadd_rn(__fadd_rn(acc[r][0], acc[r][1]), __fadd_rn(acc[r][2], acc[r][3]));
+                    merge_min(best_d[r], best_k[r], n_at_min[r], ref_distance(z2[r], e2k, dot), k, 1);
+                }
             }
-            const float dist = ref_distance(z2, __ldg(p.e2 + k), __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3)));
-            merge_min(best_d, best_k, n_at_min, dist, k, 1);
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float d2 = __shfl_xor_sync(0xffffffffu, best_d, o);
-            const int k2 = __shfl_xor_sync(0xffffffffu, best_k, o);
-            const int c2 = __shfl_xor_sync(0xffffffffu, n_at_min, o);
-            merge_min(best_d, best_k, n_at_min, d2, k2, c2);
+        for (int r = 0; r < kFbGroup; r++) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float d2 = __shfl_xor_sync(0xffffffffu, best_d[r], o);
+                const int k2 = __shfl_xor_sync(0xffffffffu, best_k[r], o);
+                const int c2 = __shfl_xor_sync(0xffffffffu, n_at_min[r], o);
+                merge_min(best_d[r], best_k[r], n_at_min[r], d2, k2, c2);
+            }
+            if (lane == 0) { sd[r][warp] = best_d[r]; sk[r][warp] = best_k[r]; sn[r][warp] = n_at_min[r]; }
         }
-        if (lane == 0) { sd[warp] = best_d; sk[warp] = best_k; sn[warp] = n_at_min; }
         __syncthreads();
-        if (tid == 0) {
-            float d = sd[0];
-            int k = sk[0], cnt = sn[0];
-            for (int v = 1; v < kFbThreads / 32; v++) merge_min(d, k, cnt, sd[v], sk[v], sn[v]);
-            bool final_part = !split;
+        // thread r finishes row r of the group
+        if (tid < kFbGroup && row_s[tid] >= 0) {
+            const int r = tid;
+            float d = sd[r][0];
+            int k = sk[r][0], cnt = sn[r][0];
+            for (int v = 1; v < kFbThreads / 32; v++) merge_min(d, k, cnt, sd[r][v], sk[r][v], sn[r][v]);
+            if (split) p.part[((int64_t)g * kFbGroup + r) * parts + part0] = make_float4(d, __int_as_float(k), __int_as_float(cnt), 0.0f);
+            sd[r][0] = d; sk[r][0] = k; sn[r][0] = cnt;
+        }
+        if (split) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                is_final = (atomicAdd(p.arrive + g, 1u) == (unsigned)parts - 1);
+                if (is_final) p.arrive[g] = 0;                   // re-arm for the next call on this workspace
+            }
+            __syncthreads();
+            if (!is_final) continue;
+            __threadfence();
+        } else {
+            __syncthreads();
+        }
+        if (tid < kFbGroup && row_s[tid] >= 0) {
+            const int r = tid;
+            const int64_t n = row_s[r];
+            float d = sd[r][0];
+            int k = sk[r][0], cnt = sn[r][0];
             if (split) {
-                p.part[(int64_t)i * kFbParts + part] = make_float4(d, __int_as_float(k), __int_as_float(cnt), 0.0f);
-                __threadfence();
-                final_part = (atomicAdd(p.arrive + i, 1u) == kFbParts - 1);
-                if (final_part) {
-                    __threadfence();
-                    d = INFINITY; k = 0x7fffffff; cnt = 0;
-                    for (int q = 0; q < kFbParts; q++) {
-                        const float4 r = __ldcg(p.part + (int64_t)i * kFbParts + q);
-                        merge_min(d, k, cnt, r.x, __float_as_int(r.y), __float_as_int(r.z));
-                    }
-                    p.arrive[i] = 0;                             // re-arm for the next call on this workspace
+                d = INFINITY; k = 0x7fffffff; cnt = 0;
+                for (int q = 0; q < parts; q++) {
+                    const float4 v = __ldcg(p.part + ((int64_t)g * kFbGroup + r) * parts + q);
+                    merge_min(d, k, cnt, v.x, __float_as_int(v.y), __float_as_int(v.z));
                 }
             }
             // a row can be listed twice (once per epilogue group): the first finisher publishes and counts it
-            if (final_part && atomicExch(p.out_cnt + 2 * n, -2) != -2) {
+            if (atomicExch(p.out_cnt + 2 * n, -2) != -2) {
                 if (k == 0x7fffffff) k = 0;                      // every distance NaN: torch.argmin -> 0 as well
                 reinterpret_cast<uint2*>(p.out_q)[n * kOutCap] = make_uint2((uint32_t)(k >> 5), 1u << (k & 31));
                 if (p.stats != nullptr) {
