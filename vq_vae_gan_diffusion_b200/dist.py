@@ -3,16 +3,17 @@
 Latents shard by batch across ranks (one process per GPU), the codebook is replicated.  Per training step exactly
 one exchange happens, a SUM all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests) of
 
-    grad_E      (K, D) fp32     codebook gradient
-    [hist | loss_sum | n]       (K + 2) fp64: usage histogram (exact in fp64), sum of per-rank losses, rank count
+    grad_E   (K, D) fp32     codebook gradient          -- launched from inside backward
+    hist     (K)    int64    usage histogram             -- launched right after forward, overlaps backward
+    loss     (1)    fp32     sum of the per-rank losses  -- idem
 
 Everything else is local.  With ``n_global = sum of shard sizes`` passed to the backward, the SUM of the per-rank
 codebook gradients equals the single-device gradient on the concatenated batch, and the per-rank ``grad_z`` already
 is the corresponding slice of the global-batch gradient; no 1/W rescale is needed.
 
-The all-reduce is launched from a post-accumulate-grad hook on the codebook weight, i.e. as soon as the scatter-add
-kernel has been enqueued; NCCL runs it on its own stream, so the rest of the backward pass (quant_conv, encoder)
-overlaps it.  ``wait()`` joins it before the optimizer step.
+The gradient all-reduce is launched from a post-accumulate-grad hook on the codebook weight, i.e. as soon as the
+scatter-add kernel has been enqueued; NCCL runs it on its own stream, so the rest of the backward pass (quant_conv,
+encoder) overlaps it.  ``wait()`` joins it before the optimizer step (stream-ordered, the host does not block).
 """
 from __future__ import annotations
 
@@ -23,7 +24,7 @@ __all__ = ["pack_stats", "unpack_stats", "allreduce_codebook", "DataParallelVQ"]
 
 
 def pack_stats(hist: torch.Tensor, loss: torch.Tensor) -> torch.Tensor:
-    """[hist (K) | loss | 1] as float64 (counts up to 2^53 stay exact under SUM)."""
+    """[hist (K) | loss | 1] as float64 (counts up to 2^53 stay exact under SUM): one buffer, one collective."""
     K = hist.numel()
     buf = torch.empty(K + 2, dtype=torch.float64, device=hist.device)
     buf[:K] = hist
@@ -49,7 +50,7 @@ class DataParallelVQ(torch.nn.Module):
     """Wraps a CodeBook for batch-sharded training.
 
         dp = DataParallelVQ(codebook)             # after dist.init_process_group
-        z_q, idx, loss = dp(z_local)              # local forward; stats all-reduce starts
+        z_q, idx, loss = dp(z_local)              # local forward; histogram / loss all-reduce starts
         (loss + downstream(z_q)).backward()       # grad_E all-reduce starts inside backward, overlapped
         dp.wait()                                 # before optimizer.step(): weight.grad is the global gradient
         dp.global_histogram, dp.global_loss
@@ -64,9 +65,8 @@ class DataParallelVQ(torch.nn.Module):
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         codebook.grad_world_size = self.world_size
         self._pending = []
-        self._stats_buf = None
-        self.global_histogram = None
-        self.global_loss = None
+        self._hist = None
+        self._loss_sum = None
         self.sync_grads = True
         self._hook = codebook.codebook.weight.register_post_accumulate_grad_hook(self._on_grad_ready)
 
@@ -79,9 +79,12 @@ class DataParallelVQ(torch.nn.Module):
         z_q, idx, loss = out
         cb = self.codebook_module
         if loss is not None and cb.last_histogram is not None:
-            self._stats_buf = pack_stats(cb.last_histogram, loss)
+            # the module hands out fresh tensors every call, so they can be reduced in place
+            self._hist = cb.last_histogram
+            self._loss_sum = loss.detach().clone()
             if self.world_size > 1:
-                self._pending.append(dist.all_reduce(self._stats_buf, op=dist.ReduceOp.SUM, group=self.group,
+                self._pending.append(dist.all_reduce(self._hist, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+                self._pending.append(dist.all_reduce(self._loss_sum, op=dist.ReduceOp.SUM, group=self.group,
                                                      async_op=True))
         return out
 
@@ -91,9 +94,14 @@ class DataParallelVQ(torch.nn.Module):
             if w is not None:
                 w.wait()
         self._pending.clear()
-        if self._stats_buf is not None:
-            self.global_histogram, self.global_loss = unpack_stats(self._stats_buf)
-            self._stats_buf = None
+
+    @property
+    def global_histogram(self):
+        return self._hist
+
+    @property
+    def global_loss(self):
+        return None if self._loss_sum is None else self._loss_sum / self.world_size
 
     def no_sync(self):
         """Context manager: skip the gradient all-reduce (gradient-accumulation micro-steps)."""
