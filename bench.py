@@ -66,7 +66,34 @@ class ClockSampler:
         self._stop = threading.Event()
         self._t = None
 
+    def _run_nvml(self) -> bool:
+        """Dense sampling (every ~5 ms) through NVML; returns False when pynvml is unusable."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception:
+            return False
+        bits = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40))
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+            except Exception:
+                break
+            act = ["Active" if r & b else "Not Active" for _, b in bits]
+            # same column order as the nvidia-smi query: hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
+            line = f"{mhz}, {mx}, {pw:.1f}, {act[0]}, {act[3]}, {act[2]}, {act[1]}"
+            self.samples.append((time.time(), line))
+            time.sleep(0.005)
+        return True
+
     def _run(self):
+        if self._run_nvml():
+            return
         try:
             proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                      "--format=csv,noheader,nounits", "-lms", "100"],
@@ -201,7 +228,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg4", choices=list(WORKLOADS))
@@ -345,8 +372,14 @@ def main():
     roofline = None
     if gemm_avg:
         ach = flops / (gemm_avg / 1e3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json"))).get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": "vq_argmin_gemm_kernel", "achieved": ach, "peak": peaks["bf16_tflops"],
-                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": traffic,
+                    "traffic_note": "DRAM bytes of one launch from the committed ncu --set full capture (profiles/)",
                     "kernel_ms": gemm_avg, "kernel_share_of_step": gemm_avg / ms_step,
                     "peak_source": peaks["source"] + ", burst", "peak_sustained": peaks["bf16_tflops_sustained"],
                     "frac_of_sustained": ach / peaks["bf16_tflops_sustained"] if peaks["bf16_tflops_sustained"] else None,
