@@ -133,6 +133,11 @@ int vq_debug_scores(const float* z_nchw, int64_t B, int64_t HW, int D,
                     const void* E_h, const float* e_norm2, const float* cb_scalars, int K,
                     float* scores, void* workspace, size_t workspace_bytes, vq_stream_t stream);
 
+/* Debug: while stamps_dev is non-NULL, vq_argmin / vq_forward calls on this thread run an instrumented GEMM kernel whose
+ * CTA 0 records clock64() stamps for its first `tiles` code tiles, 8 int64 per tile: MMA wait start, MMA wait end,
+ * MMA issued, epilogue(group 0) woke, released, done, epilogue(group 1) released, done. */
+int vq_debug_timeline(long long* stamps_dev, int tiles);
+
 #ifdef __cplusplus
 }
 #endif

@@ -76,6 +76,7 @@ _SIGNATURES = {
     "vq_embed_nchw": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _vp]),
     "vq_profile_enable": (_int, [_int]),
     "vq_profile_collect": (_int, [ctypes.POINTER(_f32), _int, ctypes.POINTER(_int)]),
+    "vq_debug_timeline": (_int, [_vp, _int]),
     "vq_debug_scores": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _int, _vp, _vp, _sz, _vp]),
 }
 

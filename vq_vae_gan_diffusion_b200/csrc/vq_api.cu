@@ -58,6 +58,8 @@ struct Prof {
     int created = 0;
 };
 thread_local Prof g_prof;
+thread_local long long* g_timeline = nullptr;   // debug: device buffer for per-tile clock stamps (vq_debug_timeline)
+thread_local int g_timeline_tiles = 0;
 
 // ---- per-device info (SM count, capability), cached
 struct DevInfo { int sms = 0; int cc = 0; bool attrs_set = false; };
@@ -84,6 +86,8 @@ int device_info(DevInfo** out) {
         VQ_CUDA(cudaFuncSetAttribute(vq::vq_argmin_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)vq::kGemmSmemBytes));
         VQ_CUDA(cudaFuncSetAttribute(vq::vq_argmin_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)vq::kGemmSmemBytes));
+        VQ_CUDA(cudaFuncSetAttribute(vq::vq_argmin_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)vq::kGemmSmemBytes));
         const int bwd_smem = (int)(2 * vq::kBwdTileBytes);
         VQ_CUDA(cudaFuncSetAttribute(vq::vq_backward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
@@ -222,6 +226,8 @@ int run_gemm(const float* z, int64_t N, int64_t HW, const void* E_h, const float
     gp.fb_rows = w.fb_rows;
     gp.fb_count = w.fb_count;
     gp.dbg_scores = dbg_scores;
+    gp.timeline = g_timeline;
+    gp.timeline_tiles = g_timeline_tiles;
     const int grid = gp.row_tiles < dev->sms ? gp.row_tiles : dev->sms;
     VQ_CUDA(cudaMemsetAsync(w.fb_count, 0, sizeof(int32_t), st));
     const bool prof = g_prof.on && g_prof.n < kProfCap;
@@ -233,7 +239,9 @@ int run_gemm(const float* z, int64_t N, int64_t HW, const void* E_h, const float
         }
         VQ_CUDA(cudaEventRecord(g_prof.ev[g_prof.n][0], st));
     }
-    if (dbg_scores)
+    if (g_timeline != nullptr)
+        vq::vq_argmin_gemm_kernel<false, true><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(tm_z, tm_e, gp);
+    else if (dbg_scores)
         vq::vq_argmin_gemm_kernel<true><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(tm_z, tm_e, gp);
     else
         vq::vq_argmin_gemm_kernel<false><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(tm_z, tm_e, gp);
@@ -275,6 +283,12 @@ VQ_EXPORT int vq_profile_collect(float* ms_host, int cap, int* n_host) {
     }
     *n_host = n;
     g_prof.n = 0;
+    return VQ_OK;
+}
+
+VQ_EXPORT int vq_debug_timeline(long long* stamps_dev, int tiles) {
+    g_timeline = stamps_dev;
+    g_timeline_tiles = stamps_dev ? tiles : 0;
     return VQ_OK;
 }
 

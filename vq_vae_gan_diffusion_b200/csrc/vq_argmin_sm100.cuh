@@ -51,6 +51,7 @@ struct GemmSmem {
     float ring_s[kEpiGroups][kRingCap][kRowTile];            // 8 KiB   chunk minima
     float m_part[2][kEpiGroups][kRowTile];                   // 2 KiB   per-group running minima (double buffered)
     int32_t c_part[2][kEpiGroups][kRowTile];                 // 2 KiB   per-group push counts
+    float m_live[kEpiGroups][kRowTile];                      // 1 KiB   running minima, refreshed once per code tile
     alignas(8) uint64_t a_full[kNumDChunks];
     uint64_t a_empty[kNumDChunks];
     uint64_t b_full[kStagesB];
@@ -77,6 +78,8 @@ struct GemmParams {
     int32_t* fb_rows;          // (2N) worklist of the rows flagged -1 (for vq_fallback_kernel)
     int32_t* fb_count;         // (1)  its length, zeroed before launch
     float* dbg_scores;         // (N, K_pad) or null
+    long long* timeline;       // debug: per-tile clock64 stamps of CTA 0 (kTimeline builds), [tile][8]
+    int timeline_tiles;
 };
 
 __device__ __forceinline__ float min3(float a, float b, float c) {
@@ -89,7 +92,7 @@ __device__ __forceinline__ void epi_barrier() {               // the 256 epilogu
     asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
-template <bool kDebugScores>
+template <bool kDebugScores, bool kTimeline = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
                       const GemmParams p) {
@@ -156,15 +159,26 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(kRowTile, kCodeTile);
             uint32_t stage = 0, b_phase = 0, a_phase = 0, buf = 0, t_phase = 0;
+            int tl_seq = 0;
+            long long tl_bwait = 0;
             for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x) {
                 for (int kt = 0; kt < p.k_tiles; kt++) {
+                    long long tl0 = 0;
+                    if (kTimeline) tl0 = clock64();
                     mbar_wait(&s.t_empty[buf], t_phase ^ 1);
                     tc_fence_after();
+                    if (kTimeline && blockIdx.x == 0 && tl_seq < p.timeline_tiles) {
+                        p.timeline[tl_seq * 12 + 0] = tl0;
+                        p.timeline[tl_seq * 12 + 1] = clock64();
+                    }
                     const uint32_t d_tmem = tmem_base + buf * kCodeTile;
                     for (int dc = 0; dc < kNumDChunks; dc++) {
                         if (kt == 0) mbar_wait(&s.a_full[dc], a_phase);
+                        long long tb0 = 0;
+                        if (kTimeline) tb0 = clock64();
                         mbar_wait(&s.b_full[stage], b_phase);
                         tc_fence_after();
+                        if (kTimeline) tl_bwait += clock64() - tb0;
                         const uint64_t adesc = umma_desc_sw128(smem_u32(s.a[dc]));
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[stage]));
 #pragma unroll
@@ -177,6 +191,12 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                         if (++stage == kStagesB) { stage = 0; b_phase ^= 1; }
                     }
                     umma_commit(&s.t_full[buf]);
+                    if (kTimeline && blockIdx.x == 0 && tl_seq < p.timeline_tiles) {
+                        p.timeline[tl_seq * 12 + 2] = clock64();
+                        p.timeline[tl_seq * 12 + 8] = tl_bwait;
+                    }
+                    tl_bwait = 0;
+                    tl_seq++;
                     buf ^= 1;
                     if (buf == 0) t_phase ^= 1;
                 }
@@ -194,11 +214,15 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
         const uint32_t ring_q_sa = smem_u32(&s.ring_q[grp][0][trow]);
         const uint32_t ring_m_sa = smem_u32(&s.ring_m[grp][0][trow]);
         const uint32_t ring_s_sa = smem_u32(&s.ring_s[grp][0][trow]);
+        const uint32_t live_own_sa = smem_u32(&s.m_live[grp][trow]);
+        const uint32_t live_other_sa = smem_u32(&s.m_live[grp ^ 1][trow]);
+        sts_f32(live_own_sa, INFINITY);
+        epi_barrier();
         constexpr uint32_t kSlotStride = kRowTile * 4;
         const float e2max = __ldg(p.cb + 0);
         const float e_inv = __ldg(p.cb + 2);
         uint32_t buf = 0, phase = 0;
-        int rti = 0;
+        int rti = 0, tl_seq = 0;
         for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x, rti++) {
             const int64_t row = (int64_t)rt * kRowTile + trow;
             const bool row_ok = row < p.N;
@@ -213,8 +237,13 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                 mbar_wait(&s.t_full[buf], phase);
                 mbar_wait(&s.e2_full[buf], phase);
                 tc_fence_after();
+                const bool tl_on = kTimeline && blockIdx.x == 0 && lane == 0 && quarter == 2 && tl_seq < p.timeline_tiles;
+                if (tl_on && grp == 0) p.timeline[tl_seq * 12 + 3] = clock64();
                 const uint32_t taddr = t_lane + buf * kCodeTile;
                 const uint32_t e2a = e2_sa[buf];
+                // the other column group's running minimum (possibly one tile stale: still an upper bound of the row
+                // minimum) tightens this group's threshold
+                thr = fminf(thr, fminf(m_run, lds_f32(live_other_sa)) + margin);
 
                 uint32_t acc[2][32];
                 float4 ev[2][8];
@@ -238,6 +267,7 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                             mbar_arrive(&s.t_empty[buf]);
                             mbar_arrive(&s.e2_empty[buf]);
                         }
+                        if (tl_on) p.timeline[tl_seq * 12 + (grp == 0 ? 4 : 6)] = clock64();
                     }
                     float sc[32];
 #pragma unroll
@@ -264,7 +294,7 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                         // slow path: this chunk holds a code within the running threshold -> one ring entry with the
                         // mask of all such codes (only quads whose minimum passes are looked into)
                         m_run = fminf(m_run, cm);
-                        thr = m_run + margin;
+                        thr = fminf(thr, m_run + margin);
                         uint32_t cmask = 0;
 #pragma unroll
                         for (int q = 0; q < 8; q++) {
@@ -282,6 +312,9 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                     }
                     __syncwarp();
                 }
+                sts_f32(live_own_sa, m_run);
+                if (tl_on) p.timeline[tl_seq * 12 + (grp == 0 ? 5 : 7)] = clock64();
+                tl_seq++;
                 buf ^= 1;
                 if (buf == 0) phase ^= 1;
             }
@@ -291,6 +324,7 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
             const int pb = rti & 1;
             s.m_part[pb][grp][trow] = m_run;
             s.c_part[pb][grp][trow] = cnt;
+            sts_f32(live_own_sa, INFINITY);                     // next row tile starts from scratch (before the barrier)
             epi_barrier();
             const float m_fin = fminf(m_run, s.m_part[pb][grp ^ 1][trow]);
             const int cnt_all = cnt + s.c_part[pb][grp ^ 1][trow];

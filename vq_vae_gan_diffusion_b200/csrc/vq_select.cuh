@@ -51,7 +51,7 @@ __device__ __forceinline__ float exact_distance_tile(const TileRow* t, int r, co
                                                      const float* __restrict__ e2, int k, float z2) {
     const float4* e4 = reinterpret_cast<const float4*>(E + (int64_t)k * kD);
     float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
-#pragma unroll 8
+#pragma unroll 16
     for (int q = 0; q < kD / 4; q++) {
         const float4 e = __ldg(e4 + q);
         p0 = __fmaf_rn(t[4 * q + 0][r], e.x, p0);
