@@ -13,13 +13,13 @@ scaling), the configuration the north-star target (>= 60 % of tensor-pipe peak o
 quoted on.  Inputs (268 MB of z + 268 MB of g_out per GPU) exceed the 126 MB L2, so no L2 flush is needed.
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same step driven from pinned host
-buffers (H2D of z and g_out, D2H of loss and indices inside the timed region), `roofline` = the distance-GEMM kernel
-against the measured bf16 tensor peak, `cpu_baseline` = the numpy/BLAS port of the reference timed on this box's
+buffers (H2D of z and g_out -- double buffered on a copy stream -- and D2H of loss and indices inside the timed region), `roofline` = the distance-GEMM kernel
+against the measured bf16 tensor peak, `cpu_baseline` = the torch-CPU port of the reference (same ATen ops) timed on this box's
 host cores on a bounded row sample.
 
 --impl reference: the reference arm.  The reference is pure Python/PyTorch and cannot travel to the GPU box, so this
-arm times the oracle port (oracle/vq_oracle.py: forward_blas/backward_blas, same ATen-style op sequence, BLAS
-sgemm on all host threads) on a bounded sample of the same workload.
+arm times the oracle port (oracle/vq_oracle.py: torch_cpu_step, the same ATen op sequence as codebook.py, on all
+host threads) on a bounded sample of the same workload.
 """
 from __future__ import annotations
 
@@ -328,19 +328,41 @@ def main():
         g_host = None if tok else g_out.permute(0, 2, 3, 1).contiguous().cpu().pin_memory()
         idx_host = torch.empty(N, dtype=torch.int64).pin_memory()
         loss_host = torch.empty((), dtype=torch.float32).pin_memory()
-        z_dev = torch.empty_like(z).requires_grad_(not tok)
-        g_dev_nhwc = None if tok else torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
-        g_dev = None if tok else g_dev_nhwc.permute(0, 3, 1, 2)
+        # Double-buffered input staging: a copy stream uploads step i+1's host buffers while step i computes (what a
+        # real input pipeline does).  Every step's H2D copies and D2H reads are inside the timed region.
+        copy_stream = torch.cuda.Stream(device=dev)
+        slots = []
+        for _ in range(2):
+            zd = torch.empty_like(z).requires_grad_(not tok)
+            gn = None if tok else torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
+            slots.append(dict(z=zd, g_nhwc=gn, g=None if tok else gn.permute(0, 3, 1, 2),
+                              ready=torch.cuda.Event(), free=torch.cuda.Event()))
+        for sl in slots:
+            sl["free"].record()
+        state = {"i": 0, "primed": False}
+
+        def upload(sl):
+            with torch.cuda.stream(copy_stream), torch.no_grad():
+                copy_stream.wait_event(sl["free"])                  # the step that used this slot has finished
+                sl["z"].copy_(z_host, non_blocking=True)
+                if not tok:
+                    sl["g_nhwc"].copy_(g_host, non_blocking=True)
+                sl["ready"].record(copy_stream)
 
         def e2e_step():
-            with torch.no_grad():
-                z_dev.copy_(z_host, non_blocking=True)
-                if not tok:
-                    g_dev_nhwc.copy_(g_host, non_blocking=True)
-            idx, loss = step(z_dev, g_dev)
+            cur = slots[state["i"] & 1]
+            nxt = slots[(state["i"] + 1) & 1]
+            if not state["primed"]:
+                upload(cur)
+                state["primed"] = True
+            upload(nxt)                                             # prefetch the next step's inputs
+            torch.cuda.current_stream().wait_event(cur["ready"])
+            idx, loss = step(cur["z"], cur["g"])
+            cur["free"].record()
             idx_host.copy_(idx, non_blocking=True)
             if loss is not None:
                 loss_host.copy_(loss.detach(), non_blocking=True)
+            state["i"] += 1
 
         for _ in range(2):
             e2e_step()
