@@ -1,7 +1,8 @@
 // vq_select.cuh -- exact fp32 decision + fused forward tail, and the exact full-row fallback.
 //
 // vq_select_kernel<kForward>: one CTA = 32 latents (8 warps, 4 rows per warp).
-//   1. load the fp32 z tile once (coalesced along hw) into shared memory
+//   1. expand the candidate entries, then load the fp32 z tile once (16-byte loads along hw) into shared memory
+//      (skipped in tokeniser mode when every row of the CTA has a single candidate)
 //   2. expand the candidate entries (32-code chunk + quad mask) written by the GEMM epilogue into quads, then
 //      recompute the distance of every candidate code with the reference's fp32 formula (codebook.py:70-79) in
 //      the oracle's canonical accumulation order -- one thread per (row, code): a warp pass covers 4 rows x 8 codes,
@@ -77,9 +78,6 @@ vq_select_kernel(const SelectParams p) {
     const int64_t n0 = (int64_t)blockIdx.x * kSelRows;
     if (tid < 4) st_s[tid] = 0;
 
-    // 1. z tile
-    load_tile_nchw<kVec, false>(t, p.z, n0, p.N, p.HW, warp, lane);
-
     // 2a. expand this warp's candidate entries into quads (independent of the z tile)
     int nq[4];
     unsigned resolved_mask = 0;                               // rows decided by vq_fallback_kernel (stats counted there)
@@ -112,6 +110,12 @@ vq_select_kernel(const SelectParams p) {
         }
         nq[rr] = min(kMaxCands, __shfl_sync(0xffffffffu, incl, 31));
     }
+
+    // 1. z tile (fp32): always needed by the forward tail; in tokeniser mode only when some row of this CTA has more
+    //    than one candidate and therefore needs exact distances
+    const int need_exact = (nq[0] > 1) | (nq[1] > 1) | (nq[2] > 1) | (nq[3] > 1);
+    const bool want_tile = kForward ? true : (__syncthreads_or(need_exact) != 0);
+    if (want_tile) load_tile_nchw<kVec, false>(t, p.z, n0, p.N, p.HW, warp, lane);
     __syncthreads();
 
     // 2b. exact distances: lane = 8*rr + c -> row rr of this warp, code slot c (two quads per pass and row)
@@ -121,13 +125,20 @@ vq_select_kernel(const SelectParams p) {
         const int64_t n = n0 + r;
         const bool row_ok = n < p.N;
         const int my_nq = (rr == 0) ? nq[0] : (rr == 1) ? nq[1] : (rr == 2) ? nq[2] : nq[3];
-        const int max_nq = max(max(nq[0], nq[1]), max(nq[2], nq[3]));
+        // a row with a single candidate is decided without any arithmetic (the margin argument guarantees the
+        // oracle's argmin is among the candidates), so only rows with >= 2 candidates take part in the passes
+        const int max_nq = max(max(nq[0] > 1 ? nq[0] : 0, nq[1] > 1 ? nq[1] : 0), max(nq[2] > 1 ? nq[2] : 0, nq[3] > 1 ? nq[3] : 0));
         const float z2 = row_ok ? __ldg(p.z2 + n) : 0.0f;
         const unsigned seg = 0xffu << (rr * 8);
         float best_d = INFINITY;
         int best_k = 0x7fffffff, n_at_min = 0;
+        if (my_nq == 1) {
+            best_k = clist[warp][rr][0];
+            if (best_k >= p.K) best_k = 0;
+            n_at_min = 1;
+        }
         for (int base = 0; base < max_nq; base += 8) {
-            int k = (base + c < my_nq) ? clist[warp][rr][base + c] : -1;
+            int k = (my_nq > 1 && base + c < my_nq) ? clist[warp][rr][base + c] : -1;
             if (k >= p.K) k = -1;                              // pad codes of the last chunk
             float dist = INFINITY;
             if (k >= 0) dist = exact_distance_tile(t, r, p.E, p.e2, k, z2);
