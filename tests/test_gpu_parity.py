@@ -240,6 +240,25 @@ def test_backward_gout_layouts(vq, oracle):
     assert_close(zt.grad.cpu().numpy(), gz0, "grad_z (loss only)")
 
 
+@pytest.mark.parametrize("B,H,W,K", [(1, 1, 1, 1), (1, 1, 1, 7), (5, 1, 3, 257), (1, 3, 32, 513), (2, 2, 48, 1), (3, 7, 11, 1025)])
+def test_edge_shapes_vs_oracle(B, H, W, K, vq, oracle):
+    """Minimum sizes, K crossing code-tile boundaries, N not a multiple of any tile, vector and scalar tile paths."""
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(1000 + B * 131 + H * 17 + W * 3 + K)
+    E = rng.standard_normal((K, 256)).astype(np.float32)
+    z = rng.standard_normal((B, 256, H, W)).astype(np.float32)
+    g = rng.standard_normal((B, H, W, 256)).astype(np.float32)
+    got = run_module(vq, z, E, g)
+    ref = oracle.forward(z, E)
+    assert np.array_equal(got["idx"], ref["idx"])
+    assert np.array_equal(got["hist"], ref["hist"])
+    assert np.array_equal(got["zq_rows"], ref["zq_nhwc"])
+    assert abs(got["loss"] - float(ref["loss"])) <= 1e-6 * abs(float(ref["loss"]))
+    gz, gE = oracle.backward(np.transpose(g, (0, 3, 1, 2)), 1.0, z, ref["idx"], E)
+    assert_close(got["grad_z"], gz, "grad_z")
+    assert_close(got["grad_E"], gE, "grad_E")
+
+
 def test_degenerate_codebook_mass_fallback(vq, oracle):
     """Every row overflows its candidate list (identical codes): the exact fallback decides all of them, including
     the worklist tail beyond the split-scan capacity; torch.argmin semantics -> lowest index of the tied minimum."""
