@@ -156,7 +156,10 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.  Issuing from inside an
+        // `if (lane == 0)` region makes the compiler wrap every uniform-datapath instruction (UTCHMMA, UTCBAR) in an
+        // elect/broadcast loop, which lengthens the issue path that paces the tensor pipe.
+        {
             constexpr uint32_t idesc = umma_idesc_f16(kRowTile, kCodeTile);
             uint32_t stage = 0, b_phase = 0, a_phase = 0, buf = 0, t_phase = 0;
             int tl_seq = 0;
@@ -167,7 +170,7 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                     if (kTimeline) tl0 = clock64();
                     mbar_wait(&s.t_empty[buf], t_phase ^ 1);
                     tc_fence_after();
-                    if (kTimeline && blockIdx.x == 0 && tl_seq < p.timeline_tiles) {
+                    if (kTimeline && lane == 0 && blockIdx.x == 0 && tl_seq < p.timeline_tiles) {
                         p.timeline[tl_seq * 12 + 0] = tl0;
                         p.timeline[tl_seq * 12 + 1] = clock64();
                     }
@@ -181,17 +184,20 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                         if (kTimeline) tl_bwait += clock64() - tb0;
                         const uint64_t adesc = umma_desc_sw128(smem_u32(s.a[dc]));
                         const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[stage]));
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < kDChunk / 16; k++) {
-                            // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-                            umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dc | k) != 0);
+                            for (int k = 0; k < kDChunk / 16; k++) {
+                                // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+                                umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dc | k) != 0);
+                            }
+                            umma_commit(&s.b_empty[stage]);
+                            if (kt == p.k_tiles - 1) umma_commit(&s.a_empty[dc]);
+                            if (dc == kNumDChunks - 1) umma_commit(&s.t_full[buf]);
                         }
-                        umma_commit(&s.b_empty[stage]);
-                        if (kt == p.k_tiles - 1) umma_commit(&s.a_empty[dc]);
+                        __syncwarp();
                         if (++stage == kStagesB) { stage = 0; b_phase ^= 1; }
                     }
-                    umma_commit(&s.t_full[buf]);
-                    if (kTimeline && blockIdx.x == 0 && tl_seq < p.timeline_tiles) {
+                    if (kTimeline && lane == 0 && blockIdx.x == 0 && tl_seq < p.timeline_tiles) {
                         p.timeline[tl_seq * 12 + 2] = clock64();
                         p.timeline[tl_seq * 12 + 8] = tl_bwait;
                     }
