@@ -34,7 +34,8 @@ constexpr int kStagesB = 4;
 constexpr int kEpiGroups = 2;
 constexpr int kGroupCols = kCodeTile / kEpiGroups;           // 128 accumulator columns per epilogue group
 constexpr int kChunk = 32;                                   // codes per tcgen05.ld / per candidate entry
-constexpr int kGemmThreads = 64 + kEpiGroups * 128;         // 320
+constexpr int kGemmThreads = 64 + kEpiGroups * 128 + 32;    // 352: TMA, MMA-even, 8 epilogue warps, MMA-odd
+constexpr int kMmaWarpB = 2 + 4 * kEpiGroups;                // warp 10
 constexpr uint32_t kBytesAChunk = kRowTile * kDChunk * 2;    // 16 KiB
 constexpr uint32_t kBytesBStage = kCodeTile * kDChunk * 2;   // 32 KiB
 constexpr uint32_t kBytesE2Tile = kCodeTile * 4;             // 1 KiB
@@ -54,7 +55,7 @@ struct GemmSmem {
     float m_live[kEpiGroups][kRowTile];                      // 1 KiB   running minima, refreshed once per code tile
     alignas(8) uint64_t a_full[kNumDChunks];
     uint64_t a_empty[kNumDChunks];
-    uint64_t b_full[kStagesB];
+    uint64_t b_full[2][kStagesB];        // one set per tile parity: each MMA warp sees every phase of its own set
     uint64_t b_empty[kStagesB];
     uint64_t t_full[2];
     uint64_t t_empty[2];
@@ -63,6 +64,7 @@ struct GemmSmem {
     uint32_t tmem_base;
 };
 constexpr size_t kGemmSmemBytes = sizeof(GemmSmem) + 1024;   // + slack for manual 1024 B alignment
+static_assert(kStagesB == kNumDChunks, "the MMA issuers assume the operand ring holds exactly one code tile");
 static_assert(kGemmSmemBytes <= 232448, "exceeds the 227 KiB of shared memory a CTA can opt into");
 
 struct GemmParams {
@@ -106,7 +108,7 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
         tma_prefetch_desc(&tmap_z);
         tma_prefetch_desc(&tmap_e);
         for (int i = 0; i < kNumDChunks; i++) { mbar_init(&s.a_full[i], 1); mbar_init(&s.a_empty[i], 1); }
-        for (int i = 0; i < kStagesB; i++) { mbar_init(&s.b_full[i], 1); mbar_init(&s.b_empty[i], 1); }
+        for (int i = 0; i < kStagesB; i++) { mbar_init(&s.b_full[0][i], 1); mbar_init(&s.b_full[1][i], 1); mbar_init(&s.b_empty[i], 1); }
         for (int i = 0; i < 2; i++) {
             mbar_init(&s.t_full[i], 1);
             mbar_init(&s.t_empty[i], 4 * kEpiGroups);
@@ -130,8 +132,10 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
             const uint64_t pol_keep = policy_evict_last();    // codebook tiles are re-read by every CTA
             const uint64_t pol_stream = policy_evict_first(); // z tiles are read exactly once
             uint32_t stage = 0, b_phase = 0, a_phase = 0, buf = 0, e_phase = 0;
+            long long it = 0;                                   // global code-tile counter of this CTA
             for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x) {
-                for (int kt = 0; kt < p.k_tiles; kt++) {
+                for (int kt = 0; kt < p.k_tiles; kt++, it++) {
+                    uint64_t* const bfull = s.b_full[it & 1];
                     for (int dc = 0; dc < kNumDChunks; dc++) {
                         if (kt == 0) {
                             mbar_wait(&s.a_empty[dc], a_phase ^ 1);
@@ -139,8 +143,8 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                             tma_load_2d_hint(s.a[dc], &tmap_z, dc * kDChunk, rt * kRowTile, &s.a_full[dc], pol_stream);
                         }
                         mbar_wait(&s.b_empty[stage], b_phase ^ 1);
-                        mbar_expect_tx(&s.b_full[stage], kBytesBStage);
-                        tma_load_2d_hint(s.b[stage], &tmap_e, dc * kDChunk, kt * kCodeTile, &s.b_full[stage], pol_keep);
+                        mbar_expect_tx(&bfull[stage], kBytesBStage);
+                        tma_load_2d_hint(s.b[stage], &tmap_e, dc * kDChunk, kt * kCodeTile, &bfull[stage], pol_keep);
                         if (++stage == kStagesB) { stage = 0; b_phase ^= 1; }
                     }
                     // |e|^2 of this code tile, issued after its operand stages so that waiting for the epilogue to
@@ -154,59 +158,67 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                 a_phase ^= 1;
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.  Issuing from inside an
-        // `if (lane == 0)` region makes the compiler wrap every uniform-datapath instruction (UTCHMMA, UTCBAR) in an
-        // elect/broadcast loop, which lengthens the issue path that paces the tensor pipe.
+    } else if (warp == 1 || warp == kMmaWarpB) {
+        // ------------------------------------------------------------------ MMA issuers (two warps, alternating tiles)
+        // The issuing thread paces the tensor pipe, and every barrier it has to look at (TMEM buffer, operand stages)
+        // costs ~100 cycles even when already complete.  Two warps therefore alternate code tiles -- warp 1 the even
+        // ones (accumulator buffer 0), warp kMmaWarpB the odd ones (buffer 1): while one issues its 16 MMAs the other
+        // is already through the waits of the next tile.  No ordering is needed between the two: they write different
+        // accumulators, tcgen05.commit tracks only the committing thread's MMAs, and the operand ring itself orders
+        // tile j+1's use of a stage after tile j's (the stage is re-filled only after tile j's MMA on it completed).
+        // Each whole warp walks its loop (warp-uniform control flow) and one elected lane issues: issuing from an
+        // `if (lane == 0)` region makes the compiler wrap every uniform-datapath instruction in an elect/broadcast loop.
         {
             constexpr uint32_t idesc = umma_idesc_f16(kRowTile, kCodeTile);
-            uint32_t stage = 0, b_phase = 0, a_phase = 0, buf = 0, t_phase = 0;
-            int tl_seq = 0;
-            long long tl_bwait = 0;
-            for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x) {
-                for (int kt = 0; kt < p.k_tiles; kt++) {
+            const uint32_t buf = (warp == 1) ? 0u : 1u;
+            const uint32_t d_tmem = tmem_base + buf * kCodeTile;
+            long long it = 0;                                   // global code-tile counter of this CTA
+            int rti = 0, tl_seq = 0;
+            for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x, rti++) {
+                // both warps look at every row tile's z chunks (even when a short codebook gives a warp no code tile in
+                // this row tile): an mbarrier parity wait must never fall a whole phase behind
+#pragma unroll
+                for (int dc = 0; dc < kNumDChunks; dc++) mbar_wait(&s.a_full[dc], rti & 1);
+                for (int kt = 0; kt < p.k_tiles; kt++, it++) {
+                    if ((uint32_t)(it & 1) != buf) continue;
+                    const uint32_t use = (uint32_t)(it >> 1);    // how often this buffer was used before
                     long long tl0 = 0;
                     if (kTimeline) tl0 = clock64();
-                    mbar_wait(&s.t_empty[buf], t_phase ^ 1);
+                    mbar_wait(&s.t_empty[buf], (use & 1) ^ 1);
                     tc_fence_after();
-                    if (kTimeline && lane == 0 && blockIdx.x == 0 && tl_seq < p.timeline_tiles) {
-                        p.timeline[tl_seq * 12 + 0] = tl0;
-                        p.timeline[tl_seq * 12 + 1] = clock64();
+                    if (kTimeline && lane == 0 && blockIdx.x == 0 && it < p.timeline_tiles) {
+                        p.timeline[it * 12 + 0] = tl0;
+                        p.timeline[it * 12 + 1] = clock64();
                     }
-                    const uint32_t d_tmem = tmem_base + buf * kCodeTile;
+                    long long tl_bwait = 0;
+#pragma unroll
                     for (int dc = 0; dc < kNumDChunks; dc++) {
-                        if (kt == 0) mbar_wait(&s.a_full[dc], a_phase);
+                        // the ring holds exactly one code tile: stage == dc, and its parity flips every tile
                         long long tb0 = 0;
                         if (kTimeline) tb0 = clock64();
-                        mbar_wait(&s.b_full[stage], b_phase);
+                        mbar_wait(&s.b_full[buf][dc], use & 1);
                         tc_fence_after();
                         if (kTimeline) tl_bwait += clock64() - tb0;
                         const uint64_t adesc = umma_desc_sw128(smem_u32(s.a[dc]));
-                        const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[stage]));
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[dc]));
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < kDChunk / 16; k++) {
                                 // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
                                 umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dc | k) != 0);
                             }
-                            umma_commit(&s.b_empty[stage]);
+                            umma_commit(&s.b_empty[dc]);
                             if (kt == p.k_tiles - 1) umma_commit(&s.a_empty[dc]);
                             if (dc == kNumDChunks - 1) umma_commit(&s.t_full[buf]);
                         }
                         __syncwarp();
-                        if (++stage == kStagesB) { stage = 0; b_phase ^= 1; }
                     }
-                    if (kTimeline && lane == 0 && blockIdx.x == 0 && tl_seq < p.timeline_tiles) {
-                        p.timeline[tl_seq * 12 + 2] = clock64();
-                        p.timeline[tl_seq * 12 + 8] = tl_bwait;
+                    if (kTimeline && lane == 0 && blockIdx.x == 0 && it < p.timeline_tiles) {
+                        p.timeline[it * 12 + 2] = clock64();
+                        p.timeline[it * 12 + 8] = tl_bwait;
                     }
-                    tl_bwait = 0;
-                    tl_seq++;
-                    buf ^= 1;
-                    if (buf == 0) t_phase ^= 1;
+                    (void)tl_seq;
                 }
-                a_phase ^= 1;
             }
         }
     } else {
