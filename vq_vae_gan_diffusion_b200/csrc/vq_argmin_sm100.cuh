@@ -128,7 +128,8 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
-        if (lane == 0) {
+        // (whole warp in the loop, one elected lane issues: see the note on the MMA warps)
+        {
             const uint64_t pol_keep = policy_evict_last();    // codebook tiles are re-read by every CTA
             const uint64_t pol_stream = policy_evict_first(); // z tiles are read exactly once
             uint32_t stage = 0, b_phase = 0, a_phase = 0, buf = 0, e_phase = 0;
@@ -139,19 +140,28 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                     for (int dc = 0; dc < kNumDChunks; dc++) {
                         if (kt == 0) {
                             mbar_wait(&s.a_empty[dc], a_phase ^ 1);
-                            mbar_expect_tx(&s.a_full[dc], kBytesAChunk);
-                            tma_load_2d_hint(s.a[dc], &tmap_z, dc * kDChunk, rt * kRowTile, &s.a_full[dc], pol_stream);
+                            if (elect_one()) {
+                                mbar_expect_tx(&s.a_full[dc], kBytesAChunk);
+                                tma_load_2d_hint(s.a[dc], &tmap_z, dc * kDChunk, rt * kRowTile, &s.a_full[dc], pol_stream);
+                            }
+                            __syncwarp();
                         }
                         mbar_wait(&s.b_empty[stage], b_phase ^ 1);
-                        mbar_expect_tx(&bfull[stage], kBytesBStage);
-                        tma_load_2d_hint(s.b[stage], &tmap_e, dc * kDChunk, kt * kCodeTile, &bfull[stage], pol_keep);
+                        if (elect_one()) {
+                            mbar_expect_tx(&bfull[stage], kBytesBStage);
+                            tma_load_2d_hint(s.b[stage], &tmap_e, dc * kDChunk, kt * kCodeTile, &bfull[stage], pol_keep);
+                        }
+                        __syncwarp();
                         if (++stage == kStagesB) { stage = 0; b_phase ^= 1; }
                     }
                     // |e|^2 of this code tile, issued after its operand stages so that waiting for the epilogue to
                     // release the buffer (two tiles back) never delays an operand load
                     mbar_wait(&s.e2_empty[buf], e_phase ^ 1);
-                    mbar_expect_tx(&s.e2_full[buf], kBytesE2Tile);
-                    bulk_load_1d(s.e2s[buf], p.e2 + (int64_t)kt * kCodeTile, kBytesE2Tile, &s.e2_full[buf]);
+                    if (elect_one()) {
+                        mbar_expect_tx(&s.e2_full[buf], kBytesE2Tile);
+                        bulk_load_1d(s.e2s[buf], p.e2 + (int64_t)kt * kCodeTile, kBytesE2Tile, &s.e2_full[buf]);
+                    }
+                    __syncwarp();
                     buf ^= 1;
                     if (buf == 0) e_phase ^= 1;
                 }
