@@ -37,7 +37,18 @@ def debug_scores(z: torch.Tensor, E: torch.Tensor):
     _native.check(L.vq_debug_scores(z.data_ptr(), B, H * W, D, E_h.data_ptr(), e2.data_ptr(), cb.data_ptr(), K,
                                     scores.data_ptr(), ws.data_ptr(), ws.numel(), st), "debug_scores")
     torch.cuda.synchronize()
-    return scores, E_h, e2, cb
+    return scores, untile_operand(E_h, 256), e2, cb
+
+
+def untile_operand(img: torch.Tensor, rows: int) -> torch.Tensor:
+    """Operand image [tile][D chunk][rows][8 pieces ^ (row & 7)][8 halves] -> row-major (n_rows, 256)."""
+    n = img.numel() // 256
+    x = img.reshape(n // rows, 4, rows, 8, 8)
+    r = torch.arange(rows, device=img.device)
+    j = torch.arange(8, device=img.device)
+    phys = (j[None, :] ^ (r[:, None] & 7))                                  # physical piece holding logical piece j
+    idx = phys[None, None, :, :, None].expand(x.shape[0], 4, rows, 8, 8)
+    return torch.gather(x, 3, idx).permute(0, 2, 1, 3, 4).reshape(n, 256)
 
 
 def expected_scores(z: torch.Tensor, E: torch.Tensor, E_h, e2, cb):

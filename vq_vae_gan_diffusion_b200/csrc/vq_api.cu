@@ -100,43 +100,6 @@ int device_info(DevInfo** out) {
     return VQ_OK;
 }
 
-// ---- TMA descriptors.  cuTensorMapEncodeTiled is resolved through the runtime so the library has no link-time
-// dependency on libcuda (it must load on the GPU-less build box).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn g_encode = nullptr;
-
-int get_encode(EncodeTiledFn* out) {
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_encode == nullptr) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess)
-            return fail(VQ_E_DEVICE, "cuTensorMapEncodeTiled not available from the driver (%s)", cudaGetErrorString(e));
-        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
-    }
-    *out = g_encode;
-    return VQ_OK;
-}
-
-// (rows, 256) fp16 row-major matrix, box = (box_rows, 64 elements = 128 bytes), SWIZZLE_128B
-int make_tmap(CUtensorMap* m, const void* base, int64_t rows, int box_rows) {
-    EncodeTiledFn enc;
-    int rc = get_encode(&enc);
-    if (rc != VQ_OK) return rc;
-    cuuint64_t dims[2] = {(cuuint64_t)vq::kD, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)vq::kD * 2};
-    cuuint32_t box[2] = {(cuuint32_t)vq::kDChunk, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(VQ_E_INVALID, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return VQ_OK;
-}
-
 // ---- workspace layout
 struct Workspace {
     __half* z_h;            // (N_pad, D)
@@ -207,13 +170,9 @@ int run_gemm(const float* z, int64_t N, int64_t HW, const void* E_h, const float
                                                                                                    w.z2, w.z_inv_scale);
     VQ_LAUNCH_CHECK("vq_prep_z_kernel");
 
-    CUtensorMap tm_z, tm_e;
-    rc = make_tmap(&tm_z, w.z_h, n_pad, vq::kRowTile);
-    if (rc != VQ_OK) return rc;
-    rc = make_tmap(&tm_e, E_h, k_pad, vq::kCodeTile);
-    if (rc != VQ_OK) return rc;
-
     vq::GemmParams gp;
+    gp.z_h = w.z_h;
+    gp.e_h = static_cast<const __half*>(E_h);
     gp.e2 = e2;
     gp.cb = cb;
     gp.z2 = w.z2;
@@ -240,11 +199,11 @@ int run_gemm(const float* z, int64_t N, int64_t HW, const void* E_h, const float
         VQ_CUDA(cudaEventRecord(g_prof.ev[g_prof.n][0], st));
     }
     if (g_timeline != nullptr)
-        vq::vq_argmin_gemm_kernel<false, true><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(tm_z, tm_e, gp);
+        vq::vq_argmin_gemm_kernel<false, true><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(gp);
     else if (dbg_scores)
-        vq::vq_argmin_gemm_kernel<true><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(tm_z, tm_e, gp);
+        vq::vq_argmin_gemm_kernel<true><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(gp);
     else
-        vq::vq_argmin_gemm_kernel<false><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(tm_z, tm_e, gp);
+        vq::vq_argmin_gemm_kernel<false><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(gp);
     VQ_LAUNCH_CHECK("vq_argmin_gemm_kernel");
     if (prof) {
         VQ_CUDA(cudaEventRecord(g_prof.ev[g_prof.n][1], st));

@@ -8,9 +8,11 @@
 // first minimum.
 //
 // CTA = 10 warps, persistent over row tiles (128 latents each):
-//   warp 0      TMA producer: A = z tile (4 chunks of [128 x 64] fp16, SWIZZLE_128B) once per row tile,
-//               B = codebook tile ([256 codes x 64] fp16 per stage) through a 4-stage ring, and the |e|^2 slice of
-//               every code tile (1 KiB bulk copy) into a double buffer.
+//   warp 0      TMA producer (cp.async.bulk): A = z tile (4 chunks of [128 x 64] fp16) once per row tile, B = codebook
+//               tile ([256 codes x 64] fp16 = 32 KiB per stage) through a 4-stage ring, and the |e|^2 slice of every
+//               code tile (1 KiB) into a double buffer.  Both operands are stored in global memory as ready-made
+//               SWIZZLE_128B shared-memory images (vq_prep.cuh), so every stage is ONE contiguous bulk copy instead of
+//               256 strided 128-byte rows of a tensor-map box.
 //   warp 1      TMEM allocator + MMA issuer: per code tile 16 x tcgen05.mma (M128 N256 K16) into one of two
 //               256-column fp32 accumulators (the epilogue of tile j overlaps the MMAs of tile j+1).
 //   warps 2..5  epilogue group 0: columns [0, 128) of every accumulator tile
@@ -68,6 +70,8 @@ static_assert(kStagesB == kNumDChunks, "the MMA issuers assume the operand ring 
 static_assert(kGemmSmemBytes <= 232448, "exceeds the 227 KiB of shared memory a CTA can opt into");
 
 struct GemmParams {
+    const __half* z_h;         // operand image of the latents  [row tile][D chunk][128][64] (vq_prep.cuh)
+    const __half* e_h;         // operand image of the codebook [code tile][D chunk][256][64]
     const float* e2;           // (K_pad) |e_k|^2, +inf on pad rows
     const float* cb;           // codebook scalars (vq_prep.cuh)
     const float* z2;           // (N)
@@ -96,8 +100,7 @@ __device__ __forceinline__ void epi_barrier() {               // the 256 epilogu
 
 template <bool kDebugScores, bool kTimeline = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_constant__ CUtensorMap tmap_e,
-                      const GemmParams p) {
+vq_argmin_gemm_kernel(const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     GemmSmem& s = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -105,8 +108,6 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_z);
-        tma_prefetch_desc(&tmap_e);
         for (int i = 0; i < kNumDChunks; i++) { mbar_init(&s.a_full[i], 1); mbar_init(&s.a_empty[i], 1); }
         for (int i = 0; i < kStagesB; i++) { mbar_init(&s.b_full[0][i], 1); mbar_init(&s.b_full[1][i], 1); mbar_init(&s.b_empty[i], 1); }
         for (int i = 0; i < 2; i++) {
@@ -142,14 +143,16 @@ vq_argmin_gemm_kernel(const __grid_constant__ CUtensorMap tmap_z, const __grid_c
                             mbar_wait(&s.a_empty[dc], a_phase ^ 1);
                             if (elect_one()) {
                                 mbar_expect_tx(&s.a_full[dc], kBytesAChunk);
-                                tma_load_2d_hint(s.a[dc], &tmap_z, dc * kDChunk, rt * kRowTile, &s.a_full[dc], pol_stream);
+                                bulk_load_1d_hint(s.a[dc], p.z_h + ((int64_t)rt * kNumDChunks + dc) * (kRowTile * kDChunk),
+                                                  kBytesAChunk, &s.a_full[dc], pol_stream);
                             }
                             __syncwarp();
                         }
                         mbar_wait(&s.b_empty[stage], b_phase ^ 1);
                         if (elect_one()) {
                             mbar_expect_tx(&bfull[stage], kBytesBStage);
-                            tma_load_2d_hint(s.b[stage], &tmap_e, dc * kDChunk, kt * kCodeTile, &bfull[stage], pol_keep);
+                            bulk_load_1d_hint(s.b[stage], p.e_h + ((int64_t)kt * kNumDChunks + dc) * (kCodeTile * kDChunk),
+                                              kBytesBStage, &bfull[stage], pol_keep);
                         }
                         __syncwarp();
                         if (++stage == kStagesB) { stage = 0; b_phase ^= 1; }

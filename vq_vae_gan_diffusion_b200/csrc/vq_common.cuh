@@ -68,6 +68,13 @@ __device__ __forceinline__ void load_tile_nchw(TileRow* t, const float* __restri
     }
 }
 
+// Offset (in 16-bit elements) of element (row, dl) -- dl in [0, 64) -- of block `block` in an "operand image": blocks of
+// `rows` x 64 elements stored exactly as a SWIZZLE_128B K-major UMMA operand sits in shared memory (row pitch 128 B,
+// the eight 16-byte pieces of a row XOR-ed with (row & 7)).  A block is contiguous, so it is loaded with one bulk copy.
+__host__ __device__ __forceinline__ int64_t operand_image_offset(int64_t block, int rows, int row, int dl) {
+    return block * (int64_t)rows * kDChunk + (int64_t)row * kDChunk + ((((dl >> 3) ^ (row & 7)) << 3) | (dl & 7));
+}
+
 // Canonical-order dot product pieces (oracle/vq_oracle.c: vqo_dot): partial j sums the terms d == j (mod 4)
 // in ascending d with one fma each; the result is (p0 + p1) + (p2 + p3).
 __device__ __forceinline__ float combine4(float p) {

@@ -29,8 +29,14 @@ vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_p
     const int64_t n0 = (int64_t)blockIdx.x * kSelRows;
 
     if (kVec && n0 >= N) {                                   // pad rows of the last GEMM row tile: zero operand rows
-        for (int i = tid; i < kSelRows * kD / 2; i += kPrepThreads)
-            if (n0 * kD / 2 + i < n_pad * kD / 2) reinterpret_cast<__half2*>(z_h + n0 * kD)[i] = __floats2half2_rn(0.f, 0.f);
+        // (a 32-row slab of a row tile is not contiguous in the operand image: zero it piecewise)
+        for (int i = tid; i < kSelRows * kD / 2; i += kPrepThreads) {
+            const int r = i / (kD / 2), d = 2 * (i % (kD / 2));
+            const int64_t n = n0 + r;
+            if (n < n_pad)
+                *reinterpret_cast<__half2*>(z_h + operand_image_offset((n / kRowTile) * kNumDChunks + d / kDChunk, kRowTile,
+                                                                       (int)(n % kRowTile), d % kDChunk)) = __floats2half2_rn(0.f, 0.f);
+        }
         return;
     }
     load_tile_nchw<kVec, false>(t, z, n0, N, HW, warp, lane);
@@ -64,11 +70,15 @@ vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_p
         const int64_t n = n0 + r;
         if (n >= n_pad) break;
         const float sc = scale_s[r];
-        __half2* dst = reinterpret_cast<__half2*>(z_h + n * kD);
+        // operand image: [row tile][64-wide D chunk][128 rows][128 B], 16-byte pieces XOR-swizzled by (row & 7) -- the
+        // exact shared-memory image of a SWIZZLE_128B K-major UMMA operand, so a chunk is ONE contiguous bulk copy
+        const int64_t rt = n / kRowTile;
+        const int rr_t = (int)(n % kRowTile);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < kNumDChunks; i++) {
             const int d = 2 * lane + 64 * i;
-            dst[d >> 1] = __floats2half2_rn(t[d][r] * sc, t[d + 1][r] * sc);   // rows >= N were zero-filled above
+            __half2* dst = reinterpret_cast<__half2*>(z_h + operand_image_offset(rt * kNumDChunks + i, kRowTile, rr_t, 2 * lane));
+            *dst = __floats2half2_rn(t[d][r] * sc, t[d + 1][r] * sc);   // rows >= N were zero-filled above
         }
     }
 }
@@ -136,14 +146,16 @@ vq_codebook_convert_kernel(const float* __restrict__ E, int K, int k_pad, __half
     for (int rr = 0; rr < 4; rr++) {
         const int k = k0 + warp * 4 + rr;
         if (k >= k_pad) break;
-        __half2* dst = reinterpret_cast<__half2*>(e_h + (int64_t)k * kD);
         const float2* src = reinterpret_cast<const float2*>(E + (int64_t)k * kD);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int d2 = lane + 32 * i;                       // float2 index: d = 2*d2
+        for (int i = 0; i < kNumDChunks; i++) {
+            const int d2 = lane + 32 * i;                       // float2 index: d = 2*d2 = 64*i + 2*lane
             float2 v = make_float2(0.0f, 0.0f);
             if (k < K) v = __ldg(src + d2);
-            dst[d2] = __floats2half2_rn(v.x * sc, v.y * sc);
+            // operand image: [code tile][64-wide D chunk][256 codes][128 B] with the SWIZZLE_128B pattern (see prep_z)
+            __half2* dst = reinterpret_cast<__half2*>(
+                e_h + operand_image_offset((int64_t)(k / kCodeTile) * kNumDChunks + i, kCodeTile, k % kCodeTile, 2 * lane));
+            *dst = __floats2half2_rn(v.x * sc, v.y * sc);
         }
     }
 }
