@@ -276,37 +276,47 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                 // minimum) tightens this group's threshold
                 thr = fminf(thr, fminf(m_run, lds_f32(live_other_sa)) + margin);
 
-                uint32_t acc[2][32];
+                // The accumulator buffer must go back to the MMA warps EARLY: a buffer cycles MMA -> drain -> MMA and the
+                // next MMA on it is due one tile time after the previous one ended.  All four 32-column loads of this
+                // warp are therefore issued within its first two chunks (three register buffers; tcgen05.wait::ld
+                // waits for everything outstanding), and the buffer is released at the start of the third chunk.
+                static_assert(kGroupCols / kChunk == 4, "load schedule below is written for four chunks per warp");
+                uint32_t acc[3][32];
                 float4 ev[2][8];
                 tmem_ld32(taddr, acc[0]);
+                tmem_ld32(taddr + kChunk, acc[1]);
 #pragma unroll
                 for (int q = 0; q < 8; q++) ev[0][q] = lds128(e2a + q * 16);
 #pragma unroll
                 for (int c = 0; c < kGroupCols / kChunk; c++) {
                     const int h = c & 1;
-                    tmem_ld_wait();
+                    const int ab = c % 3;
+                    if (c == 0) {
+                        tmem_ld_wait();                                 // chunks 0 and 1 are in registers
+                        tmem_ld32(taddr + 2 * kChunk, acc[2]);
+                    } else if (c == 1) {
+                        tmem_ld32(taddr + 3 * kChunk, acc[0]);          // acc[0] was consumed by chunk 0
+                    } else if (c == 2) {
+                        tmem_ld_wait();                                 // chunks 2 and 3 are in registers:
+                        tc_fence_before();                              // release the accumulator buffer to the MMA warps
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&s.t_empty[buf]);
+                        if (tl_on) p.timeline[tl_seq * 12 + (grp == 0 ? 4 : 6)] = clock64();
+                    }
                     if (c + 1 < kGroupCols / kChunk) {
-                        // prefetch the next chunk (accumulators and |e|^2) while this one is reduced
-                        tmem_ld32(taddr + (c + 1) * kChunk, acc[h ^ 1]);
 #pragma unroll
                         for (int q = 0; q < 8; q++) ev[h ^ 1][q] = lds128(e2a + (c + 1) * kChunk * 4 + q * 16);
                     } else {
-                        // everything this warp needs from the buffer is in registers: release it to the MMA / TMA now
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) {
-                            mbar_arrive(&s.t_empty[buf]);
-                            mbar_arrive(&s.e2_empty[buf]);
-                        }
-                        if (tl_on) p.timeline[tl_seq * 12 + (grp == 0 ? 4 : 6)] = clock64();
+                        __syncwarp();                                   // every lane has read its last |e|^2 values
+                        if (lane == 0) mbar_arrive(&s.e2_empty[buf]);
                     }
                     float sc[32];
 #pragma unroll
                     for (int q = 0; q < 8; q++) {
-                        sc[4 * q + 0] = __fmaf_rn(cscale, __uint_as_float(acc[h][4 * q + 0]), ev[h][q].x);
-                        sc[4 * q + 1] = __fmaf_rn(cscale, __uint_as_float(acc[h][4 * q + 1]), ev[h][q].y);
-                        sc[4 * q + 2] = __fmaf_rn(cscale, __uint_as_float(acc[h][4 * q + 2]), ev[h][q].z);
-                        sc[4 * q + 3] = __fmaf_rn(cscale, __uint_as_float(acc[h][4 * q + 3]), ev[h][q].w);
+                        sc[4 * q + 0] = __fmaf_rn(cscale, __uint_as_float(acc[ab][4 * q + 0]), ev[h][q].x);
+                        sc[4 * q + 1] = __fmaf_rn(cscale, __uint_as_float(acc[ab][4 * q + 1]), ev[h][q].y);
+                        sc[4 * q + 2] = __fmaf_rn(cscale, __uint_as_float(acc[ab][4 * q + 2]), ev[h][q].z);
+                        sc[4 * q + 3] = __fmaf_rn(cscale, __uint_as_float(acc[ab][4 * q + 3]), ev[h][q].w);
                     }
                     if (kDebugScores) {
                         if (row_ok) {
