@@ -280,6 +280,35 @@ def test_degenerate_codebook_mass_fallback(vq, oracle):
     assert st["fallback_rows"] == B * H * W
 
 
+def test_partial_fallback_split_scan(vq, oracle):
+    """A few rows overflow their candidate list (a cluster of identical / nearly identical codes), the rest do not:
+    the fallback's split scan (several code blocks per row group, merged by the last arriver) decides them."""
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(11)
+    K, B, H, W = 4096, 2, 32, 32
+    E = rng.standard_normal((K, 256)).astype(np.float32)
+    v = rng.standard_normal(256).astype(np.float32)
+    E[100:200] = v                                            # 100 identical codes (lowest index must win) ...
+    E[1000:1100] = v + 1e-4 * rng.standard_normal((100, 256)).astype(np.float32)   # ... and 100 near copies
+    pick = rng.integers(2000, K, size=B * H * W)              # ordinary rows stay away from the cluster
+    zf = E[pick] + 0.3 * rng.standard_normal((B * H * W, 256)).astype(np.float32)
+    hot = rng.choice(B * H * W, size=21, replace=False)      # 21 rows next to the cluster: 3 row groups, one ragged
+    zf[hot] = v + 0.05 * rng.standard_normal((21, 256)).astype(np.float32)
+    z = np.ascontiguousarray(zf.reshape(B, H, W, 256).transpose(0, 3, 1, 2))
+    cb = vq.CodeBook(K, 256).to(dev)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(torch.from_numpy(E))
+        z_q, idx, loss = cb(torch.from_numpy(z).to(dev))
+        idx_tok = cb.encode_indices(torch.from_numpy(z).to(dev))
+    st = cb.stats_dict()
+    ref = oracle.forward(z, E)
+    assert np.array_equal(idx.cpu().numpy(), ref["idx"])
+    assert np.array_equal(idx_tok.cpu().numpy(), ref["idx"])
+    assert np.array_equal(z_q.permute(0, 2, 3, 1).reshape(-1, 256).cpu().numpy(), ref["zq_nhwc"])
+    assert st["fallback_rows"] == 21, st
+    assert st["tie_rows"] == ref["tie_rows"]
+
+
 def test_embed_nchw(vq):
     dev = torch.device("cuda:0")
     W = torch.randn(300, 256, device=dev)

@@ -114,6 +114,7 @@ struct Workspace {
     float4* fb_part;             // (kFbMaxGroups * kFbGroup, kFbMaxParts)
     unsigned int* fb_arrive;     // (kFbMaxGroups)
     unsigned long long* stats;   // (VQ_STAT_COUNT) internal copy when the caller passes none
+    size_t control_bytes;        // blocks_done .. fb_arrive, cleared by one memset per call
     size_t bytes;
 };
 
@@ -132,11 +133,13 @@ Workspace carve(void* base, int64_t N) {
     w.out_cnt = static_cast<int32_t*>(take((size_t)n_pad * 2 * 4));
     w.out_q = static_cast<uint32_t*>(take((size_t)n_pad * vq::kOutCap * 8));
     w.loss_partial = static_cast<double*>(take((size_t)(n_pad / vq::kSelRows) * 8));
-    w.blocks_done = static_cast<unsigned int*>(take(256));
     w.fb_rows = static_cast<int32_t*>(take((size_t)n_pad * 2 * 4));
-    w.fb_count = static_cast<int32_t*>(take(256));
     w.fb_part = static_cast<float4*>(take((size_t)vq::kFbMaxGroups * vq::kFbGroup * vq::kFbMaxParts * sizeof(float4)));
+    // control words, contiguous so that one memset per call clears them all: [blocks_done | fb_count | fb_arrive]
+    w.blocks_done = static_cast<unsigned int*>(take(256));
+    w.fb_count = static_cast<int32_t*>(take(256));
     w.fb_arrive = static_cast<unsigned int*>(take((size_t)vq::kFbMaxGroups * sizeof(unsigned int)));
+    w.control_bytes = 512 + (size_t)vq::kFbMaxGroups * sizeof(unsigned int);
     w.stats = static_cast<unsigned long long*>(take(256));
     w.bytes = off;
     return w;
@@ -188,7 +191,7 @@ int run_gemm(const float* z, int64_t N, int64_t HW, const void* E_h, const float
     gp.timeline = g_timeline;
     gp.timeline_tiles = g_timeline_tiles;
     const int grid = gp.row_tiles < dev->sms ? gp.row_tiles : dev->sms;
-    VQ_CUDA(cudaMemsetAsync(w.fb_count, 0, sizeof(int32_t), st));
+    VQ_CUDA(cudaMemsetAsync(w.blocks_done, 0, w.control_bytes, st));     // loss arrival counter, worklist length, group arrivals
     const bool prof = g_prof.on && g_prof.n < kProfCap;
     if (prof) {
         while (g_prof.created <= g_prof.n) {
@@ -321,15 +324,11 @@ static int forward_impl(bool training, const float* z, int64_t B, int64_t HW, in
         fp.HW = HW; fp.K = K;
         fp.out_cnt = w.out_cnt; fp.out_q = w.out_q; fp.stats = stats;
         fp.part = w.fb_part; fp.arrive = w.fb_arrive;
-        VQ_CUDA(cudaMemsetAsync(w.fb_arrive, 0, (size_t)vq::kFbMaxGroups * sizeof(unsigned int), st));
-        // code blocks: one code per thread when that needs <= kFbMaxParts blocks, else proportionally larger blocks
-        fp.per_part = vq::kFbThreads * (int)((K + (int64_t)vq::kFbThreads * vq::kFbMaxParts - 1) / ((int64_t)vq::kFbThreads * vq::kFbMaxParts));
-        fp.parts = (K + fp.per_part - 1) / fp.per_part;
         DevInfo* dev;
         rc = device_info(&dev);
         if (rc != VQ_OK) return rc;
-        const int64_t want = ((N + vq::kFbGroup - 1) / vq::kFbGroup) * fp.parts;
-        const unsigned fgrid = (unsigned)(want < 4 * dev->sms ? want : 4 * dev->sms);
+        // the kernel sizes its own work split from the worklist length; 128 registers x 256 threads -> 2 CTAs per SM
+        const unsigned fgrid = (unsigned)(2 * dev->sms);
         vq::vq_fallback_kernel<<<fgrid, vq::kFbThreads, 0, st>>>(fp);
         VQ_LAUNCH_CHECK("vq_fallback_kernel");
     }
@@ -345,7 +344,6 @@ static int forward_impl(bool training, const float* z, int64_t B, int64_t HW, in
     const unsigned grid = (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows);
     const bool vec = (HW % vq::kSelRows == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
     if (training) {
-        VQ_CUDA(cudaMemsetAsync(w.blocks_done, 0, sizeof(unsigned int), st));
         if (vec) vq::vq_select_kernel<true, true><<<grid, vq::kSelThreads, 0, st>>>(sp);
         else     vq::vq_select_kernel<true, false><<<grid, vq::kSelThreads, 0, st>>>(sp);
     } else {

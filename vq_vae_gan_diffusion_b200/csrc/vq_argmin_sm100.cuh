@@ -55,6 +55,7 @@ struct GemmSmem {
     float m_part[2][kEpiGroups][kRowTile];                   // 2 KiB   per-group running minima (double buffered)
     int32_t c_part[2][kEpiGroups][kRowTile];                 // 2 KiB   per-group push counts
     float m_live[kEpiGroups][kRowTile];                      // 1 KiB   running minima, refreshed once per code tile
+    uint8_t bad_part[kEpiGroups][kRowTile];                  //         per-group "row needs the exact fallback" verdicts
     alignas(8) uint64_t a_full[kNumDChunks];
     uint64_t a_empty[kNumDChunks];
     uint64_t b_full[2][kStagesB];        // one set per tile parity: each MMA warp sees every phase of its own set
@@ -387,8 +388,13 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                     }
                 }
                 p.out_cnt[row * kEpiGroups + grp] = bad ? -1 : n_out;
-                if (bad) p.fb_rows[atomicAdd(p.fb_count, 1)] = (int32_t)row;
+                s.bad_part[grp][trow] = bad ? 1 : 0;
             }
+            // a row goes on the fallback worklist ONCE, whichever group(s) flagged it: group 0 lists it after seeing
+            // group 1's verdict
+            epi_barrier();
+            if (row_ok && grp == 0 && (s.bad_part[0][trow] | s.bad_part[1][trow]) != 0)
+                p.fb_rows[atomicAdd(p.fb_count, 1)] = (int32_t)row;
             __syncwarp();
         }
     }

@@ -47,27 +47,54 @@ struct SelectParams {
     unsigned long long* stats; // (VQ_STAT_COUNT) or null
 };
 
-// canonical-order distance of latent row (shared tile column r) to code k; one thread does the whole dot product
-__device__ __forceinline__ float exact_distance_tile(const TileRow* t, int r, const float* __restrict__ E,
+// ---------------------------------------------------------------------------------------------------------------
+// The select kernel keeps its [32 latents x 256] fp32 tile ROW-major in shared memory -- the exact stage reads a whole
+// latent row per candidate, 16 bytes at a time -- with the 16-byte pieces of row r XOR-swizzled by
+// g(r) = (r >> 2) ^ (2 (r & 3)): conflict-free for (a) the tile fill (lanes over 8 row groups x 4 d, one row of each
+// group per store), (b) the exact stage (a warp reads the same piece of its 4 rows, 8 lanes per row broadcast) and
+// (c) the forward tail (lanes over d of one row).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int sel_swz(int r) { return ((r >> 2) ^ ((r & 3) << 1)) & 7; }
+__device__ __forceinline__ int sel_off(int r, int d) {                     // word offset of element (r, d)
+    return r * kD + ((((d >> 2) ^ sel_swz(r)) << 2) | (d & 3));
+}
+
+// canonical-order distance of latent row r (tile row) to code k; one thread does the whole dot product
+__device__ __forceinline__ float exact_distance_tile(const float* tile, int r, const float* __restrict__ E,
                                                      const float* __restrict__ e2, int k, float z2) {
     const float4* e4 = reinterpret_cast<const float4*>(E + (int64_t)k * kD);
+    const float4* zrow = reinterpret_cast<const float4*>(tile + r * kD);
+    const int g = sel_swz(r);
     float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
-#pragma unroll 16
-    for (int q = 0; q < kD / 4; q++) {
-        const float4 e = __ldg(e4 + q);
-        p0 = __fmaf_rn(t[4 * q + 0][r], e.x, p0);
-        p1 = __fmaf_rn(t[4 * q + 1][r], e.y, p1);
-        p2 = __fmaf_rn(t[4 * q + 2][r], e.z, p2);
-        p3 = __fmaf_rn(t[4 * q + 3][r], e.w, p3);
+#pragma unroll 2
+    for (int a = 0; a < kD / 32; a++) {
+        float4 e[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) e[b] = __ldg(e4 + 8 * a + b);
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const float4 zv = zrow[8 * a + (b ^ g)];
+            p0 = __fmaf_rn(zv.x, e[b].x, p0);
+            p1 = __fmaf_rn(zv.y, e[b].y, p1);
+            p2 = __fmaf_rn(zv.z, e[b].z, p2);
+            p3 = __fmaf_rn(zv.w, e[b].w, p3);
+        }
     }
     const float dot = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
     return ref_distance(z2, __ldg(e2 + k), dot);
 }
 
+// total order on non-NaN floats as unsigned keys (ascending); NaN -> 0xffffffff ("never the minimum")
+__device__ __forceinline__ uint32_t dist_key(float d) {
+    if (!(d == d)) return 0xffffffffu;
+    const uint32_t b = __float_as_uint(d + 0.0f);                          // -0.0 -> +0.0
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
 template <bool kForward, bool kVec>
-__global__ void __launch_bounds__(kSelThreads)
+__global__ void __launch_bounds__(kSelThreads, 4)
 vq_select_kernel(const SelectParams p) {
-    __shared__ TileRow t[kD];
+    __shared__ __align__(16) float tile[kSelRows * kD];       // 32 KiB, swizzled row-major (sel_off)
     __shared__ int clist[kSelWarps][4][kMaxCands];            // candidate codes of each row of each warp
     __shared__ int idx_s[kSelRows];
     __shared__ double red_s[kSelWarps];
@@ -78,7 +105,18 @@ vq_select_kernel(const SelectParams p) {
     const int64_t n0 = (int64_t)blockIdx.x * kSelRows;
     if (tid < 4) st_s[tid] = 0;
 
-    // 2a. expand this warp's candidate entries into quads (independent of the z tile)
+    // 1a. forward mode always needs the fp32 z tile: put its loads in flight before anything else (16-byte loads along
+    //     hw, 8 per thread) so that the candidate expansion below runs in their shadow
+    const int dsub = lane >> 3, hq = lane & 7;
+    float4 zreg[8];
+    if (kForward && kVec) {
+        const int64_t b = n0 / p.HW, hw0 = n0 % p.HW;
+        const float* src = p.z + (b * kD + dsub) * p.HW + hw0 + 4 * hq;
+#pragma unroll
+        for (int i = 0; i < 8; i++) zreg[i] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)((warp * 8 + i) * 4) * p.HW));
+    }
+
+    // 2a. expand this warp's candidate entries (32-code chunk + code mask) into code lists
     int nq[4];
     unsigned resolved_mask = 0;                               // rows decided by vq_fallback_kernel (stats counted there)
 #pragma unroll
@@ -111,58 +149,103 @@ vq_select_kernel(const SelectParams p) {
         nq[rr] = min(kMaxCands, __shfl_sync(0xffffffffu, incl, 31));
     }
 
-    // 1. z tile (fp32): always needed by the forward tail; in tokeniser mode only when some row of this CTA has more
-    //    than one candidate and therefore needs exact distances
+    // 1b. z tile into shared memory.  Tokeniser mode loads it only when some row of this CTA has more than one
+    //     candidate and therefore needs exact distances.
     const int need_exact = (nq[0] > 1) | (nq[1] > 1) | (nq[2] > 1) | (nq[3] > 1);
     const bool want_tile = kForward ? true : (__syncthreads_or(need_exact) != 0);
-    if (want_tile) load_tile_nchw<kVec, false>(t, p.z, n0, p.N, p.HW, warp, lane);
+    if (want_tile) {
+        if (kVec) {
+            if (!kForward) {
+                const int64_t b = n0 / p.HW, hw0 = n0 % p.HW;
+                const float* src = p.z + (b * kD + dsub) * p.HW + hw0 + 4 * hq;
+#pragma unroll
+                for (int i = 0; i < 8; i++) zreg[i] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)((warp * 8 + i) * 4) * p.HW));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int d = (warp * 8 + i) * 4 + dsub;
+                tile[sel_off(4 * hq + 0, d)] = zreg[i].x;
+                tile[sel_off(4 * hq + 1, d)] = zreg[i].y;
+                tile[sel_off(4 * hq + 2, d)] = zreg[i].z;
+                tile[sel_off(4 * hq + 3, d)] = zreg[i].w;
+            }
+        } else {
+            const int64_t n = n0 + lane;
+            const bool ok = n < p.N;
+            const int64_t b = ok ? n / p.HW : 0, hw = ok ? n % p.HW : 0;
+            const float* src = p.z + (b * kD) * p.HW + hw;
+#pragma unroll 8
+            for (int i = 0; i < kD / 8; i++) {
+                const int d = warp + 8 * i;
+                tile[sel_off(lane, d)] = ok ? __ldg(src + (int64_t)d * p.HW) : 0.0f;
+            }
+        }
+    }
     __syncthreads();
 
-    // 2b. exact distances: lane = 8*rr + c -> row rr of this warp, code slot c (two quads per pass and row)
+    // 2b. exact distances.  The candidates of the warp's rows that need a decision (>= 2 candidates) are pooled into
+    //     one list and dealt out one (row, code) pair per lane, so a pass keeps all 32 lanes busy whatever the split
+    //     between rows.  Per pass and row: first minimum over the row's lanes with two redux.sync (distance key, then
+    //     lowest index at that key) and a ballot for the multiplicity; every lane tracks all four rows' results.
     {
-        const int rr = lane >> 3, c = lane & 7;
-        const int r = warp * 4 + rr;
-        const int64_t n = n0 + r;
-        const bool row_ok = n < p.N;
-        const int my_nq = (rr == 0) ? nq[0] : (rr == 1) ? nq[1] : (rr == 2) ? nq[2] : nq[3];
-        // a row with a single candidate is decided without any arithmetic (the margin argument guarantees the
-        // oracle's argmin is among the candidates), so only rows with >= 2 candidates take part in the passes
-        const int max_nq = max(max(nq[0] > 1 ? nq[0] : 0, nq[1] > 1 ? nq[1] : 0), max(nq[2] > 1 ? nq[2] : 0, nq[3] > 1 ? nq[3] : 0));
-        const float z2 = row_ok ? __ldg(p.z2 + n) : 0.0f;
-        const unsigned seg = 0xffu << (rr * 8);
-        float best_d = INFINITY;
-        int best_k = 0x7fffffff, n_at_min = 0;
-        if (my_nq == 1) {
-            best_k = clist[warp][rr][0];
-            if (best_k >= p.K) best_k = 0;
-            n_at_min = 1;
-        }
-        for (int base = 0; base < max_nq; base += 8) {
-            int k = (my_nq > 1 && base + c < my_nq) ? clist[warp][rr][base + c] : -1;
-            if (k >= p.K) k = -1;                              // pad codes of the last chunk
-            float dist = INFINITY;
-            if (k >= 0) dist = exact_distance_tile(t, r, p.E, p.e2, k, z2);
-            // first minimum within the row's 8 lanes (lexicographic on (distance, index))
-            float pd = dist;
-            int pk = (k >= 0) ? k : 0x7fffffff;
+        int off[5];
+        off[0] = 0;
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
-                const float d2 = __shfl_xor_sync(0xffffffffu, pd, o);
-                const int k2 = __shfl_xor_sync(0xffffffffu, pk, o);
-                if (d2 < pd || (d2 == pd && k2 < pk)) { pd = d2; pk = k2; }
+        for (int rr = 0; rr < 4; rr++) off[rr + 1] = off[rr] + (nq[rr] > 1 ? nq[rr] : 0);
+        const int total = off[4];
+        uint32_t best_u[4];
+        int best_k[4], n_at_min[4];
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++) {
+            best_u[rr] = 0xffffffffu; best_k[rr] = 0x7fffffff; n_at_min[rr] = 0;
+            if (nq[rr] == 1) {
+                // a single candidate is decided without any arithmetic: the margin argument guarantees that the
+                // oracle's argmin is among the candidates
+                best_k[rr] = clist[warp][rr][0];
+                if (best_k[rr] >= p.K) best_k[rr] = 0;
+                n_at_min[rr] = 1;
             }
-            const int eq = __popc(__ballot_sync(0xffffffffu, k >= 0 && dist == pd) & seg);
-            if (pd < best_d) { best_d = pd; best_k = pk; n_at_min = eq; }
-            else if (pd == best_d) { n_at_min += eq; best_k = min(best_k, pk); }
         }
-        if (best_k == 0x7fffffff) best_k = 0;                 // every distance NaN: torch.argmin -> 0 as well
-        if (row_ok && c == 0) {
-            idx_s[r] = best_k;
-            p.idx[n] = (int64_t)best_k;
-            if (p.stats != nullptr && !((resolved_mask >> rr) & 1u)) {
-                if (n_at_min > 1) atomicAdd(&st_s[0], 1u);
-                if (my_nq > 1) atomicAdd(&st_s[1], 1u);
-                atomicAdd(&st_s[3], (unsigned)my_nq);
+        for (int base = 0; base < total; base += 32) {
+            const int f = base + lane;
+            const bool active = f < total;
+            const int rr = (f >= off[3]) ? 3 : (f >= off[2]) ? 2 : (f >= off[1]) ? 1 : 0;
+            const int pos = f - ((rr == 3) ? off[3] : (rr == 2) ? off[2] : (rr == 1) ? off[1] : 0);
+            int k = active ? clist[warp][rr][pos] : -1;
+            if (k >= p.K) k = -1;                              // pad codes of the last chunk
+            const int r = warp * 4 + rr;
+            uint32_t u = 0xffffffffu;
+            if (k >= 0) u = dist_key(exact_distance_tile(tile, r, p.E, p.e2, k, __ldg(p.z2 + n0 + r)));
+#pragma unroll
+            for (int r2 = 0; r2 < 4; r2++) {
+                const bool mine = (k >= 0) && (rr == r2);
+                if (__ballot_sync(0xffffffffu, mine) == 0u) continue;          // warp-uniform
+                const uint32_t um = __reduce_min_sync(0xffffffffu, mine ? u : 0xffffffffu);
+                if (um == 0xffffffffu) continue;                               // only NaN distances in this pass
+                const bool at = mine && (u == um);
+                const int km = (int)__reduce_min_sync(0xffffffffu, at ? (uint32_t)k : 0x7fffffffu);
+                const int c = __popc(__ballot_sync(0xffffffffu, at));
+                if (um < best_u[r2]) { best_u[r2] = um; best_k[r2] = km; n_at_min[r2] = c; }
+                else if (um == best_u[r2]) { n_at_min[r2] += c; best_k[r2] = min(best_k[r2], km); }
+            }
+        }
+        // lane rr publishes row rr of this warp
+        if (lane < 4) {
+            const int rr = lane;
+            const int r = warp * 4 + rr;
+            const int64_t n = n0 + r;
+            int bk = (rr == 0) ? best_k[0] : (rr == 1) ? best_k[1] : (rr == 2) ? best_k[2] : best_k[3];
+            const int na = (rr == 0) ? n_at_min[0] : (rr == 1) ? n_at_min[1] : (rr == 2) ? n_at_min[2] : n_at_min[3];
+            const int my_nq = (rr == 0) ? nq[0] : (rr == 1) ? nq[1] : (rr == 2) ? nq[2] : nq[3];
+            if (bk == 0x7fffffff) bk = 0;                     // every distance NaN: torch.argmin -> 0 as well
+            if (n < p.N) {
+                idx_s[r] = bk;
+                p.idx[n] = (int64_t)bk;
+                if (p.stats != nullptr && !((resolved_mask >> rr) & 1u)) {
+                    if (na > 1) atomicAdd(&st_s[0], 1u);
+                    if (my_nq > 1) atomicAdd(&st_s[1], 1u);
+                    atomicAdd(&st_s[3], (unsigned)my_nq);
+                }
             }
         }
     }
@@ -191,7 +274,7 @@ vq_select_kernel(const SelectParams p) {
 #pragma unroll
             for (int i = 0; i < kD / 32; i++) {
                 const int d = lane + 32 * i;
-                const float zv = t[d][r];
+                const float zv = tile[sel_off(r, d)];
                 const float diff = __fsub_rn(ev[rr][i], zv);       // fl(e - z)
                 __stcs(out + d, __fadd_rn(zv, diff));              // fl(z + fl(e - z)), codebook.py:106
                 sq = __fmaf_rn(diff, diff, sq);
@@ -245,7 +328,6 @@ struct FallbackParams {
     uint32_t* out_q;
     float4* part;              // (kFbMaxGroups * kFbGroup, parts) partial (distance, index, multiplicity) results
     unsigned int* arrive;      // (kFbMaxGroups) arrival counters, zero on entry, re-armed by the kernel
-    int parts, per_part;       // code blocks per group and codes per block (multiple of kFbThreads)
     unsigned long long* stats;
 };
 
@@ -257,9 +339,11 @@ __device__ __forceinline__ void merge_min(float& d, int& k, int& c, float d2, in
 
 // Work item = (group of kFbGroup worklist entries, block of codes): one thread per code streams its code row once
 // with 128-bit loads and applies it to all rows of the group (held in shared memory), so the codebook traffic of the
-// fallback is 1/kFbGroup of a row-by-row scan and a handful of overflowed rows is spread over the whole chip.  The
-// last code block of a group to arrive merges the per-block minima.  Groups beyond kFbMaxGroups (a degenerate
-// codebook: every row overflows) are scanned block after block by a single CTA each.
+// fallback is 1/kFbGroup of a row-by-row scan.  The number of code blocks per group is chosen ON THE DEVICE from the
+// worklist length so that groups x blocks fills the resident CTAs about once: a handful of overflowed rows is spread
+// over the whole chip (one or two codes per thread), while a degenerate codebook (every row overflows) gets one CTA
+// per group scanning all codes with no merge step.  The last code block of a group to arrive merges the per-block
+// minima cooperatively.
 __global__ void __launch_bounds__(kFbThreads)
 vq_fallback_kernel(const FallbackParams p) {
     __shared__ float4 zr4[kFbGroup][kD / 4];
@@ -269,16 +353,21 @@ vq_fallback_kernel(const FallbackParams p) {
     __shared__ int is_final;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int count = __ldg(p.fb_count);
+    if (count == 0) return;
     const int groups = (count + kFbGroup - 1) / kFbGroup;
-    const int parts = p.parts, per_part = p.per_part;
+    // code blocks per group: fill the grid once; a multiple of kFbThreads codes each; never more than kFbMaxParts
+    int parts = max(1, min(min(kFbMaxParts, (int)gridDim.x / groups), (p.K + kFbThreads - 1) / kFbThreads));
+    if (groups > kFbMaxGroups) parts = 1;
+    const int per_part = ((p.K + parts * kFbThreads - 1) / (parts * kFbThreads)) * kFbThreads;
+    parts = (p.K + per_part - 1) / per_part;
+    const bool split = parts > 1;
     const int64_t items = (int64_t)groups * parts;
     for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
         const int g = (int)(w / parts), part0 = (int)(w % parts);
-        const bool split = g < kFbMaxGroups;
-        if (!split && part0 != 0) continue;                      // block-uniform
         __syncthreads();
         if (tid < kFbGroup) row_s[tid] = (g * kFbGroup + tid < count) ? (int64_t)__ldg(p.fb_rows + g * kFbGroup + tid) : -1;
         __syncthreads();
+#pragma unroll
         for (int r = 0; r < kFbGroup; r++) {
             const int64_t n = row_s[r];
             if (tid < kD) reinterpret_cast<float*>(zr4[r])[tid] = (n >= 0) ? __ldg(p.z + ((n / p.HW) * kD + tid) * p.HW + n % p.HW) : 0.0f;
@@ -291,56 +380,57 @@ vq_fallback_kernel(const FallbackParams p) {
             z2[r] = (row_s[r] >= 0) ? __ldg(p.z2 + row_s[r]) : 0.0f;
             best_d[r] = INFINITY; best_k[r] = 0x7fffffff; n_at_min[r] = 0;
         }
-        const int part_lo = split ? part0 : 0, part_hi = split ? part0 + 1 : parts;
-        for (int part = part_lo; part < part_hi; part++) {
-            const int k_hi = min(p.K, (part + 1) * per_part);
-            for (int k = part * per_part + tid; k < k_hi; k += kFbThreads) {   // ascending k per thread
-                const float4* e4 = reinterpret_cast<const float4*>(p.E + (int64_t)k * kD);
-                float acc[kFbGroup][4];
+        const int k_hi = min(p.K, (part0 + 1) * per_part);
+        for (int k = part0 * per_part + tid; k < k_hi; k += kFbThreads) {   // ascending k per thread
+            const float4* e4 = reinterpret_cast<const float4*>(p.E + (int64_t)k * kD);
+            float acc[kFbGroup][4];
 #pragma unroll
-                for (int r = 0; r < kFbGroup; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
-#pragma unroll 4
-                for (int q = 0; q < kD / 4; q++) {
-                    const float4 e = __ldg(e4 + q);
-#pragma unroll
-                    for (int r = 0; r < kFbGroup; r++) {
-                        const float4 zv = zr4[r][q];
-                        acc[r][0] = __fmaf_rn(zv.x, e.x, acc[r][0]);
-                        acc[r][1] = __fmaf_rn(zv.y, e.y, acc[r][1]);
-                        acc[r][2] = __fmaf_rn(zv.z, e.z, acc[r][2]);
-                        acc[r][3] = __fmaf_rn(zv.w, e.w, acc[r][3]);
-                    }
-                }
-                const float e2k = __ldg(p.e2 + k);
+            for (int r = 0; r < kFbGroup; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+#pragma unroll 8
+            for (int q = 0; q < kD / 4; q++) {
+                const float4 e = __ldg(e4 + q);
 #pragma unroll
                 for (int r = 0; r < kFbGroup; r++) {
-                    const float dot = __fadd_rn(__fadd_rn(acc[r][0], acc[r][1]), __fadd_rn(acc[r][2], acc[r][3]));
-                    merge_min(best_d[r], best_k[r], n_at_min[r], ref_distance(z2[r], e2k, dot), k, 1);
+                    const float4 zv = zr4[r][q];
+                    acc[r][0] = __fmaf_rn(zv.x, e.x, acc[r][0]);
+                    acc[r][1] = __fmaf_rn(zv.y, e.y, acc[r][1]);
+                    acc[r][2] = __fmaf_rn(zv.z, e.z, acc[r][2]);
+                    acc[r][3] = __fmaf_rn(zv.w, e.w, acc[r][3]);
                 }
             }
-        }
+            const float e2k = __ldg(p.e2 + k);
 #pragma unroll
-        for (int r = 0; r < kFbGroup; r++) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const float d2 = __shfl_xor_sync(0xffffffffu, best_d[r], o);
-                const int k2 = __shfl_xor_sync(0xffffffffu, best_k[r], o);
-                const int c2 = __shfl_xor_sync(0xffffffffu, n_at_min[r], o);
-                merge_min(best_d[r], best_k[r], n_at_min[r], d2, k2, c2);
+            for (int r = 0; r < kFbGroup; r++) {
+                const float dot = __fadd_rn(__fadd_rn(acc[r][0], acc[r][1]), __fadd_rn(acc[r][2], acc[r][3]));
+                merge_min(best_d[r], best_k[r], n_at_min[r], ref_distance(z2[r], e2k, dot), k, 1);
             }
-            if (lane == 0) { sd[r][warp] = best_d[r]; sk[r][warp] = best_k[r]; sn[r][warp] = n_at_min[r]; }
         }
-        __syncthreads();
-        // thread r finishes row r of the group
-        if (tid < kFbGroup && row_s[tid] >= 0) {
-            const int r = tid;
-            float d = sd[r][0];
-            int k = sk[r][0], cnt = sn[r][0];
-            for (int v = 1; v < kFbThreads / 32; v++) merge_min(d, k, cnt, sd[r][v], sk[r][v], sn[r][v]);
-            if (split) p.part[((int64_t)g * kFbGroup + r) * parts + part0] = make_float4(d, __int_as_float(k), __int_as_float(cnt), 0.0f);
-            sd[r][0] = d; sk[r][0] = k; sn[r][0] = cnt;
-        }
+        // block-level merge of the per-thread minima: warp shuffles, then thread r finishes row r
+        auto block_merge = [&]() {
+#pragma unroll
+            for (int r = 0; r < kFbGroup; r++) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float d2 = __shfl_xor_sync(0xffffffffu, best_d[r], o);
+                    const int k2 = __shfl_xor_sync(0xffffffffu, best_k[r], o);
+                    const int c2 = __shfl_xor_sync(0xffffffffu, n_at_min[r], o);
+                    merge_min(best_d[r], best_k[r], n_at_min[r], d2, k2, c2);
+                }
+                if (lane == 0) { sd[r][warp] = best_d[r]; sk[r][warp] = best_k[r]; sn[r][warp] = n_at_min[r]; }
+            }
+            __syncthreads();
+            if (tid < kFbGroup) {
+                float d = sd[tid][0];
+                int k = sk[tid][0], cnt = sn[tid][0];
+                for (int v = 1; v < kFbThreads / 32; v++) merge_min(d, k, cnt, sd[tid][v], sk[tid][v], sn[tid][v]);
+                sd[tid][0] = d; sk[tid][0] = k; sn[tid][0] = cnt;
+            }
+        };
+        block_merge();
         if (split) {
+            if (tid < kFbGroup && row_s[tid] >= 0)
+                p.part[((int64_t)g * kFbGroup + tid) * parts + part0] =
+                    make_float4(sd[tid][0], __int_as_float(sk[tid][0]), __int_as_float(sn[tid][0]), 0.0f);
             __threadfence();
             __syncthreads();
             if (tid == 0) {
@@ -350,21 +440,24 @@ vq_fallback_kernel(const FallbackParams p) {
             __syncthreads();
             if (!is_final) continue;
             __threadfence();
-        } else {
-            __syncthreads();
-        }
-        if (tid < kFbGroup && row_s[tid] >= 0) {
-            const int r = tid;
-            const int64_t n = row_s[r];
-            float d = sd[r][0];
-            int k = sk[r][0], cnt = sn[r][0];
-            if (split) {
-                d = INFINITY; k = 0x7fffffff; cnt = 0;
-                for (int q = 0; q < parts; q++) {
+            // the last block to arrive merges the per-block results of the group, all threads taking part
+#pragma unroll
+            for (int r = 0; r < kFbGroup; r++) {
+                best_d[r] = INFINITY; best_k[r] = 0x7fffffff; n_at_min[r] = 0;
+                if (row_s[r] < 0) continue;                      // block-uniform
+                for (int q = tid; q < parts; q += kFbThreads) {
                     const float4 v = __ldcg(p.part + ((int64_t)g * kFbGroup + r) * parts + q);
-                    merge_min(d, k, cnt, v.x, __float_as_int(v.y), __float_as_int(v.z));
+                    merge_min(best_d[r], best_k[r], n_at_min[r], v.x, __float_as_int(v.y), __float_as_int(v.z));
                 }
             }
+            __syncthreads();
+            block_merge();
+        }
+        __syncthreads();
+        if (tid < kFbGroup && row_s[tid] >= 0) {
+            const int64_t n = row_s[tid];
+            int k = sk[tid][0];
+            const int cnt = sn[tid][0];
             // a row can be listed twice (once per epilogue group): the first finisher publishes and counts it
             if (atomicExch(p.out_cnt + 2 * n, -2) != -2) {
                 if (k == 0x7fffffff) k = 0;                      // every distance NaN: torch.argmin -> 0 as well
