@@ -58,8 +58,8 @@ vq_backward_kernel(const BackwardParams p) {
     }
 
     // 1. tiles
-    load_tile_nchw<kVec, true>(zt, p.z, n0, p.N, p.HW, warp, lane);
     const bool has_g = p.gout != nullptr && p.grad_z != nullptr;
+    load_tile_nchw<kVec, true>(zt, p.z, n0, p.N, p.HW, warp, lane);
     if (has_g) {
         if (kGoutCL) {
             // rows of 256 contiguous floats: warp w stages rows 4w..4w+3, lanes over d (8 requests per row in flight)

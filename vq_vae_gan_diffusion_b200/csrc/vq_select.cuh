@@ -59,29 +59,26 @@ __device__ __forceinline__ int sel_off(int r, int d) {                     // wo
     return r * kD + ((((d >> 2) ^ sel_swz(r)) << 2) | (d & 3));
 }
 
-// canonical-order distance of latent row r (tile row) to code k; one thread does the whole dot product
-__device__ __forceinline__ float exact_distance_tile(const float* tile, int r, const float* __restrict__ E,
-                                                     const float* __restrict__ e2, int k, float z2) {
-    const float4* e4 = reinterpret_cast<const float4*>(E + (int64_t)k * kD);
-    const float4* zrow = reinterpret_cast<const float4*>(tile + r * kD);
+// One canonical partial sum of the dot product of latent row r (tile row) with code k: the terms d == j (mod 4) in
+// ascending d, one fma each (oracle/vq_oracle.c: vqo_dot).  Four lanes (j = 0..3) share a (row, code) pair; all 64
+// code-row loads of a lane are independent and issued in two batches of 32, so a pass costs two L2 round trips.
+__device__ __forceinline__ float exact_partial_tile(const float* tile, int r, const float* __restrict__ E, int k, int j) {
+    const float* e = E + (int64_t)k * kD + j;
     const int g = sel_swz(r);
-    float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;
-#pragma unroll 2
-    for (int a = 0; a < kD / 32; a++) {
-        float4 e[8];
+    const float* zrow = tile + r * kD + j;
+    int zo[8];
 #pragma unroll
-        for (int b = 0; b < 8; b++) e[b] = __ldg(e4 + 8 * a + b);
+    for (int b = 0; b < 8; b++) zo[b] = (b ^ g) << 2;
+    float p = 0.0f;
 #pragma unroll
-        for (int b = 0; b < 8; b++) {
-            const float4 zv = zrow[8 * a + (b ^ g)];
-            p0 = __fmaf_rn(zv.x, e[b].x, p0);
-            p1 = __fmaf_rn(zv.y, e[b].y, p1);
-            p2 = __fmaf_rn(zv.z, e[b].z, p2);
-            p3 = __fmaf_rn(zv.w, e[b].w, p3);
-        }
+    for (int h = 0; h < 2; h++) {
+        float ev[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) ev[i] = __ldg(e + 4 * (32 * h + i));
+#pragma unroll
+        for (int i = 0; i < 32; i++) p = __fmaf_rn(zrow[32 * (4 * h + (i >> 3)) + zo[i & 7]], ev[i], p);
     }
-    const float dot = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
-    return ref_distance(z2, __ldg(e2 + k), dot);
+    return p;
 }
 
 // total order on non-NaN floats as unsigned keys (ascending); NaN -> 0xffffffff ("never the minimum")
@@ -113,24 +110,38 @@ vq_select_kernel(const SelectParams p) {
         const int64_t b = n0 / p.HW, hw0 = n0 % p.HW;
         const float* src = p.z + (b * kD + dsub) * p.HW + hw0 + 4 * hq;
 #pragma unroll
-        for (int i = 0; i < 8; i++) zreg[i] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)((warp * 8 + i) * 4) * p.HW));
+        for (int i = 0; i < 8; i++) zreg[i] = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)((warp * 8 + i) * 4) * p.HW));
     }
 
     // 2a. expand this warp's candidate entries (32-code chunk + code mask) into code lists
+    //     (counts and entry slots are fetched together, unconditionally: one DRAM round trip instead of two; the 16
+    //     slots of a row are one 128-byte line)
     int nq[4];
     unsigned resolved_mask = 0;                               // rows decided by vq_fallback_kernel (stats counted there)
+    int2 cnt2[4];
+    uint2 eq[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const int64_t n = n0 + warp * 4 + rr;
+        cnt2[rr] = make_int2(0, 0);
+        eq[rr] = make_uint2(0u, 0u);
+        if (n < p.N) {
+            cnt2[rr] = __ldg(reinterpret_cast<const int2*>(p.out_cnt) + n);
+            if (lane < kOutCap) eq[rr] = __ldg(reinterpret_cast<const uint2*>(p.out_q) + n * kOutCap + lane);
+        }
+    }
 #pragma unroll
     for (int rr = 0; rr < 4; rr++) {
         const int64_t n = n0 + warp * 4 + rr;
         nq[rr] = 0;
         if (n >= p.N) continue;                               // warp-uniform
-        const int c0 = __ldg(p.out_cnt + 2 * n), c1 = __ldg(p.out_cnt + 2 * n + 1);
+        const int c0 = cnt2[rr].x, c1 = cnt2[rr].y;
         const bool resolved = (c0 == -2);
         if (resolved) resolved_mask |= 1u << rr;
         const int g = lane >> 3, i = lane & 7;                // slot = lane: group g owns slots [8g, 8g + 8)
         const bool valid = resolved ? (lane == 0) : (lane < kOutCap && i < (g ? c1 : c0));
-        uint2 e = make_uint2(0u, 0u);                         // (chunk id, mask of candidate codes in the chunk)
-        if (valid) e = __ldg(reinterpret_cast<const uint2*>(p.out_q) + n * kOutCap + lane);
+        uint2 e = eq[rr];                                     // (chunk id, mask of candidate codes in the chunk)
+        if (!valid) e = make_uint2(0u, 0u);
         const int pc = __popc(e.y);
         int incl = pc;
 #pragma unroll
@@ -206,19 +217,23 @@ vq_select_kernel(const SelectParams p) {
                 n_at_min[rr] = 1;
             }
         }
-        for (int base = 0; base < total; base += 32) {
-            const int f = base + lane;
+        for (int base = 0; base < total; base += 8) {
+            const int f = base + (lane >> 2), j = lane & 3;    // pair index, canonical partial sum of this lane
             const bool active = f < total;
             const int rr = (f >= off[3]) ? 3 : (f >= off[2]) ? 2 : (f >= off[1]) ? 1 : 0;
             const int pos = f - ((rr == 3) ? off[3] : (rr == 2) ? off[2] : (rr == 1) ? off[1] : 0);
             int k = active ? clist[warp][rr][pos] : -1;
             if (k >= p.K) k = -1;                              // pad codes of the last chunk
             const int r = warp * 4 + rr;
+            float pj = 0.0f;
+            if (k >= 0) pj = exact_partial_tile(tile, r, p.E, k, j);
+            const float dot = combine4(pj);                    // (p0 + p1) + (p2 + p3) on all four lanes
+            const bool lead = (k >= 0) && (j == 0);
             uint32_t u = 0xffffffffu;
-            if (k >= 0) u = dist_key(exact_distance_tile(tile, r, p.E, p.e2, k, __ldg(p.z2 + n0 + r)));
+            if (lead) u = dist_key(ref_distance(__ldg(p.z2 + n0 + r), __ldg(p.e2 + k), dot));
 #pragma unroll
             for (int r2 = 0; r2 < 4; r2++) {
-                const bool mine = (k >= 0) && (rr == r2);
+                const bool mine = lead && (rr == r2);
                 if (__ballot_sync(0xffffffffu, mine) == 0u) continue;          // warp-uniform
                 const uint32_t um = __reduce_min_sync(0xffffffffu, mine ? u : 0xffffffffu);
                 if (um == 0xffffffffu) continue;                               // only NaN distances in this pass
