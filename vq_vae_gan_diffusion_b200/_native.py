@@ -89,11 +89,12 @@ def lib():
     if _lib is None:
         with _lock:
             if _lib is None:
-                if not os.path.exists(LIB_PATH):
+                path = os.environ.get("VQ_B200_LIB", LIB_PATH)      # A/B builds of the same ABI (tuning only)
+                if not os.path.exists(path):
                     raise VQNativeError(
-                        f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                        f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                         "(there is no CPU / PyTorch fallback for the VQ hot path)")
-                L = ctypes.CDLL(LIB_PATH)
+                L = ctypes.CDLL(path)
                 for name, (res, args) in _SIGNATURES.items():
                     fn = getattr(L, name)
                     fn.restype = res

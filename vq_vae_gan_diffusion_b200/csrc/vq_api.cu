@@ -89,11 +89,6 @@ int device_info(DevInfo** out) {
                                      (int)vq::kGemmSmemBytes));
         VQ_CUDA(cudaFuncSetAttribute(vq::vq_argmin_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)vq::kGemmSmemBytes));
-        const int bwd_smem = (int)(2 * vq::kBwdTileBytes);
-        VQ_CUDA(cudaFuncSetAttribute(vq::vq_backward_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
-        VQ_CUDA(cudaFuncSetAttribute(vq::vq_backward_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
-        VQ_CUDA(cudaFuncSetAttribute(vq::vq_backward_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
-        VQ_CUDA(cudaFuncSetAttribute(vq::vq_backward_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem));
         d.attrs_set = true;
     }
     *out = &d;
@@ -415,18 +410,18 @@ VQ_EXPORT int vq_backward(const float* gout, const int64_t* gout_strides, float 
     bp.beta = beta;
     bp.grad_z = grad_z; bp.grad_E = grad_E;
     const unsigned grid = (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows);
-    const size_t smem = 2 * vq::kBwdTileBytes;
     // channels-last upstream gradient (d contiguous; the layout of the z_q we returned) is read lanes-over-d, an
     // hw-contiguous one like z; 16-byte tile accesses need hw-contiguous, 16-byte aligned 32-latent tiles
-    const bool cl = gout != nullptr && bp.gs_d == 1 && !(bp.gs_hw == 1 && HW > 1);
+    const bool cl = gout != nullptr && bp.gs_d == 1 && !(bp.gs_hw == 1 && HW > 1) && bp.gs_b % 4 == 0 && bp.gs_hw % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
     const bool vec = (HW % vq::kSelRows == 0) && ((reinterpret_cast<uintptr_t>(z_nchw) & 15) == 0) &&
                      (grad_z == nullptr || (reinterpret_cast<uintptr_t>(grad_z) & 15) == 0);
     if (vec) {
-        if (cl) vq::vq_backward_kernel<true, true><<<grid, vq::kBwdThreads, smem, st>>>(bp);
-        else    vq::vq_backward_kernel<true, false><<<grid, vq::kBwdThreads, smem, st>>>(bp);
+        if (cl) vq::vq_backward_kernel<true, true><<<grid, vq::kBwdThreads, 0, st>>>(bp);
+        else    vq::vq_backward_kernel<true, false><<<grid, vq::kBwdThreads, 0, st>>>(bp);
     } else {
-        if (cl) vq::vq_backward_kernel<false, true><<<grid, vq::kBwdThreads, smem, st>>>(bp);
-        else    vq::vq_backward_kernel<false, false><<<grid, vq::kBwdThreads, smem, st>>>(bp);
+        if (cl) vq::vq_backward_kernel<false, true><<<grid, vq::kBwdThreads, 0, st>>>(bp);
+        else    vq::vq_backward_kernel<false, false><<<grid, vq::kBwdThreads, 0, st>>>(bp);
     }
     VQ_LAUNCH_CHECK("vq_backward_kernel");
     return VQ_OK;

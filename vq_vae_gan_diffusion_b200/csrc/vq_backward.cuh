@@ -1,12 +1,14 @@
 // vq_backward.cuh -- fused straight-through backward + codebook scatter-add, and the NCHW embedding lookup.
 //
-// vq_backward_kernel: one CTA = 32 latents, two [256 x 32] fp32 tiles in shared memory.
-//   1. z tile (NCHW, 16-byte loads, lanes over hw) and the upstream-gradient tile: channels-last g_out (d contiguous,
-//      the layout of the z_q we returned) is read lanes-over-d, an hw-contiguous g_out like z; any other layout with
-//      strided scalar loads
-//   2. lanes over d: gather e = E[idx[n]] rows (coalesced 1 KiB reads, L2 resident), diff = z - e kept in the z tile,
-//      grad_E[idx[n]][d] += -coef * beta * diff  (red.global.add.f32, 128-byte coalesced)
-//   3. lanes over hw: grad_z = g_out + coef * diff written as NCHW with 16-byte stores   [autograd of codebook.py:96-106]
+// vq_backward_kernel: one CTA = 32 latents, ONE [32 x 256] fp32 tile in shared memory (row-major, 16-byte pieces
+// XOR-swizzled: vq_common.cuh tile_off), two transposes in total:
+//   1. z tile (NCHW: 16-byte loads along hw, 4 latents x 1 d per request) -> shared memory, column form -> row form
+//   2. row form, warp w owns latents 4w..4w+3, lane owns d in [4 lane, 4 lane + 4) and [128 + 4 lane, ...), everything in
+//      16-byte requests: e = E[idx[n]] (L2 resident), diff = z - e, grad_E[idx[n]] += -coef * beta * diff
+//      (red.global.add.v4.f32), grad = g_out + coef * diff with a channels-last g_out (the layout of the z_q we
+//      returned) read straight from global memory in row form; grad (or diff) goes back into the tile
+//   3. row form -> column form: grad_z written as NCHW with 16-byte stores; an hw-contiguous g_out (e.g. NCHW) is
+//      added here, read in column form like z                                    [autograd of codebook.py:96-106]
 // HBM traffic per latent: read g_out 4D + z 4D + idx 8, write grad_z 4D -- the algorithmic minimum; the codebook
 // and its gradient (16 MiB each at K = 16384) stay in the 126 MB L2.
 #pragma once
@@ -15,7 +17,9 @@
 namespace vq {
 
 constexpr int kBwdThreads = 256;
-constexpr size_t kBwdTileBytes = (size_t)kD * (kSelRows + 1) * sizeof(float);
+#ifndef VQ_BWD_MIN_BLOCKS
+#define VQ_BWD_MIN_BLOCKS 3               // resident CTAs per SM the register allocation is tuned for
+#endif
 
 struct BackwardParams {
     const float* gout;        // may be null
@@ -33,19 +37,24 @@ struct BackwardParams {
     float* grad_E;            // (K, D) or null, zeroed before launch
 };
 
-// kVec: HW % 32 == 0 (see load_tile_nchw).  kGoutCL: g_out is channels-last (gs_d == 1).
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// kVec: HW % 32 == 0 and 16-byte aligned z / grad_z (the 32 latents of a tile are 32 consecutive hw positions of one
+// batch item).  kGoutCL: g_out is channels-last (gs_d == 1) with 16-byte aligned rows.
 template <bool kVec, bool kGoutCL>
-__global__ void __launch_bounds__(kBwdThreads)
+__global__ void __launch_bounds__(kBwdThreads, VQ_BWD_MIN_BLOCKS)
 vq_backward_kernel(const BackwardParams p) {
-    extern __shared__ __align__(16) float bsm[];
-    TileRow* zt = reinterpret_cast<TileRow*>(bsm);                          // z, then z - e
-    TileRow* gt = reinterpret_cast<TileRow*>(bsm + kD * (kSelRows + 1));    // upstream gradient
+    __shared__ __align__(16) float tile[kSelRows * kD];       // 32 KiB: z, then grad (kGoutCL) or diff
     __shared__ int idx_s[kSelRows];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int dsub = lane >> 3, hq = lane & 7;
     const int64_t n0 = (int64_t)blockIdx.x * kSelRows;
     // coef = 2 * g_loss / (n_global * D), evaluated like the oracle (double, rounded once)
     const float coef = (float)(2.0 * (double)(p.g_loss_dev != nullptr ? __ldg(p.g_loss_dev) : p.g_loss) * p.inv_nd);
+    const bool has_g = p.gout != nullptr && p.grad_z != nullptr;
 
     if (tid < kSelRows) {
         const int64_t n = n0 + tid;
@@ -57,111 +66,139 @@ vq_backward_kernel(const BackwardParams p) {
         idx_s[tid] = k;
     }
 
-    // 1. tiles
-    const bool has_g = p.gout != nullptr && p.grad_z != nullptr;
-    load_tile_nchw<kVec, true>(zt, p.z, n0, p.N, p.HW, warp, lane);
-    if (has_g) {
-        if (kGoutCL) {
-            // rows of 256 contiguous floats: warp w stages rows 4w..4w+3, lanes over d (8 requests per row in flight)
-            float v[4][kD / 32];
+    // 1. z tile, column form -> shared memory; the channels-last upstream gradient (row form) is requested right
+    //    behind it so that both streams are in flight together
+    if (kVec) {
+        const int64_t b = n0 / p.HW, hw0 = n0 % p.HW;
+        const float* src = p.z + (b * kD + dsub) * p.HW + hw0 + 4 * hq;
+        float4 v[8];
 #pragma unroll
-            for (int rr = 0; rr < 4; rr++) {
-                const int64_t n = n0 + warp * 4 + rr;
-                const float* g = p.gout + (n < p.N ? (n / p.HW) * p.gs_b + (n % p.HW) * p.gs_hw : 0);
+        for (int i = 0; i < 8; i++) v[i] = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)((warp * 8 + i) * 4) * p.HW));
 #pragma unroll
-                for (int i = 0; i < kD / 32; i++) v[rr][i] = (n < p.N) ? __ldcs(g + lane + 32 * i) : 0.0f;
-            }
-#pragma unroll
-            for (int rr = 0; rr < 4; rr++)
-#pragma unroll
-                for (int i = 0; i < kD / 32; i++) gt[lane + 32 * i][warp * 4 + rr] = v[rr][i];
-        } else if (kVec && p.gs_hw == 1 && p.gs_d % 4 == 0 && p.gs_b % 4 == 0 &&
-                   (reinterpret_cast<uintptr_t>(p.gout) & 15) == 0) {
-            // hw-contiguous (e.g. NCHW-contiguous) gradient: same access pattern as z, with its own strides
-            const int64_t b = n0 / p.HW, hw0 = n0 % p.HW;
-            const int dsub = lane >> 3, hq = lane & 7;
-            const float* src = p.gout + b * p.gs_b + dsub * p.gs_d + hw0 + 4 * hq;
-            float4 v[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                v[i] = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)((warp * 8 + i) * 4) * p.gs_d));
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                float* dst = &gt[(warp * 8 + i) * 4 + dsub][4 * hq];
-                dst[0] = v[i].x; dst[1] = v[i].y; dst[2] = v[i].z; dst[3] = v[i].w;
-            }
-        } else {
-            const int64_t n = n0 + lane;
-            const bool ok = n < p.N;
-            const float* g = p.gout + (ok ? (n / p.HW) * p.gs_b + (n % p.HW) * p.gs_hw : 0);
+        for (int i = 0; i < 8; i++) {
+            const int d = (warp * 8 + i) * 4 + dsub;
+            tile[tile_off(4 * hq + 0, d)] = v[i].x;
+            tile[tile_off(4 * hq + 1, d)] = v[i].y;
+            tile[tile_off(4 * hq + 2, d)] = v[i].z;
+            tile[tile_off(4 * hq + 3, d)] = v[i].w;
+        }
+    } else {
+        const int64_t n = n0 + lane;
+        const bool ok = n < p.N;
+        const int64_t b = ok ? n / p.HW : 0, hw = ok ? n % p.HW : 0;
+        const float* src = p.z + (b * kD) * p.HW + hw;
 #pragma unroll 8
-            for (int i = 0; i < kD / 8; i++) {
-                const int d = warp + 8 * i;
-                gt[d][lane] = ok ? __ldcs(g + (int64_t)d * p.gs_d) : 0.0f;
-            }
+        for (int i = 0; i < kD / 8; i++) {
+            const int d = warp + 8 * i;
+            tile[tile_off(lane, d)] = ok ? __ldcs(src + (int64_t)d * p.HW) : 0.0f;
+        }
+    }
+    float4 gv[4][2];
+    if (kGoutCL && has_g) {
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++) {
+            const int64_t n = n0 + warp * 4 + rr;
+            const float4* g4 = reinterpret_cast<const float4*>(p.gout + (n < p.N ? (n / p.HW) * p.gs_b + (n % p.HW) * p.gs_hw : 0));
+#pragma unroll
+            for (int h = 0; h < 2; h++) gv[rr][h] = (n < p.N) ? __ldcs(g4 + lane + 32 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
     }
     __syncthreads();
 
-    // 2. lanes over d: diff = z - e (kept in the tile), scatter-add into the codebook gradient
+    // 2. row form: diff = z - e, scatter-add into the codebook gradient, grad (or diff) back into the tile
     {
         const float ce = -(p.beta * coef);
-        float ev[4][kD / 32];
+        float4 ev[4][2];
         int kk[4];
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) {
             const int r = warp * 4 + rr;
             kk[rr] = (n0 + r < p.N) ? idx_s[r] : -1;
-            const float* e = p.E + (int64_t)max(kk[rr], 0) * kD;
+            const float4* e4 = reinterpret_cast<const float4*>(p.E + (int64_t)max(kk[rr], 0) * kD);
 #pragma unroll
-            for (int i = 0; i < kD / 32; i++) ev[rr][i] = (kk[rr] >= 0) ? __ldg(e + lane + 32 * i) : 0.0f;
+            for (int h = 0; h < 2; h++) ev[rr][h] = (kk[rr] >= 0) ? __ldg(e4 + lane + 32 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) {
             const int r = warp * 4 + rr;
-            float* ge = (p.grad_E != nullptr && kk[rr] >= 0) ? p.grad_E + (int64_t)kk[rr] * kD : nullptr;
+            const bool live = (n0 + r < p.N) && kk[rr] >= 0;
+            float4* zrow4 = reinterpret_cast<float4*>(tile + r * kD);
+            const int g = tile_swz(r);
+            float* ge = (p.grad_E != nullptr && live) ? p.grad_E + (int64_t)kk[rr] * kD : nullptr;
 #pragma unroll
-            for (int i = 0; i < kD / 32; i++) {
-                const int d = lane + 32 * i;
-                const float diff = (n0 + r < p.N) ? __fsub_rn(zt[d][r], ev[rr][i]) : 0.0f;
-                zt[d][r] = diff;
-                if (ge != nullptr) atomicAdd(ge + d, ce * diff);      // result unused -> RED.E.ADD.F32
+            for (int h = 0; h < 2; h++) {
+                const int q = lane + 32 * h;
+                const float4 zv = zrow4[q ^ g];
+                const float4 e = ev[rr][h];
+                float4 diff = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (live) {
+                    diff.x = __fsub_rn(zv.x, e.x); diff.y = __fsub_rn(zv.y, e.y);
+                    diff.z = __fsub_rn(zv.z, e.z); diff.w = __fsub_rn(zv.w, e.w);
+                }
+                if (ge != nullptr) red_add_v4(ge + 4 * q, ce * diff.x, ce * diff.y, ce * diff.z, ce * diff.w);
+                if (kGoutCL) {
+                    float4 o;
+                    const float4 gg = has_g ? gv[rr][h] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    o.x = __fmaf_rn(coef, diff.x, gg.x); o.y = __fmaf_rn(coef, diff.y, gg.y);
+                    o.z = __fmaf_rn(coef, diff.z, gg.z); o.w = __fmaf_rn(coef, diff.w, gg.w);
+                    zrow4[q ^ g] = o;
+                } else {
+                    zrow4[q ^ g] = diff;
+                }
             }
         }
     }
     if (p.grad_z == nullptr) return;
     __syncthreads();
 
-    // 3. grad_z = g_out + coef * diff, NCHW
+    // 3. column form: grad_z as NCHW.  With a channels-last g_out the tile already holds the result; otherwise it holds
+    //    diff and the upstream gradient is read here with its own strides (hw-contiguous: 16-byte loads like z).
     if (kVec) {
         const int64_t b = n0 / p.HW, hw0 = n0 % p.HW;
-        const int dsub = lane >> 3, hq = lane & 7;
         float* dstb = p.grad_z + (b * kD + dsub) * p.HW + hw0 + 4 * hq;
+        const bool g_vec = !kGoutCL && has_g && p.gs_hw == 1 && p.gs_d % 4 == 0 && p.gs_b % 4 == 0 &&
+                           (reinterpret_cast<uintptr_t>(p.gout) & 15) == 0;
+        const float* gsrc = has_g ? p.gout + b * p.gs_b + dsub * p.gs_d + (hw0 + 4 * hq) * p.gs_hw : nullptr;
+        float4 gq[8];
+        if (!kGoutCL) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                gq[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g_vec) {
+                    gq[i] = __ldcs(reinterpret_cast<const float4*>(gsrc + (int64_t)((warp * 8 + i) * 4) * p.gs_d));
+                } else if (has_g) {
+                    const float* gp = gsrc + (int64_t)((warp * 8 + i) * 4) * p.gs_d;
+                    gq[i].x = __ldcs(gp); gq[i].y = __ldcs(gp + p.gs_hw);
+                    gq[i].z = __ldcs(gp + 2 * p.gs_hw); gq[i].w = __ldcs(gp + 3 * p.gs_hw);
+                }
+            }
+        }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int d = (warp * 8 + i) * 4 + dsub;
             float4 o;
-            if (has_g) {
-                o.x = __fmaf_rn(coef, zt[d][4 * hq + 0], gt[d][4 * hq + 0]);
-                o.y = __fmaf_rn(coef, zt[d][4 * hq + 1], gt[d][4 * hq + 1]);
-                o.z = __fmaf_rn(coef, zt[d][4 * hq + 2], gt[d][4 * hq + 2]);
-                o.w = __fmaf_rn(coef, zt[d][4 * hq + 3], gt[d][4 * hq + 3]);
-            } else {
-                o.x = __fmaf_rn(coef, zt[d][4 * hq + 0], 0.0f);
-                o.y = __fmaf_rn(coef, zt[d][4 * hq + 1], 0.0f);
-                o.z = __fmaf_rn(coef, zt[d][4 * hq + 2], 0.0f);
-                o.w = __fmaf_rn(coef, zt[d][4 * hq + 3], 0.0f);
+            o.x = tile[tile_off(4 * hq + 0, d)];
+            o.y = tile[tile_off(4 * hq + 1, d)];
+            o.z = tile[tile_off(4 * hq + 2, d)];
+            o.w = tile[tile_off(4 * hq + 3, d)];
+            if (!kGoutCL) {
+                o.x = __fmaf_rn(coef, o.x, gq[i].x); o.y = __fmaf_rn(coef, o.y, gq[i].y);
+                o.z = __fmaf_rn(coef, o.z, gq[i].z); o.w = __fmaf_rn(coef, o.w, gq[i].w);
             }
             __stcs(reinterpret_cast<float4*>(dstb + (int64_t)((warp * 8 + i) * 4) * p.HW), o);
         }
     } else {
         const int64_t n = n0 + lane;
         if (n < p.N) {
-            float* dst = p.grad_z + ((n / p.HW) * kD) * p.HW + (n % p.HW);
+            const int64_t b = n / p.HW, hw = n % p.HW;
+            float* dst = p.grad_z + (b * kD) * p.HW + hw;
+            const float* g = (!kGoutCL && has_g) ? p.gout + b * p.gs_b + hw * p.gs_hw : nullptr;
 #pragma unroll 8
             for (int i = 0; i < kD / 8; i++) {
                 const int d = warp + 8 * i;
-                __stcs(dst + (int64_t)d * p.HW, __fmaf_rn(coef, zt[d][lane], has_g ? gt[d][lane] : 0.0f));
+                float o = tile[tile_off(lane, d)];
+                if (!kGoutCL) o = __fmaf_rn(coef, o, g != nullptr ? __ldcs(g + (int64_t)d * p.gs_d) : 0.0f);
+                __stcs(dst + (int64_t)d * p.HW, o);
             }
         }
     }

@@ -68,6 +68,17 @@ __device__ __forceinline__ void load_tile_nchw(TileRow* t, const float* __restri
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Row-major [32 latents x 256] fp32 tile in shared memory with the 16-byte pieces of row r XOR-swizzled by
+// g(r) = (r >> 2) ^ (2 (r & 3)).  Conflict-free for (a) the column-form fill / drain (lanes over 8 row groups x 4 d,
+// one row of each group per scalar access), (b) one warp reading the same piece of its 4 rows (8 lanes per row
+// broadcast) and (c) lanes over the pieces of one row (16-byte accesses, four wavefronts per 512 bytes).
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int tile_swz(int r) { return ((r >> 2) ^ ((r & 3) << 1)) & 7; }
+__device__ __forceinline__ int tile_off(int r, int d) {                    // word offset of element (r, d)
+    return r * kD + ((((d >> 2) ^ tile_swz(r)) << 2) | (d & 3));
+}
+
 // Offset (in 16-bit elements) of element (row, dl) -- dl in [0, 64) -- of block `block` in an "operand image": blocks of
 // `rows` x 64 elements stored exactly as a SWIZZLE_128B K-major UMMA operand sits in shared memory (row pitch 128 B,
 // the eight 16-byte pieces of a row XOR-ed with (row & 7)).  A block is contiguous, so it is loaded with one bulk copy.

@@ -47,24 +47,12 @@ struct SelectParams {
     unsigned long long* stats; // (VQ_STAT_COUNT) or null
 };
 
-// ---------------------------------------------------------------------------------------------------------------
-// The select kernel keeps its [32 latents x 256] fp32 tile ROW-major in shared memory -- the exact stage reads a whole
-// latent row per candidate, 16 bytes at a time -- with the 16-byte pieces of row r XOR-swizzled by
-// g(r) = (r >> 2) ^ (2 (r & 3)): conflict-free for (a) the tile fill (lanes over 8 row groups x 4 d, one row of each
-// group per store), (b) the exact stage (a warp reads the same piece of its 4 rows, 8 lanes per row broadcast) and
-// (c) the forward tail (lanes over d of one row).
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int sel_swz(int r) { return ((r >> 2) ^ ((r & 3) << 1)) & 7; }
-__device__ __forceinline__ int sel_off(int r, int d) {                     // word offset of element (r, d)
-    return r * kD + ((((d >> 2) ^ sel_swz(r)) << 2) | (d & 3));
-}
-
 // One canonical partial sum of the dot product of latent row r (tile row) with code k: the terms d == j (mod 4) in
 // ascending d, one fma each (oracle/vq_oracle.c: vqo_dot).  Four lanes (j = 0..3) share a (row, code) pair; all 64
 // code-row loads of a lane are independent and issued in two batches of 32, so a pass costs two L2 round trips.
 __device__ __forceinline__ float exact_partial_tile(const float* tile, int r, const float* __restrict__ E, int k, int j) {
     const float* e = E + (int64_t)k * kD + j;
-    const int g = sel_swz(r);
+    const int g = tile_swz(r);
     const float* zrow = tile + r * kD + j;
     int zo[8];
 #pragma unroll
@@ -91,7 +79,7 @@ __device__ __forceinline__ uint32_t dist_key(float d) {
 template <bool kForward, bool kVec>
 __global__ void __launch_bounds__(kSelThreads, 4)
 vq_select_kernel(const SelectParams p) {
-    __shared__ __align__(16) float tile[kSelRows * kD];       // 32 KiB, swizzled row-major (sel_off)
+    __shared__ __align__(16) float tile[kSelRows * kD];       // 32 KiB, swizzled row-major (vq_common.cuh tile_off)
     __shared__ int clist[kSelWarps][4][kMaxCands];            // candidate codes of each row of each warp
     __shared__ int idx_s[kSelRows];
     __shared__ double red_s[kSelWarps];
@@ -175,10 +163,10 @@ vq_select_kernel(const SelectParams p) {
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int d = (warp * 8 + i) * 4 + dsub;
-                tile[sel_off(4 * hq + 0, d)] = zreg[i].x;
-                tile[sel_off(4 * hq + 1, d)] = zreg[i].y;
-                tile[sel_off(4 * hq + 2, d)] = zreg[i].z;
-                tile[sel_off(4 * hq + 3, d)] = zreg[i].w;
+                tile[tile_off(4 * hq + 0, d)] = zreg[i].x;
+                tile[tile_off(4 * hq + 1, d)] = zreg[i].y;
+                tile[tile_off(4 * hq + 2, d)] = zreg[i].z;
+                tile[tile_off(4 * hq + 3, d)] = zreg[i].w;
             }
         } else {
             const int64_t n = n0 + lane;
@@ -188,7 +176,7 @@ vq_select_kernel(const SelectParams p) {
 #pragma unroll 8
             for (int i = 0; i < kD / 8; i++) {
                 const int d = warp + 8 * i;
-                tile[sel_off(lane, d)] = ok ? __ldg(src + (int64_t)d * p.HW) : 0.0f;
+                tile[tile_off(lane, d)] = ok ? __ldg(src + (int64_t)d * p.HW) : 0.0f;
             }
         }
     }
@@ -268,31 +256,39 @@ vq_select_kernel(const SelectParams p) {
     if (p.stats != nullptr && tid < 4 && st_s[tid] != 0) atomicAdd(p.stats + tid, (unsigned long long)st_s[tid]);
     if (!kForward) return;
 
-    // 3. forward tail: all four code rows of this warp are requested before the first one is consumed
+    // 3. forward tail, 16 bytes per lane and request: lane <-> d in [4 lane, 4 lane + 4) and [128 + 4 lane, ...); all four
+    //    code rows of this warp are requested before the first one is consumed
     float sq = 0.0f;
     {
-        float ev[4][kD / 32];
+        float4 ev[4][2];
         int kk[4];
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) {
             const int r = warp * 4 + rr;
             kk[rr] = (n0 + r < p.N) ? idx_s[r] : -1;
-            const float* e = p.E + (int64_t)max(kk[rr], 0) * kD;
+            const float4* e4 = reinterpret_cast<const float4*>(p.E + (int64_t)max(kk[rr], 0) * kD);
 #pragma unroll
-            for (int i = 0; i < kD / 32; i++) ev[rr][i] = (kk[rr] >= 0) ? __ldg(e + lane + 32 * i) : 0.0f;
+            for (int h = 0; h < 2; h++) ev[rr][h] = (kk[rr] >= 0) ? __ldg(e4 + lane + 32 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) {
             if (kk[rr] < 0) continue;
             const int r = warp * 4 + rr;
-            float* out = p.zq + (n0 + r) * kD;
+            const float4* zrow4 = reinterpret_cast<const float4*>(tile + r * kD);
+            const int g = tile_swz(r);
+            float4* out4 = reinterpret_cast<float4*>(p.zq + (n0 + r) * kD);
 #pragma unroll
-            for (int i = 0; i < kD / 32; i++) {
-                const int d = lane + 32 * i;
-                const float zv = tile[sel_off(r, d)];
-                const float diff = __fsub_rn(ev[rr][i], zv);       // fl(e - z)
-                __stcs(out + d, __fadd_rn(zv, diff));              // fl(z + fl(e - z)), codebook.py:106
-                sq = __fmaf_rn(diff, diff, sq);
+            for (int h = 0; h < 2; h++) {
+                const float4 zv = zrow4[(lane + 32 * h) ^ g];
+                const float4 e = ev[rr][h];
+                float4 diff, o;
+                diff.x = __fsub_rn(e.x, zv.x); diff.y = __fsub_rn(e.y, zv.y);     // fl(e - z)
+                diff.z = __fsub_rn(e.z, zv.z); diff.w = __fsub_rn(e.w, zv.w);
+                o.x = __fadd_rn(zv.x, diff.x); o.y = __fadd_rn(zv.y, diff.y);     // fl(z + fl(e - z)), codebook.py:106
+                o.z = __fadd_rn(zv.z, diff.z); o.w = __fadd_rn(zv.w, diff.w);
+                __stcs(out4 + lane + 32 * h, o);
+                sq = __fmaf_rn(diff.x, diff.x, sq); sq = __fmaf_rn(diff.y, diff.y, sq);
+                sq = __fmaf_rn(diff.z, diff.z, sq); sq = __fmaf_rn(diff.w, diff.w, sq);
             }
             if (p.hist != nullptr && lane == 0) atomicAdd(p.hist + kk[rr], 1ull);
         }
