@@ -322,8 +322,8 @@ static int forward_impl(bool training, const float* z, int64_t B, int64_t HW, in
         DevInfo* dev;
         rc = device_info(&dev);
         if (rc != VQ_OK) return rc;
-        // the kernel sizes its own work split from the worklist length; 128 registers x 256 threads -> 2 CTAs per SM
-        const unsigned fgrid = (unsigned)(2 * dev->sms);
+        // the kernel sizes its own work split from the worklist length so that one wave of resident CTAs covers it
+        const unsigned fgrid = (unsigned)(vq::kFbCtasPerSm * dev->sms);
         vq::vq_fallback_kernel<<<fgrid, vq::kFbThreads, 0, st>>>(fp);
         VQ_LAUNCH_CHECK("vq_fallback_kernel");
     }

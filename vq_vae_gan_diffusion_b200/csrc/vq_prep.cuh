@@ -18,13 +18,13 @@ constexpr int kCbE2Max = 0;      // max_k |e_k|^2
 constexpr int kCbMaxAbs = 1;     // max |E[k][d]|
 constexpr int kCbInvScale = 2;   // 2^(ex_E - 15): inverse of the fp16 operand scale
 
-// One CTA = 32 consecutive latents.  Tile held in shared memory as t[d][row] (+1 pad).
+// One CTA = 32 consecutive latents, tile in shared memory row-major with swizzled 16-byte pieces (vq_common.cuh
+// tile_off): column-form fill (16-byte loads along hw), then everything per latent row -- warp w owns rows 4w..4w+3.
 template <bool kVec>
 __global__ void __launch_bounds__(kPrepThreads)
 vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_pad,
                  __half* __restrict__ z_h, float* __restrict__ z2, float* __restrict__ z_inv_scale) {
-    __shared__ TileRow t[kD];
-    __shared__ float scale_s[kSelRows];
+    __shared__ __align__(16) float tile[kSelRows * kD];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n0 = (int64_t)blockIdx.x * kSelRows;
 
@@ -39,46 +39,83 @@ vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_p
         }
         return;
     }
-    load_tile_nchw<kVec, false>(t, z, n0, N, HW, warp, lane);
-    __syncthreads();
-
-    // |z|^2 in canonical order and max|z|: 4 threads per row, thread j owns the terms d == j (mod 4)
-    if (tid < 4 * kSelRows) {
-        const int r = tid >> 2, j = tid & 3;
-        float p = 0.0f, mx = 0.0f;
-#pragma unroll 16
-        for (int q = 0; q < kD / 4; q++) {
-            const float v = t[4 * q + j][r];
-            p = __fmaf_rn(v, v, p);
-            mx = fmaxf(mx, fabsf(v));
+    if (kVec) {
+        const int dsub = lane >> 3, hq = lane & 7;
+        const int64_t b = n0 / HW, hw0 = n0 % HW;
+        const float* src = z + (b * kD + dsub) * HW + hw0 + 4 * hq;
+        float4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)((warp * 8 + i) * 4) * HW));
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int d = (warp * 8 + i) * 4 + dsub;
+            tile[tile_off(4 * hq + 0, d)] = v[i].x;
+            tile[tile_off(4 * hq + 1, d)] = v[i].y;
+            tile[tile_off(4 * hq + 2, d)] = v[i].z;
+            tile[tile_off(4 * hq + 3, d)] = v[i].w;
         }
-        const float s = combine4(p);
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        if (j == 0) {
-            const int ex = exponent_of(mx);
-            scale_s[r] = pow2f(kOperandTopExp - ex);
-            if (n0 + r < N) { z2[n0 + r] = s; z_inv_scale[n0 + r] = pow2f(ex - kOperandTopExp); }
+    } else {
+        const int64_t n = n0 + lane;
+        const bool ok = n < N;
+        const int64_t b = ok ? n / HW : 0, hw = ok ? n % HW : 0;
+        const float* src = z + (b * kD) * HW + hw;
+#pragma unroll 8
+        for (int i = 0; i < kD / 8; i++) {
+            const int d = warp + 8 * i;
+            tile[tile_off(lane, d)] = ok ? __ldg(src + (int64_t)d * HW) : 0.0f;      // rows >= N: zero operand rows
         }
     }
     __syncthreads();
 
-    // fp16 rows: warp w writes rows 4w..4w+3, lane covers d = 2*lane + 64*i (4-byte stores, 128 B per warp request)
+    // |z|^2 in canonical order and max|z|: lanes 0..15 of warp w = (row 4w + (lane >> 2), partial j = lane & 3), each
+    // a chain of 64 fma over d == j (mod 4) ascending.  (4 rows x 4 d-offsets of one piece: conflict-free.)
+    float sc_row;                                            // operand scale of row 4w + (lane >> 3) ... see below
+    {
+        const int rr = (lane >> 2) & 3, j = lane & 3;
+        const int r = warp * 4 + rr;
+        const float* zrow = tile + r * kD + j;
+        const int g = tile_swz(r);
+        float p = 0.0f, mx = 0.0f;
+        if (lane < 16) {
+#pragma unroll 16
+            for (int q = 0; q < kD / 4; q++) {
+                const float v = zrow[(q ^ g) << 2];
+                p = __fmaf_rn(v, v, p);
+                mx = fmaxf(mx, fabsf(v));
+            }
+        }
+        const float s = combine4(p);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const int ex = exponent_of(mx);
+        if (lane < 16 && j == 0 && n0 + r < N) { z2[n0 + r] = s; z_inv_scale[n0 + r] = pow2f(ex - kOperandTopExp); }
+        sc_row = pow2f(kOperandTopExp - ex);                 // valid on lanes 0..15: scale of row 4w + (lane >> 2)
+    }
+
+    // fp16 operand rows: lane owns d in [4 lane, 4 lane + 4) and [128 + 4 lane, ...): two 16-byte reads and two 8-byte
+    // stores per row; lanes 0..15 / 16..31 of a store cover one full 128-byte row of two D chunks of the operand image
+    // ([row tile][64-wide D chunk][128 rows][128 B], 16-byte pieces XOR-swizzled by (row & 7): the exact shared-memory
+    // image of a SWIZZLE_128B K-major UMMA operand, so the GEMM loads a chunk with ONE contiguous bulk copy)
 #pragma unroll
     for (int rr = 0; rr < 4; rr++) {
         const int r = warp * 4 + rr;
         const int64_t n = n0 + r;
-        if (n >= n_pad) break;
-        const float sc = scale_s[r];
-        // operand image: [row tile][64-wide D chunk][128 rows][128 B], 16-byte pieces XOR-swizzled by (row & 7) -- the
-        // exact shared-memory image of a SWIZZLE_128B K-major UMMA operand, so a chunk is ONE contiguous bulk copy
+        const float sc = __shfl_sync(0xffffffffu, sc_row, 4 * rr);
+        if (n >= n_pad) continue;                            // warp-uniform
+        const float4* zrow4 = reinterpret_cast<const float4*>(tile + r * kD);
+        const int g = tile_swz(r);
         const int64_t rt = n / kRowTile;
         const int rr_t = (int)(n % kRowTile);
 #pragma unroll
-        for (int i = 0; i < kNumDChunks; i++) {
-            const int d = 2 * lane + 64 * i;
-            __half2* dst = reinterpret_cast<__half2*>(z_h + operand_image_offset(rt * kNumDChunks + i, kRowTile, rr_t, 2 * lane));
-            *dst = __floats2half2_rn(t[d][r] * sc, t[d + 1][r] * sc);   // rows >= N were zero-filled above
+        for (int h = 0; h < 2; h++) {
+            const int q = lane + 32 * h;                     // d = 4q .. 4q + 3
+            const float4 v = zrow4[q ^ g];
+            const int d = 4 * q;
+            __half2 lo = __floats2half2_rn(v.x * sc, v.y * sc), hi = __floats2half2_rn(v.z * sc, v.w * sc);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(z_h + operand_image_offset(rt * kNumDChunks + d / kDChunk, kRowTile, rr_t, d % kDChunk)) = pk;
         }
     }
 }

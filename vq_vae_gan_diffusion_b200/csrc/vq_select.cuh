@@ -27,6 +27,8 @@ constexpr int kFbThreads = 256;
 constexpr int kFbGroup = 8;             // overflowed rows scanned together (they share every code-row load)
 constexpr int kFbMaxGroups = 512;       // row groups whose scan is split over code blocks (4096 rows)
 constexpr int kFbMaxParts = 256;        // code blocks per group
+constexpr int kFbCtasPerSm = 3;         // resident CTAs per SM the kernel is tuned for (registers, 45 KiB of shared memory)
+constexpr int kFbPitch = 36;            // floats per staged code-row segment (32 + 4: 144-byte pitch, conflict-free)
 
 struct SelectParams {
     const float* z;            // (B, D, HW) fp32
@@ -355,9 +357,10 @@ __device__ __forceinline__ void merge_min(float& d, int& k, int& c, float d2, in
 // over the whole chip (one or two codes per thread), while a degenerate codebook (every row overflows) gets one CTA
 // per group scanning all codes with no merge step.  The last code block of a group to arrive merges the per-block
 // minima cooperatively.
-__global__ void __launch_bounds__(kFbThreads)
+__global__ void __launch_bounds__(kFbThreads, kFbCtasPerSm)
 vq_fallback_kernel(const FallbackParams p) {
     __shared__ float4 zr4[kFbGroup][kD / 4];
+    __shared__ __align__(16) float stage[kFbThreads / 32][32 * kFbPitch];      // 36 KiB: per-warp [32 codes][32 d] transposer
     __shared__ float sd[kFbGroup][kFbThreads / 32];
     __shared__ int sk[kFbGroup][kFbThreads / 32], sn[kFbGroup][kFbThreads / 32];
     __shared__ int64_t row_s[kFbGroup];
@@ -392,28 +395,50 @@ vq_fallback_kernel(const FallbackParams p) {
             best_d[r] = INFINITY; best_k[r] = 0x7fffffff; n_at_min[r] = 0;
         }
         const int k_hi = min(p.K, (part0 + 1) * per_part);
-        for (int k = part0 * per_part + tid; k < k_hi; k += kFbThreads) {   // ascending k per thread
-            const float4* e4 = reinterpret_cast<const float4*>(p.E + (int64_t)k * kD);
+        // A warp scans 32 consecutive codes at a time, one code per lane (ascending k per lane).  The code rows are
+        // fetched COALESCED -- per 128-byte column block, 8 lanes x 16 bytes per code row, 4 rows per request -- and
+        // transposed through a padded per-warp staging buffer, so that every lane then reads its own code's 32 values
+        // with 16-byte shared-memory loads (row pitch 144 B: conflict-free both ways).  Latency is covered by the other resident warps (3 CTAs per SM).
+        float* stg = &stage[warp][0];
+        const int lc = lane >> 3, ls = lane & 7;
+        for (int kb = part0 * per_part + warp * 32; kb < k_hi; kb += kFbThreads) {
+            const int k = kb + lane;
             float acc[kFbGroup][4];
 #pragma unroll
             for (int r = 0; r < kFbGroup; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
-#pragma unroll 8
-            for (int q = 0; q < kD / 4; q++) {
-                const float4 e = __ldg(e4 + q);
+#pragma unroll 1
+            for (int db = 0; db < kD / 32; db++) {
+                float4 pre[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const int c = 4 * i + lc;
+                    pre[i] = (kb + c < k_hi) ? __ldg(reinterpret_cast<const float4*>(p.E + (int64_t)(kb + c) * kD) + 8 * db + ls)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) *reinterpret_cast<float4*>(stg + (4 * i + lc) * kFbPitch + 4 * ls) = pre[i];
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const float4 e = *reinterpret_cast<const float4*>(stg + lane * kFbPitch + 4 * j);
+#pragma unroll
+                    for (int r = 0; r < kFbGroup; r++) {
+                        const float4 zv = zr4[r][8 * db + j];
+                        acc[r][0] = __fmaf_rn(zv.x, e.x, acc[r][0]);
+                        acc[r][1] = __fmaf_rn(zv.y, e.y, acc[r][1]);
+                        acc[r][2] = __fmaf_rn(zv.z, e.z, acc[r][2]);
+                        acc[r][3] = __fmaf_rn(zv.w, e.w, acc[r][3]);
+                    }
+                }
+                __syncwarp();
+            }
+            if (k < k_hi) {
+                const float e2k = __ldg(p.e2 + k);
 #pragma unroll
                 for (int r = 0; r < kFbGroup; r++) {
-                    const float4 zv = zr4[r][q];
-                    acc[r][0] = __fmaf_rn(zv.x, e.x, acc[r][0]);
-                    acc[r][1] = __fmaf_rn(zv.y, e.y, acc[r][1]);
-                    acc[r][2] = __fmaf_rn(zv.z, e.z, acc[r][2]);
-                    acc[r][3] = __fmaf_rn(zv.w, e.w, acc[r][3]);
+                    const float dot = __fadd_rn(__fadd_rn(acc[r][0], acc[r][1]), __fadd_rn(acc[r][2], acc[r][3]));
+                    merge_min(best_d[r], best_k[r], n_at_min[r], ref_distance(z2[r], e2k, dot), k, 1);
                 }
-            }
-            const float e2k = __ldg(p.e2 + k);
-#pragma unroll
-            for (int r = 0; r < kFbGroup; r++) {
-                const float dot = __fadd_rn(__fadd_rn(acc[r][0], acc[r][1]), __fadd_rn(acc[r][2], acc[r][3]));
-                merge_min(best_d[r], best_k[r], n_at_min[r], ref_distance(z2[r], e2k, dot), k, 1);
             }
         }
         // block-level merge of the per-thread minima: warp shuffles, then thread r finishes row r
