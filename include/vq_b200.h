@@ -81,6 +81,32 @@ int vq_argmin(const float* z_nchw, int64_t B, int64_t HW, int D,
               void* workspace, size_t workspace_bytes, vq_stream_t stream);
 
 /*
+ * Tokeniser mode with narrow indices (the token stream fed to the stage-2 models,
+ * network/vqTransformer/vqTransformer.py:79,117-141, never needs 64 bits): as vq_argmin, but idx holds
+ * idx_bits-wide integers -- 64 (int64), 32 (int32) or 16 (uint16, K <= 65536).  Opt-in: the reference's own dtype
+ * is int64.
+ */
+int vq_argmin_narrow(const float* z_nchw, int64_t B, int64_t HW, int D,
+                     const float* E, const void* E_h, const float* e_norm2, const float* cb_scalars, int K,
+                     void* idx, int idx_bits, unsigned long long* stats,
+                     void* workspace, size_t workspace_bytes, vq_stream_t stream);
+
+/*
+ * Nearest-code search over ROW-MAJOR vectors.  Same fp32 distance formula
+ * |x|^2 + |e|^2 - 2 x.e and first-minimum argmin as vq_argmin, for callers that hold (N, D) rows instead of an
+ * NCHW latent grid.  Replaces GaussianDiffusion2D.gaussian_to_indices
+ * (network/vqDiffusion/submodule/diffusion_gaussian2d.py:322-347: gaussian_flat (B*L, gaussian_dim) against
+ * gaussian_lookup_table (K, gaussian_dim)).  D must be 256 here; narrower vectors (gaussian_dim = 96 in
+ * configs/*.yml) are zero-padded by the caller, which changes no distance (see nearest.py).
+ *   x_rows  (N, D) fp32, contiguous
+ *   idx     (N) integers of idx_bits (64 / 32 / 16)
+ */
+int vq_argmin_rows(const float* x_rows, int64_t N, int D,
+                   const float* E, const void* E_h, const float* e_norm2, const float* cb_scalars, int K,
+                   void* idx, int idx_bits, unsigned long long* stats,
+                   void* workspace, size_t workspace_bytes, vq_stream_t stream);
+
+/*
  * Training forward.  Replaces CodeBook.forward, codebook.py:47-111.
  *   zq_nhwc (N, D) fp32 -- fl(z + fl(e - z)) in NHWC memory (the caller exposes it as the NCHW view the
  *                          reference returns, codebook.py:109)

@@ -76,3 +76,23 @@ def make_inputs(spec: dict):
 def sample_positions(n_elems: int, seed: int) -> np.ndarray:
     rng = np.random.default_rng(seed + 7919)
     return np.sort(rng.choice(n_elems, size=min(N_SAMPLES, n_elems), replace=False)).astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Row-major nearest-code search: GaussianDiffusion2D.gaussian_to_indices,
+# diffusion_gaussian2d.py:322-347.  Table = torch.rand(K, gaussian_dim) there (:287), gaussian_dim = 96 in configs/*.yml.
+NN_CASES = {
+    "nn_g96_clean":   dict(B=4, L=64, K=1024, D=96, noise=0.05, distribute_dim=2, seed=201),   # denoised vectors near table rows
+    "nn_g96_noisy":   dict(B=3, L=50, K=2048, D=96, noise=1.0, distribute_dim=2, seed=202),    # far from every row: near ties
+    "nn_g96_dim1":    dict(B=2, L=32, K=300, D=96, noise=0.2, distribute_dim=1, seed=203),     # (B, D, L) input, permuted inside
+    "nn_d256":        dict(B=2, L=40, K=512, D=256, noise=0.3, distribute_dim=2, seed=204),
+}
+
+
+def make_nn_inputs(spec: dict):
+    """-> x (B, L, D) fp32, table (K, D) fp32 (uniform [0, 1) like the reference's buffer)."""
+    rng = np.random.default_rng(spec["seed"])
+    B, L, K, D = spec["B"], spec["L"], spec["K"], spec["D"]
+    table = rng.random((K, D), dtype=np.float32)
+    x = table[rng.integers(0, K, size=B * L)] + np.float32(spec["noise"]) * rng.standard_normal((B * L, D), dtype=np.float32)
+    return np.ascontiguousarray(x.reshape(B, L, D), dtype=np.float32), table

@@ -152,3 +152,44 @@ def test_oracle_backward_n_global(oracle):
         gE_sum += gEi
     assert_close(np.concatenate(parts, 0), gz, "sharded grad_z")
     assert_close(gE_sum, gE, "sharded grad_E")
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Row-major nearest-code search: the same oracle, fed (N, D) rows as an (N, D, 1, 1) grid, against the
+# outputs of the reference's GaussianDiffusion2D.gaussian_to_indices (tests/golden/make_golden_nn.py).
+from cases import NN_CASES, make_nn_inputs  # noqa: E402
+
+
+def _rows_as_grid(x):
+    rows = x.reshape(-1, x.shape[-1])
+    return np.ascontiguousarray(rows.reshape(rows.shape[0], rows.shape[1], 1, 1))
+
+
+@pytest.mark.parametrize("name", sorted(NN_CASES))
+def test_oracle_matches_reference_nearest_rows(name, oracle):
+    spec = NN_CASES[name]
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    x, table = make_nn_inputs(spec)
+    z = _rows_as_grid(x)
+    ref = oracle.forward(z, table, want_zq=False)
+    assert tuple(gold["idx_shape"]) == (spec["B"], spec["L"])
+    cls = classify_index_mismatches(z, table, ref["idx"], gold["idx"].reshape(-1).astype(np.int64), pair_dist=oracle.pair_dist)
+    assert cls["real"] == 0, cls
+    assert cls["mismatch"] <= int(gold["ref_tie_rows"]) + int(gold["ref_ne_fp64"]) + 2, cls
+
+
+@pytest.mark.parametrize("name", ["nn_g96_clean", "nn_g96_noisy"])
+def test_zero_padding_changes_no_distance(name, oracle):
+    """The CUDA path runs 96-wide tables zero-padded to 256 columns: in the canonical order a zero column adds
+    fma(0, 0, p) == p, so indices, ties and minimal distances are bit-identical."""
+    spec = NN_CASES[name]
+    x, table = make_nn_inputs(spec)
+    z = _rows_as_grid(x)
+    a = oracle.forward(z, table, want_zq=False)
+    zp = np.zeros((z.shape[0], 256, 1, 1), np.float32)
+    zp[:, : z.shape[1]] = z
+    tp = np.zeros((table.shape[0], 256), np.float32)
+    tp[:, : table.shape[1]] = table
+    b = oracle.forward(zp, tp, want_zq=False)
+    assert np.array_equal(a["idx"], b["idx"]) and a["tie_rows"] == b["tie_rows"]
+    assert np.array_equal(a["dist_min"], b["dist_min"])

@@ -16,8 +16,9 @@ import types
 from . import _native
 from ._native import VQNativeError, build
 from .codebook import CodeBook, vq_embed_nchw
+from .nearest import CodeTable, nearest_indices
 
-__all__ = ["CodeBook", "vq_embed_nchw", "VQNativeError", "build", "install"]
+__all__ = ["CodeBook", "vq_embed_nchw", "CodeTable", "nearest_indices", "VQNativeError", "build", "install"]
 
 REFERENCE_MODULE = "network.vqvae.submodule.codebook"
 

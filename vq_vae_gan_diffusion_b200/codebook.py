@@ -197,9 +197,14 @@ class CodeBook(nn.Module):
         return _VQFunction.apply(z, self.codebook.weight, self)
 
     @torch.no_grad()
-    def encode_indices(self, z: torch.Tensor) -> torch.Tensor:
-        """Tokeniser mode (vq_argmin): what VQTransformer/VQDiffusion.encode_to_z keep of the forward."""
+    def encode_indices(self, z: torch.Tensor, dtype=torch.int64) -> torch.Tensor:
+        """Tokeniser mode (vq_argmin): what VQTransformer/VQDiffusion.encode_to_z keep of the forward.
+
+        ``dtype`` opts into a narrower token stream (int32; int16 for K <= 32768; uint16 for K <= 65536) -- the
+        reference's own dtype is int64."""
+        from .nearest import _index_bits
         self._check_input(z)
+        bits = _index_bits(dtype, self.codebook.weight.shape[0])
         B, D, H, W = z.shape
         weight = self.codebook.weight
         K = weight.shape[0]
@@ -207,11 +212,15 @@ class CodeBook(nn.Module):
         zc = z.contiguous()
         with torch.cuda.device(dev):
             E_h, e2, cb = self._derived(weight)
-            idx = torch.empty((B * H * W,), dtype=torch.int64, device=dev)
+            idx = torch.empty((B * H * W,), dtype=dtype, device=dev)
             stats = torch.empty((4,), dtype=torch.int64, device=dev)
             ws = self._workspace.get(_native.workspace_bytes(B * H * W, K, D), dev)
-            rc = _native.lib().vq_argmin(_ptr(zc), B, H * W, D, _ptr(weight), _ptr(E_h), _ptr(e2), _ptr(cb), K,
-                                         _ptr(idx), _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr(dev))
+            if bits == 64:
+                rc = _native.lib().vq_argmin(_ptr(zc), B, H * W, D, _ptr(weight), _ptr(E_h), _ptr(e2), _ptr(cb), K,
+                                             _ptr(idx), _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr(dev))
+            else:
+                rc = _native.lib().vq_argmin_narrow(_ptr(zc), B, H * W, D, _ptr(weight), _ptr(E_h), _ptr(e2), _ptr(cb), K,
+                                                    _ptr(idx), bits, _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr(dev))
             _native.check(rc, "vq_argmin")
             self._launches = int(_native.lib().vq_last_launch_count())
         self.last_stats = stats

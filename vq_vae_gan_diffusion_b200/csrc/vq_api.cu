@@ -150,7 +150,14 @@ int check_common(const void* z, int64_t B, int64_t HW, int D, int K) {
 }
 
 // shared front half of vq_argmin / vq_forward / vq_debug_scores: prep z + GEMM with fused candidate argmin
-int run_gemm(const float* z, int64_t N, int64_t HW, const void* E_h, const float* e2, const float* cb, int K,
+// layout of the latents: row-major (N, D) when `rows`, else NCHW (N / HW, D, HW) with the 16-byte fast path when possible
+int pick_layout(const float* z, int64_t HW, bool rows) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(z) & 15) == 0;
+    if (rows) return aligned ? vq::kLayoutRows : vq::kLayoutGeneric;       // (N, D) == NCHW with HW == 1
+    return (HW % vq::kSelRows == 0 && aligned) ? vq::kLayoutVec : vq::kLayoutGeneric;
+}
+
+int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, const void* E_h, const float* e2, const float* cb, int K,
              const Workspace& w, float* dbg_scores, cudaStream_t st) {
     DevInfo* dev;
     int rc = device_info(&dev);
@@ -158,14 +165,17 @@ int run_gemm(const float* z, int64_t N, int64_t HW, const void* E_h, const float
     const int64_t n_pad = round_up(N, vq::kRowTile);
     const int k_pad = vq_padded_codes(K);
 
-    // 16-byte tile accesses need 32-latent tiles that are hw-contiguous and 16-byte aligned
-    const bool vec = (HW % vq::kSelRows == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
-    if (vec)
-        vq::vq_prep_z_kernel<true><<<(unsigned)(n_pad / vq::kSelRows), vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h,
-                                                                                                  w.z2, w.z_inv_scale);
-    else
-        vq::vq_prep_z_kernel<false><<<(unsigned)(n_pad / vq::kSelRows), vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h,
-                                                                                                   w.z2, w.z_inv_scale);
+    const unsigned pgrid = (unsigned)(n_pad / vq::kSelRows);
+    switch (pick_layout(z, HW, rows)) {
+        case vq::kLayoutRows:
+            vq::vq_prep_z_kernel<vq::kLayoutRows><<<pgrid, vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2, w.z_inv_scale);
+            break;
+        case vq::kLayoutVec:
+            vq::vq_prep_z_kernel<vq::kLayoutVec><<<pgrid, vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2, w.z_inv_scale);
+            break;
+        default:
+            vq::vq_prep_z_kernel<vq::kLayoutGeneric><<<pgrid, vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2, w.z_inv_scale);
+    }
     VQ_LAUNCH_CHECK("vq_prep_z_kernel");
 
     vq::GemmParams gp;
@@ -284,8 +294,8 @@ VQ_EXPORT int vq_prepare_codebook(const float* E, int K, int D, void* E_h, float
     return VQ_OK;
 }
 
-static int forward_impl(bool training, const float* z, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
-                        const float* e2, const float* cb, int K, float beta, float* zq, int64_t* idx, float* loss,
+static int forward_impl(bool training, bool rows, const float* z, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
+                        const float* e2, const float* cb, int K, float beta, float* zq, void* idx, int idx_bits, float* loss,
                         int64_t* hist, unsigned long long* stats, void* ws, size_t ws_bytes, vq_stream_t stream) {
     g_launches = 0;
     int rc = check_common(z, B, HW, D, K);
@@ -309,7 +319,9 @@ static int forward_impl(bool training, const float* z, int64_t B, int64_t HW, in
     rc = check_ws(ws, ws_bytes, N, &w);
     if (rc != VQ_OK) return rc;
 
-    rc = run_gemm(z, N, HW, E_h, e2, cb, K, w, nullptr, st);
+    if (idx_bits != 64 && idx_bits != 32 && idx_bits != 16) return fail(VQ_E_INVALID, "idx_bits must be 16, 32 or 64, got %d", idx_bits);
+    if (idx_bits == 16 && K > 65536) return fail(VQ_E_INVALID, "16-bit indices need K <= 65536, got K=%d", K);
+    rc = run_gemm(z, N, HW, rows, E_h, e2, cb, K, w, nullptr, st);
     if (rc != VQ_OK) return rc;
 
     {   // rows whose candidate list overflowed (rare): exact scan, one CTA per row; a no-op when the worklist is empty
@@ -332,18 +344,19 @@ static int forward_impl(bool training, const float* z, int64_t B, int64_t HW, in
     sp.z = z; sp.E = E; sp.e2 = e2; sp.z2 = w.z2;
     sp.out_cnt = w.out_cnt; sp.out_q = w.out_q;
     sp.N = N; sp.HW = HW; sp.K = K; sp.beta = beta;
-    sp.idx = idx; sp.zq = zq;
+    sp.idx = idx; sp.idx_bits = idx_bits; sp.zq = zq;
     sp.hist = reinterpret_cast<unsigned long long*>(hist);
     sp.loss_partial = w.loss_partial; sp.blocks_done = w.blocks_done; sp.loss = loss;
     sp.stats = stats;
     const unsigned grid = (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows);
-    const bool vec = (HW % vq::kSelRows == 0) && ((reinterpret_cast<uintptr_t>(z) & 15) == 0);
+    const int layout = pick_layout(z, HW, rows);
     if (training) {
-        if (vec) vq::vq_select_kernel<true, true><<<grid, vq::kSelThreads, 0, st>>>(sp);
-        else     vq::vq_select_kernel<true, false><<<grid, vq::kSelThreads, 0, st>>>(sp);
+        if (layout == vq::kLayoutVec) vq::vq_select_kernel<true, vq::kLayoutVec><<<grid, vq::kSelThreads, 0, st>>>(sp);
+        else                          vq::vq_select_kernel<true, vq::kLayoutGeneric><<<grid, vq::kSelThreads, 0, st>>>(sp);
     } else {
-        if (vec) vq::vq_select_kernel<false, true><<<grid, vq::kSelThreads, 0, st>>>(sp);
-        else     vq::vq_select_kernel<false, false><<<grid, vq::kSelThreads, 0, st>>>(sp);
+        if (layout == vq::kLayoutRows)     vq::vq_select_kernel<false, vq::kLayoutRows><<<grid, vq::kSelThreads, 0, st>>>(sp);
+        else if (layout == vq::kLayoutVec) vq::vq_select_kernel<false, vq::kLayoutVec><<<grid, vq::kSelThreads, 0, st>>>(sp);
+        else                               vq::vq_select_kernel<false, vq::kLayoutGeneric><<<grid, vq::kSelThreads, 0, st>>>(sp);
     }
     VQ_LAUNCH_CHECK("vq_select_kernel");
     return VQ_OK;
@@ -352,7 +365,21 @@ static int forward_impl(bool training, const float* z, int64_t B, int64_t HW, in
 VQ_EXPORT int vq_argmin(const float* z_nchw, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
                         const float* e_norm2, const float* cb_scalars, int K, int64_t* idx, unsigned long long* stats,
                         void* workspace, size_t workspace_bytes, vq_stream_t stream) {
-    return forward_impl(false, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, 0.0f, nullptr, idx, nullptr, nullptr,
+    return forward_impl(false, false, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, 0.0f, nullptr, idx, 64, nullptr, nullptr,
+                        stats, workspace, workspace_bytes, stream);
+}
+
+VQ_EXPORT int vq_argmin_narrow(const float* z_nchw, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
+                               const float* e_norm2, const float* cb_scalars, int K, void* idx, int idx_bits,
+                               unsigned long long* stats, void* workspace, size_t workspace_bytes, vq_stream_t stream) {
+    return forward_impl(false, false, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, 0.0f, nullptr, idx, idx_bits, nullptr,
+                        nullptr, stats, workspace, workspace_bytes, stream);
+}
+
+VQ_EXPORT int vq_argmin_rows(const float* x_rows, int64_t N, int D, const float* E, const void* E_h, const float* e_norm2,
+                             const float* cb_scalars, int K, void* idx, int idx_bits, unsigned long long* stats,
+                             void* workspace, size_t workspace_bytes, vq_stream_t stream) {
+    return forward_impl(false, true, x_rows, N, 1, D, E, E_h, e_norm2, cb_scalars, K, 0.0f, nullptr, idx, idx_bits, nullptr, nullptr,
                         stats, workspace, workspace_bytes, stream);
 }
 
@@ -360,7 +387,7 @@ VQ_EXPORT int vq_forward(const float* z_nchw, int64_t B, int64_t HW, int D, cons
                          const float* e_norm2, const float* cb_scalars, int K, float beta, float* zq_nhwc, int64_t* idx,
                          float* loss, int64_t* hist, unsigned long long* stats, void* workspace, size_t workspace_bytes,
                          vq_stream_t stream) {
-    return forward_impl(true, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, beta, zq_nhwc, idx, loss, hist, stats,
+    return forward_impl(true, false, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, beta, zq_nhwc, idx, 64, loss, hist, stats,
                         workspace, workspace_bytes, stream);
 }
 
@@ -376,7 +403,7 @@ VQ_EXPORT int vq_debug_scores(const float* z_nchw, int64_t B, int64_t HW, int D,
     Workspace w;
     rc = check_ws(workspace, workspace_bytes, N, &w);
     if (rc != VQ_OK) return rc;
-    return run_gemm(z_nchw, N, HW, E_h, e_norm2, cb_scalars, K, w, scores, reinterpret_cast<cudaStream_t>(stream));
+    return run_gemm(z_nchw, N, HW, false, E_h, e_norm2, cb_scalars, K, w, scores, reinterpret_cast<cudaStream_t>(stream));
 }
 
 VQ_EXPORT int vq_backward(const float* gout, const int64_t* gout_strides, float g_loss, const float* g_loss_dev,

@@ -79,6 +79,32 @@ __device__ __forceinline__ int tile_off(int r, int d) {                    // wo
     return r * kD + ((((d >> 2) ^ tile_swz(r)) << 2) | (d & 3));
 }
 
+// Input layouts of the latent tensor, as seen by the tile kernels.
+constexpr int kLayoutGeneric = 0;   // NCHW (B, D, HW), any HW: lanes over latents, scalar accesses
+constexpr int kLayoutVec = 1;       // NCHW with HW % 32 == 0 and 16-byte aligned base: 16-byte accesses along hw
+constexpr int kLayoutRows = 2;      // row-major (N, D) vectors, 16-byte aligned: 16-byte accesses along d
+
+// Tile fill for kLayoutRows: warp w loads rows 4w..4w+3, lane owns pieces (lane, 32 + lane) of each (8 requests of 16 bytes
+// in flight per thread).  Rows >= N are zero-filled.
+__device__ __forceinline__ void fill_tile_rows(float* tile, const float* __restrict__ x, int64_t n0, int64_t N, int warp, int lane) {
+    float4 v[4][2];
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const int64_t n = n0 + warp * 4 + rr;
+        const float4* src = reinterpret_cast<const float4*>(x + (n < N ? n : 0) * kD);
+#pragma unroll
+        for (int h = 0; h < 2; h++) v[rr][h] = (n < N) ? __ldg(src + lane + 32 * h) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const int r = warp * 4 + rr;
+        float4* row4 = reinterpret_cast<float4*>(tile + r * kD);
+        const int g = tile_swz(r);
+#pragma unroll
+        for (int h = 0; h < 2; h++) row4[(lane + 32 * h) ^ g] = v[rr][h];
+    }
+}
+
 // Offset (in 16-bit elements) of element (row, dl) -- dl in [0, 64) -- of block `block` in an "operand image": blocks of
 // `rows` x 64 elements stored exactly as a SWIZZLE_128B K-major UMMA operand sits in shared memory (row pitch 128 B,
 // the eight 16-byte pieces of a row XOR-ed with (row & 7)).  A block is contiguous, so it is loaded with one bulk copy.

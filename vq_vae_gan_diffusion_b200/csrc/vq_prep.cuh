@@ -20,7 +20,7 @@ constexpr int kCbInvScale = 2;   // 2^(ex_E - 15): inverse of the fp16 operand s
 
 // One CTA = 32 consecutive latents, tile in shared memory row-major with swizzled 16-byte pieces (vq_common.cuh
 // tile_off): column-form fill (16-byte loads along hw), then everything per latent row -- warp w owns rows 4w..4w+3.
-template <bool kVec>
+template <int kLayout>
 __global__ void __launch_bounds__(kPrepThreads)
 vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_pad,
                  __half* __restrict__ z_h, float* __restrict__ z2, float* __restrict__ z_inv_scale) {
@@ -28,7 +28,7 @@ vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_p
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n0 = (int64_t)blockIdx.x * kSelRows;
 
-    if (kVec && n0 >= N) {                                   // pad rows of the last GEMM row tile: zero operand rows
+    if (kLayout != kLayoutGeneric && n0 >= N) {                                   // pad rows of the last GEMM row tile: zero operand rows
         // (a 32-row slab of a row tile is not contiguous in the operand image: zero it piecewise)
         for (int i = tid; i < kSelRows * kD / 2; i += kPrepThreads) {
             const int r = i / (kD / 2), d = 2 * (i % (kD / 2));
@@ -39,7 +39,9 @@ vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_p
         }
         return;
     }
-    if (kVec) {
+    if (kLayout == kLayoutRows) {
+        fill_tile_rows(tile, z, n0, N, warp, lane);
+    } else if (kLayout == kLayoutVec) {
         const int dsub = lane >> 3, hq = lane & 7;
         const int64_t b = n0 / HW, hw0 = n0 % HW;
         const float* src = z + (b * kD + dsub) * HW + hw0 + 4 * hq;

@@ -40,7 +40,8 @@ struct SelectParams {
     int64_t N, HW;
     int K;
     float beta;
-    int64_t* idx;              // (N)
+    void* idx;                 // (N) int64 / int32 / uint16 according to idx_bits
+    int idx_bits;
     float* zq;                 // (N, D) or null
     unsigned long long* hist;  // (K) or null
     double* loss_partial;      // (gridDim.x)
@@ -78,7 +79,7 @@ __device__ __forceinline__ uint32_t dist_key(float d) {
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
-template <bool kForward, bool kVec>
+template <bool kForward, int kLayout>
 __global__ void __launch_bounds__(kSelThreads, 4)
 vq_select_kernel(const SelectParams p) {
     __shared__ __align__(16) float tile[kSelRows * kD];       // 32 KiB, swizzled row-major (vq_common.cuh tile_off)
@@ -96,6 +97,7 @@ vq_select_kernel(const SelectParams p) {
     //     hw, 8 per thread) so that the candidate expansion below runs in their shadow
     const int dsub = lane >> 3, hq = lane & 7;
     float4 zreg[8];
+    constexpr bool kVec = (kLayout == kLayoutVec);
     if (kForward && kVec) {
         const int64_t b = n0 / p.HW, hw0 = n0 % p.HW;
         const float* src = p.z + (b * kD + dsub) * p.HW + hw0 + 4 * hq;
@@ -155,7 +157,9 @@ vq_select_kernel(const SelectParams p) {
     const int need_exact = (nq[0] > 1) | (nq[1] > 1) | (nq[2] > 1) | (nq[3] > 1);
     const bool want_tile = kForward ? true : (__syncthreads_or(need_exact) != 0);
     if (want_tile) {
-        if (kVec) {
+        if (kLayout == kLayoutRows) {
+            fill_tile_rows(tile, p.z, n0, p.N, warp, lane);
+        } else if (kVec) {
             if (!kForward) {
                 const int64_t b = n0 / p.HW, hw0 = n0 % p.HW;
                 const float* src = p.z + (b * kD + dsub) * p.HW + hw0 + 4 * hq;
@@ -245,7 +249,9 @@ vq_select_kernel(const SelectParams p) {
             if (bk == 0x7fffffff) bk = 0;                     // every distance NaN: torch.argmin -> 0 as well
             if (n < p.N) {
                 idx_s[r] = bk;
-                p.idx[n] = (int64_t)bk;
+                if (p.idx_bits == 64) reinterpret_cast<int64_t*>(p.idx)[n] = (int64_t)bk;
+                else if (p.idx_bits == 32) reinterpret_cast<int32_t*>(p.idx)[n] = bk;
+                else reinterpret_cast<uint16_t*>(p.idx)[n] = (uint16_t)bk;
                 if (p.stats != nullptr && !((resolved_mask >> rr) & 1u)) {
                     if (na > 1) atomicAdd(&st_s[0], 1u);
                     if (my_nq > 1) atomicAdd(&st_s[1], 1u);
