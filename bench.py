@@ -423,7 +423,8 @@ def main():
         "metric": "vq_latents_per_sec_fwd_bwd" if not tok else "vq_latents_per_sec_tokenize",
         "value": N * world / (ms_step / 1e3), "unit": "latents/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 (distance GEMM operands f16, f32 accumulate; exact f32 re-rank)",
+        "vs_baseline": None, "dtype": "f32",
+        "dtype_note": "results are the reference's fp32 results; the distance GEMM that proposes candidates runs f16 operands with f32 accumulation on tcgen05, the decision is an exact f32 re-rank",
         "data": "synthetic",
         "config": {"workload": args.workload + ": " + wl["desc"], "K": K, "D": D, "latents_per_gpu": N,
                    "distribution": args.distribution, "l2": "inputs (2 x 268 MB per GPU) larger than the 126 MB L2"

@@ -46,6 +46,7 @@ def main():
     ap.add_argument("--configs", default="cfg1,cfg2,cfg3,cfg4,cfg5")
     ap.add_argument("--dist", default="init,trained")
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--rows", action="store_true", help="also time the row-major nearest-code search")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     L = _native.lib()
@@ -113,6 +114,28 @@ def main():
             out["fwd_bwd_hbm_frac"] = N * 5136 / ((out["prep_ms"] + out["forward_ms"] + out["backward_ms"]) / 1e3) / 1e9 / peaks["hbm_gbs"]
             out["tokenize_hbm_frac"] = N * 1032 / (out["argmin_ms"] / 1e3) / 1e9 / peaks["hbm_gbs"]
             print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in out.items()}))
+
+    # row-major nearest-code search (vq_argmin_rows): the reference's gaussian_to_indices shape
+    # (B*L = 16*256 rows, gaussian_dim 96 zero-padded to 256, K = 1024) and a large one on the headline codebook size
+    if args.rows:
+        for label, N, K, Dn in (("gaussian_to_indices 16x256 rows, D=96, K=1024", 4096, 1024, 96),
+                                ("rows 262144 x 256, K=16384", 262144, 16384, 256)):
+            g = torch.Generator(device=dev).manual_seed(7)
+            table = torch.rand(K, Dn, device=dev, generator=g)
+            x = table[torch.randint(0, K, (N,), device=dev, generator=g)] + 0.1 * torch.randn(N, Dn, device=dev, generator=g)
+            tab = vq.CodeTable(table)
+            tab.nearest(x)
+            torch.cuda.synchronize()
+            _native.profile_enable(True)
+            t_all = timed(lambda: tab.nearest(x), args.reps, flush)[0]
+            gm = _native.profile_collect()
+            _native.profile_enable(False)
+            t_i32 = timed(lambda: tab.nearest(x, dtype=torch.int32), args.reps, flush)[0]
+            flops = 2.0 * N * K * 256
+            print(json.dumps({"config": "rows: " + label, "N": N, "K": K, "D": Dn, "nearest_ms": round(t_all, 4),
+                              "nearest_int32_ms": round(t_i32, 4), "gemm_kernel_ms": round(statistics.median(gm), 4),
+                              "gemm_frac_of_bf16_peak": round(flops / statistics.median(gm) / 1e9 / peaks["bf16_tflops"], 4),
+                              "Mrows_s": round(N / t_all / 1e3, 2), "stats": dict(zip(_native.VQ_STAT_NAMES, tab.last_stats.tolist()))}))
 
 
 if __name__ == "__main__":
