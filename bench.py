@@ -272,7 +272,7 @@ def main():
     g_loss = torch.ones((), device=dev)
 
     def step(zin, gin):
-        cb._derived_key = None                      # the optimizer changed the weight: rebuild derived state
+        cb.refresh_codebook()                       # the optimizer changed the weight: rebuild derived state
         if tok:
             return cb.encode_indices(zin), None
         cb.codebook.weight.grad = None

@@ -175,6 +175,21 @@ def test_module_contract(vq):
         d = (z.detach().permute(0, 2, 3, 1).reshape(-1, 256)[:, None, :] - cb.codebook.weight[None]).pow(2).sum(-1)
         assert torch.equal(idx3, d.argmin(1)) or (d.gather(1, idx3[:, None]).squeeze(1) <= d.min(1).values * (1 + 1e-5)).all()
 
+    # edits through weight.data bypass the version counter: while training the derived state is rebuilt every call,
+    # for a frozen / no_grad codebook refresh_codebook() does it
+    with torch.no_grad():
+        new_w = torch.randn(512, 256, device=dev)
+    cb.codebook.weight.data.copy_(new_w)
+    _, idx4, _ = cb(z.detach().requires_grad_(True))
+    d = (z.detach().permute(0, 2, 3, 1).reshape(-1, 256)[:, None, :] - new_w[None]).pow(2).sum(-1)
+    assert (d.gather(1, idx4[:, None]).squeeze(1) <= d.min(1).values * (1 + 1e-5)).all()
+    with torch.no_grad():
+        cb.codebook.weight.data.copy_(-new_w)
+        cb.refresh_codebook()
+        idx5 = cb.encode_indices(z.detach())
+        d = (z.detach().permute(0, 2, 3, 1).reshape(-1, 256)[:, None, :] + new_w[None]).pow(2).sum(-1)
+        assert (d.gather(1, idx5[:, None]).squeeze(1) <= d.min(1).values * (1 + 1e-5)).all()
+
     # frozen codebook (stage-2 models freeze the VQVAE, vqvae.py:103-104): grad only to z
     for p in cb.parameters():
         p.requires_grad_(False)
@@ -349,7 +364,7 @@ def test_full_size_properties(K, dist, vq, oracle):
     e = E[idx]
     # loss identity (1 + beta) * mean((e - z)^2)
     exp_loss = 1.25 * float(((e - zrows).double() ** 2).mean())
-    assert abs(float(loss) - exp_loss) <= 1e-5 * exp_loss
+    assert abs(float(loss.detach()) - exp_loss) <= 1e-5 * exp_loss
     # z_q value and straight-through gradient identities
     assert torch.equal(z_q.permute(0, 2, 3, 1).reshape(N, D), zrows + (e - zrows))
     exp_gz = gout + (2.0 / (N * D)) * (z - e.reshape(B, H, W, D).permute(0, 3, 1, 2))
@@ -434,3 +449,102 @@ def test_narrow_token_dtypes(vq, oracle):
         vq.CodeBook(40000, 256).to(dev).encode_indices(torch.zeros(1, 256, 1, 1, device=dev), dtype=torch.int16)
     with pytest.raises(ValueError):
         cb.encode_indices(zt, dtype=torch.float32)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Drop-in through a VQVAE-shaped caller (network/vqvae/vqvae.py:116-146: encoder -> quant_conv -> CodeBook ->
+# post_quant_conv -> decoder) and CUDA-graph capture of the hot path.
+class _EagerCodeBook(torch.nn.Module):
+    """Test-local restatement of codebook.py:47-111 in eager PyTorch (the reference cannot travel to the GPU box)."""
+
+    def __init__(self, K, D, beta=0.25):
+        super().__init__()
+        self.beta = beta
+        self.codebook = torch.nn.Embedding(K, D)
+
+    def forward(self, z):
+        zp = z.permute(0, 2, 3, 1).contiguous()
+        zf = zp.view(-1, zp.shape[-1])
+        w = self.codebook.weight
+        d = torch.sum(zf ** 2, dim=1, keepdim=True) + torch.sum(w ** 2, dim=1) - 2 * torch.matmul(zf, w.t())
+        idx = torch.argmin(d, dim=1)
+        z_q = self.codebook(idx).view(zp.shape)
+        loss = torch.mean((z_q.detach() - zp) ** 2 + self.beta * torch.mean((z_q - zp.detach()) ** 2))
+        z_q = zp + (z_q - zp).detach()
+        return z_q.permute(0, 3, 1, 2), idx, loss
+
+
+class _TinyVQVAE(torch.nn.Module):
+    def __init__(self, codebook):
+        super().__init__()
+        self.encoder = torch.nn.Sequential(torch.nn.Conv2d(3, 64, 4, 2, 1), torch.nn.SiLU(), torch.nn.Conv2d(64, 256, 4, 2, 1))
+        self.quant_conv = torch.nn.Conv2d(256, 256, 1)
+        self.codebook = codebook
+        self.post_quant_conv = torch.nn.Conv2d(256, 256, 1)
+        self.decoder = torch.nn.Sequential(torch.nn.ConvTranspose2d(256, 64, 4, 2, 1), torch.nn.SiLU(),
+                                           torch.nn.ConvTranspose2d(64, 3, 4, 2, 1))
+
+    def forward(self, x):                                    # vqvae.py:116-137
+        quant_x = self.quant_conv(self.encoder(x))
+        z_q, idx, q_loss = self.codebook(quant_x)
+        return self.decoder(self.post_quant_conv(z_q)), idx, q_loss
+
+
+def test_drop_in_through_vqvae_shaped_caller(vq):
+    import copy
+    dev = torch.device("cuda:0")
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(3)
+        K = 512
+        ref = _TinyVQVAE(_EagerCodeBook(K, 256)).to(dev)
+        with torch.no_grad():
+            ref.codebook.codebook.weight.normal_(0, 0.5)
+        ours = copy.deepcopy(ref)
+        ours.codebook = vq.CodeBook(K, 256).to(dev)
+        ours.codebook.load_state_dict(ref.codebook.state_dict())          # same key: codebook.weight
+        x = torch.randn(4, 3, 64, 64, device=dev)                       # -> 16x16 latents
+        outs = []
+        for m in (ref, ours):
+            dec, idx, q_loss = m(x)
+            (torch.nn.functional.l1_loss(dec, x) + q_loss).backward()
+            outs.append((dec.detach(), idx, q_loss.detach(), {n: p.grad.detach().clone() for n, p in m.named_parameters()}))
+        (dec_r, idx_r, ql_r, g_r), (dec_o, idx_o, ql_o, g_o) = outs
+        assert torch.equal(idx_r, idx_o), int((idx_r != idx_o).sum())
+        assert rel_err(dec_o.cpu().numpy(), dec_r.cpu().numpy()) <= 1e-5
+        assert abs(float(ql_o) - float(ql_r)) <= 1e-5 * abs(float(ql_r))
+        assert set(g_r) == set(g_o)
+        for n in g_r:
+            assert rel_err(g_o[n].cpu().numpy(), g_r[n].cpu().numpy()) <= 2e-5, n
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def test_cuda_graph_capture_and_replay(vq, oracle):
+    """The C-ABI never allocates or synchronises, so a whole call sequence is capturable; replays follow new input
+    contents written into the static buffers."""
+    dev = torch.device("cuda:0")
+    spec = CASES["cfg2s_trained"]
+    z_np, E_np, _ = make_inputs(spec)
+    cb = vq.CodeBook(spec["K"], spec["D"]).to(dev)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(torch.from_numpy(E_np))
+        z_static = torch.zeros(z_np.shape, device=dev)
+        cb.encode_indices(z_static)                                     # warm-up: one-time attribute setup, workspace
+        cb(z_static)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            idx_static = cb.encode_indices(z_static)
+            zq_static, idx2_static, loss_static = cb(z_static)
+        for shift in (0.0, 0.25):
+            z_now = (z_np + np.float32(shift)).astype(np.float32)
+            z_static.copy_(torch.from_numpy(z_now))
+            graph.replay()
+            torch.cuda.synchronize()
+            ref = oracle.forward(z_now, E_np)
+            assert np.array_equal(idx_static.cpu().numpy(), ref["idx"])
+            assert np.array_equal(idx2_static.cpu().numpy(), ref["idx"])
+            assert np.array_equal(zq_static.permute(0, 2, 3, 1).reshape(-1, spec["D"]).cpu().numpy(), ref["zq_nhwc"])
+            assert abs(float(loss_static) - float(ref["loss"])) <= 1e-6 * float(ref["loss"])

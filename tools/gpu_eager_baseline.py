@@ -78,7 +78,7 @@ def main():
             return idx
 
         def step_ours():
-            cb._derived_key = None
+            cb.refresh_codebook()
             if tok:
                 return cb.encode_indices(z)
             zz = z.detach().requires_grad_(True)

@@ -53,13 +53,13 @@ class _VQFunction(torch.autograd.Function):
     """forward -> vq_forward, backward -> vq_backward (include/vq_b200.h)."""
 
     @staticmethod
-    def forward(ctx, z, weight, module):
+    def forward(ctx, z, weight, module, refresh):
         B, D, H, W = z.shape
         K = weight.shape[0]
         dev = z.device
         zc = z.contiguous()                                  # NCHW; the kernels read it in place
         with torch.cuda.device(dev):
-            E_h, e2, cb = module._derived(weight)
+            E_h, e2, cb = module._derived(weight, force=refresh)
             zq = torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
             idx = torch.empty((B * H * W,), dtype=torch.int64, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
@@ -90,7 +90,7 @@ class _VQFunction(torch.autograd.Function):
         dev = zc.device
         need_z, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if not (need_z or need_w):
-            return None, None, None
+            return None, None, None, None
         strides = None
         if g_zq is not None:
             if g_zq.dtype != torch.float32:
@@ -114,7 +114,7 @@ class _VQFunction(torch.autograd.Function):
             module._launches_bwd = int(_native.lib().vq_last_launch_count())
         if grad_E is not None and module.grad_hook is not None:
             grad_E = module.grad_hook(grad_E)
-        return grad_z, grad_E, None
+        return grad_z, grad_E, None, None
 
 
 class CodeBook(nn.Module):
@@ -151,11 +151,17 @@ class CodeBook(nn.Module):
         self.last_stats = None
 
     # ------------------------------------------------------------------ derived codebook state
-    def _derived(self, weight: torch.Tensor):
-        """fp16 operand copy + |e|^2 + scalars, refreshed whenever the weight storage or version changed
-        (optimizer.step(), load_state_dict(), .to(device) all bump one of them)."""
+    def _derived(self, weight: torch.Tensor, force: bool = False):
+        """fp16 operand image + |e|^2 + scalars of the current weight.
+
+        While the codebook is being trained (grad mode on, weight requires grad) they are rebuilt on every call -- the
+        optimizer changes the weight every step anyway, and two small kernels (15 us at K = 16384) are cheaper than a
+        stale operand copy.  For a frozen codebook / under ``no_grad`` (the stage-2 tokenisers) they are cached and
+        refreshed whenever the weight's storage, version counter, device or shape changed (``optimizer.step()``,
+        ``load_state_dict()``, ``.to(device)`` all change one of them).  In-place edits through ``weight.data`` bypass
+        the version counter: call :meth:`refresh_codebook` after those."""
         key = (weight.data_ptr(), weight._version, weight.device, tuple(weight.shape))
-        if key != self._derived_key:
+        if force or key != self._derived_key:
             K, D = weight.shape
             dev = weight.device
             k_pad = _native.padded_codes(K)
@@ -168,6 +174,10 @@ class CodeBook(nn.Module):
             _native.check(rc, "vq_prepare_codebook")
             self._derived_key = key
         return self._E_h, self._e2, self._cb
+
+    def refresh_codebook(self) -> None:
+        """Drop the cached derived state (needed only after in-place edits through ``weight.data``)."""
+        self._derived_key = None
 
     def _check_input(self, z: torch.Tensor):
         if not isinstance(z, torch.Tensor) or z.dim() != 4:
@@ -194,7 +204,9 @@ class CodeBook(nn.Module):
         self._check_input(z)
         if indices_only:
             return None, self.encode_indices(z), None
-        return _VQFunction.apply(z, self.codebook.weight, self)
+        weight = self.codebook.weight
+        # (grad mode is off inside autograd.Function.forward, so "is the codebook being trained" is decided here)
+        return _VQFunction.apply(z, weight, self, weight.requires_grad and torch.is_grad_enabled())
 
     @torch.no_grad()
     def encode_indices(self, z: torch.Tensor, dtype=torch.int64) -> torch.Tensor:
