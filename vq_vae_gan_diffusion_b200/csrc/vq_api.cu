@@ -8,6 +8,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -48,6 +49,40 @@ int fail(int code, const char* fmt, ...) {
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
+// The production GEMM runs as clusters of two CTAs sharing the codebook stream (vq_argmin_sm100.cuh, kShare);
+// VQ_GEMM_SHARE=0 selects independent CTAs (A/B runs).
+bool gemm_share() {
+    static const bool v = [] {
+        const char* e = getenv("VQ_GEMM_SHARE");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    return v;
+}
+
+// launch of one GEMM variant: as clusters of two CTAs (one cluster per pair of row tiles, at most one per two SMs) when
+// `share`, else one CTA per row tile up to one per SM
+template <bool kDebug, bool kTimeline>
+cudaError_t launch_gemm(const vq::GemmParams& gp, bool share, int sms, cudaStream_t st) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(vq::kGemmThreads);
+    cfg.dynamicSmemBytes = vq::kGemmSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    if (share) {
+        const int pairs = (gp.row_tiles + 1) / 2;
+        cfg.gridDim = dim3(2 * (pairs < sms / 2 ? pairs : sms / 2));
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, vq::vq_argmin_gemm_kernel<kDebug, kTimeline, true>, gp);
+    }
+    cfg.gridDim = dim3(gp.row_tiles < sms ? gp.row_tiles : sms);
+    return cudaLaunchKernelEx(&cfg, vq::vq_argmin_gemm_kernel<kDebug, kTimeline, false>, gp);
+}
+
 // ---- optional timing of the distance-GEMM kernel (bench.py's roofline): a ring of event pairs recorded on the
 // caller's stream around that one launch; read back after the caller has synchronised.
 constexpr int kProfCap = 512;
@@ -83,12 +118,13 @@ int device_info(DevInfo** out) {
     if (d.cc != 100)
         return fail(VQ_E_DEVICE, "vq_b200 kernels are built for sm_100a only; current device is sm_%d (no fallback)", d.cc);
     if (!d.attrs_set) {
-        VQ_CUDA(cudaFuncSetAttribute(vq::vq_argmin_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)vq::kGemmSmemBytes));
-        VQ_CUDA(cudaFuncSetAttribute(vq::vq_argmin_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)vq::kGemmSmemBytes));
-        VQ_CUDA(cudaFuncSetAttribute(vq::vq_argmin_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)vq::kGemmSmemBytes));
+        const void* gemm_variants[] = {(const void*)vq::vq_argmin_gemm_kernel<false, false, false>,
+                                       (const void*)vq::vq_argmin_gemm_kernel<false, false, true>,
+                                       (const void*)vq::vq_argmin_gemm_kernel<true, false, false>,
+                                       (const void*)vq::vq_argmin_gemm_kernel<false, true, false>,
+                                       (const void*)vq::vq_argmin_gemm_kernel<false, true, true>};
+        for (const void* fn : gemm_variants)
+            VQ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vq::kGemmSmemBytes));
         d.attrs_set = true;
     }
     *out = &d;
@@ -115,7 +151,7 @@ struct Workspace {
 
 Workspace carve(void* base, int64_t N) {
     Workspace w;
-    const int64_t n_pad = round_up(N > 0 ? N : 1, vq::kRowTile);
+    const int64_t n_pad = round_up(N > 0 ? N : 1, 2 * vq::kRowTile);      // whole PAIRS of GEMM row tiles
     size_t off = 0;
     auto take = [&](size_t bytes) {
         void* p = base ? static_cast<char*>(base) + off : nullptr;
@@ -162,7 +198,7 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, const void* E_h, 
     DevInfo* dev;
     int rc = device_info(&dev);
     if (rc != VQ_OK) return rc;
-    const int64_t n_pad = round_up(N, vq::kRowTile);
+    const int64_t n_pad = round_up(N, 2 * vq::kRowTile);
     const int k_pad = vq_padded_codes(K);
 
     const unsigned pgrid = (unsigned)(n_pad / vq::kSelRows);
@@ -187,7 +223,7 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, const void* E_h, 
     gp.z_inv_scale = w.z_inv_scale;
     gp.N = N;
     gp.k_tiles = k_pad / vq::kCodeTile;
-    gp.row_tiles = (int)(n_pad / vq::kRowTile);
+    gp.row_tiles = (int)(round_up(N, vq::kRowTile) / vq::kRowTile);
     gp.out_cnt = w.out_cnt;
     gp.out_q = w.out_q;
     gp.fb_rows = w.fb_rows;
@@ -195,7 +231,6 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, const void* E_h, 
     gp.dbg_scores = dbg_scores;
     gp.timeline = g_timeline;
     gp.timeline_tiles = g_timeline_tiles;
-    const int grid = gp.row_tiles < dev->sms ? gp.row_tiles : dev->sms;
     VQ_CUDA(cudaMemsetAsync(w.blocks_done, 0, w.control_bytes, st));     // loss arrival counter, worklist length, group arrivals
     const bool prof = g_prof.on && g_prof.n < kProfCap;
     if (prof) {
@@ -206,12 +241,11 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, const void* E_h, 
         }
         VQ_CUDA(cudaEventRecord(g_prof.ev[g_prof.n][0], st));
     }
-    if (g_timeline != nullptr)
-        vq::vq_argmin_gemm_kernel<false, true><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(gp);
-    else if (dbg_scores)
-        vq::vq_argmin_gemm_kernel<true><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(gp);
-    else
-        vq::vq_argmin_gemm_kernel<false><<<grid, vq::kGemmThreads, vq::kGemmSmemBytes, st>>>(gp);
+    // sharing needs at least one pair of row tiles; the debug-score variant stays on independent CTAs
+    const bool share = gemm_share() && gp.row_tiles >= 2;
+    if (g_timeline != nullptr) VQ_CUDA((launch_gemm<false, true>(gp, share, dev->sms, st)));
+    else if (dbg_scores)       VQ_CUDA((launch_gemm<true, false>(gp, false, dev->sms, st)));
+    else                       VQ_CUDA((launch_gemm<false, false>(gp, share, dev->sms, st)));
     VQ_LAUNCH_CHECK("vq_argmin_gemm_kernel");
     if (prof) {
         VQ_CUDA(cudaEventRecord(g_prof.ev[g_prof.n][1], st));

@@ -7,14 +7,22 @@
 // vq_select_kernel (vq_select.cuh) recomputes the distances of the surviving quads exactly in fp32 and takes the
 // first minimum.
 //
-// CTA = 10 warps, persistent over row tiles (128 latents each):
-//   warp 0      TMA producer (cp.async.bulk): A = z tile (4 chunks of [128 x 64] fp16) once per row tile, B = codebook
+// CTA = 11 warps, persistent over row tiles (128 latents each).  In the production configuration (kShare) the CTAs run as
+// clusters of two that SHARE the codebook stream: the two CTAs work on different row tiles but the same code tiles, each
+// fetches half of every 32 KiB codebook stage and multicasts it into both rings (cp.async.bulk .multicast::cluster), which
+// halves the L2 -> SMEM operand traffic per SM -- the kernel runs against the 1 kW power cap, so bytes moved are clock
+// (measured: same cycles per tile, 3 % less time).  MMA issue, TMEM hand-off and epilogue stay local to the CTA; only the
+// stage-release barrier collects a commit from both CTAs.  Two alternatives were built and measured at K = 16384 and
+// dropped: cta_group::2 pairs (one M = 256 MMA over both SMs, each CTA holding half of B: two cross-CTA hops land in the
+// TMEM buffer cycle, 1.70 ms vs 1.46 ms) and 128-code half tiles with four accumulator quarters (N = 128 MMAs re-read the
+// A operand twice per tile and saturate shared-memory bandwidth, 1.59 ms).
+//   warp 0      bulk-copy producer (cp.async.bulk): A = z tile (4 chunks of [128 x 64] fp16) once per row tile, B = codebook
 //               tile ([256 codes x 64] fp16 = 32 KiB per stage) through a 4-stage ring, and the |e|^2 slice of every
 //               code tile (1 KiB) into a double buffer.  Both operands are stored in global memory as ready-made
 //               SWIZZLE_128B shared-memory images (vq_prep.cuh), so every stage is ONE contiguous bulk copy instead of
 //               256 strided 128-byte rows of a tensor-map box.
-//   warp 1      TMEM allocator + MMA issuer: per code tile 16 x tcgen05.mma (M128 N256 K16) into one of two
-//               256-column fp32 accumulators (the epilogue of tile j overlaps the MMAs of tile j+1).
+//   warps 1,10  MMA issuers (warp 1 also allocates TMEM), alternating code tiles: per tile 16 x tcgen05.mma (M128 N256 K16)
+//               into one of two 256-column fp32 accumulators (the epilogue of tile j overlaps the MMAs of tile j+1).
 //   warps 2..5  epilogue group 0: columns [0, 128) of every accumulator tile
 //   warps 6..9  epilogue group 1: columns [128, 256)
 //               thread <-> TMEM lane <-> latent row; tcgen05.ld 32 columns at a time (prefetched one chunk ahead,
@@ -99,7 +107,9 @@ __device__ __forceinline__ void epi_barrier() {               // the 256 epilogu
     asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 
-template <bool kDebugScores, bool kTimeline = false>
+// kShare: launched as clusters of two CTAs that share the codebook stream (see the header); a work unit is then a PAIR of
+// row tiles (row tile 2u + rank for the CTA of that rank; z_h is padded to whole pairs), otherwise one row tile.
+template <bool kDebugScores, bool kTimeline = false, bool kShare = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 vq_argmin_gemm_kernel(const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -107,10 +117,15 @@ vq_argmin_gemm_kernel(const GemmParams p) {
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = kShare ? cluster_ctarank() : 0u;
+    const int unit0 = kShare ? (int)cluster_id_x() : (int)blockIdx.x;
+    const int unit_step = kShare ? (int)cluster_count_x() : (int)gridDim.x;
+    const int n_units = kShare ? (p.row_tiles + 1) / 2 : p.row_tiles;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < kNumDChunks; i++) { mbar_init(&s.a_full[i], 1); mbar_init(&s.a_empty[i], 1); }
-        for (int i = 0; i < kStagesB; i++) { mbar_init(&s.b_full[0][i], 1); mbar_init(&s.b_full[1][i], 1); mbar_init(&s.b_empty[i], 1); }
+        // (a shared stage is refilled when BOTH CTAs' MMAs on it have committed)
+        for (int i = 0; i < kStagesB; i++) { mbar_init(&s.b_full[0][i], 1); mbar_init(&s.b_full[1][i], 1); mbar_init(&s.b_empty[i], kShare ? 2 : 1); }
         for (int i = 0; i < 2; i++) {
             mbar_init(&s.t_full[i], 1);
             mbar_init(&s.t_empty[i], 4 * kEpiGroups);
@@ -125,6 +140,7 @@ vq_argmin_gemm_kernel(const GemmParams p) {
     }
     tc_fence_before();
     __syncthreads();
+    if (kShare) cluster_sync_all();                          // the peer's barriers exist before anything is multicast to it
     tc_fence_after();
     const uint32_t tmem_base = s.tmem_base;
 
@@ -136,7 +152,8 @@ vq_argmin_gemm_kernel(const GemmParams p) {
             const uint64_t pol_stream = policy_evict_first(); // z tiles are read exactly once
             uint32_t stage = 0, b_phase = 0, a_phase = 0, buf = 0, e_phase = 0;
             long long it = 0;                                   // global code-tile counter of this CTA
-            for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x) {
+            for (int u = unit0; u < n_units; u += unit_step) {
+                const int64_t rt = kShare ? 2 * (int64_t)u + rank : u;
                 for (int kt = 0; kt < p.k_tiles; kt++, it++) {
                     uint64_t* const bfull = s.b_full[it & 1];
                     for (int dc = 0; dc < kNumDChunks; dc++) {
@@ -144,16 +161,27 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                             mbar_wait(&s.a_empty[dc], a_phase ^ 1);
                             if (elect_one()) {
                                 mbar_expect_tx(&s.a_full[dc], kBytesAChunk);
-                                bulk_load_1d_hint(s.a[dc], p.z_h + ((int64_t)rt * kNumDChunks + dc) * (kRowTile * kDChunk),
+                                bulk_load_1d_hint(s.a[dc], p.z_h + (rt * kNumDChunks + dc) * (kRowTile * kDChunk),
                                                   kBytesAChunk, &s.a_full[dc], pol_stream);
                             }
                             __syncwarp();
                         }
-                        mbar_wait(&s.b_empty[stage], b_phase ^ 1);
-                        if (elect_one()) {
-                            mbar_expect_tx(&bfull[stage], kBytesBStage);
-                            bulk_load_1d_hint(s.b[stage], p.e_h + ((int64_t)kt * kNumDChunks + dc) * (kCodeTile * kDChunk),
-                                              kBytesBStage, &bfull[stage], pol_keep);
+                        const __half* src = p.e_h + ((int64_t)kt * kNumDChunks + dc) * (kCodeTile * kDChunk);
+                        if (kShare) {
+                            // this CTA fetches the codes [128 rank, 128 rank + 128) of the stage for both CTAs; each CTA arms
+                            // its own barrier for the whole stage
+                            mbar_wait_cluster(&s.b_empty[stage], b_phase ^ 1);
+                            if (elect_one()) {
+                                mbar_expect_tx(&bfull[stage], kBytesBStage);
+                                bulk_load_1d_multicast(s.b[stage] + rank * (kBytesBStage / 2), src + rank * (kCodeTile / 2 * kDChunk),
+                                                       kBytesBStage / 2, &bfull[stage], (uint16_t)3, pol_keep);
+                            }
+                        } else {
+                            mbar_wait(&s.b_empty[stage], b_phase ^ 1);
+                            if (elect_one()) {
+                                mbar_expect_tx(&bfull[stage], kBytesBStage);
+                                bulk_load_1d_hint(s.b[stage], src, kBytesBStage, &bfull[stage], pol_keep);
+                            }
                         }
                         __syncwarp();
                         if (++stage == kStagesB) { stage = 0; b_phase ^= 1; }
@@ -188,7 +216,7 @@ vq_argmin_gemm_kernel(const GemmParams p) {
             const uint32_t d_tmem = tmem_base + buf * kCodeTile;
             long long it = 0;                                   // global code-tile counter of this CTA
             int rti = 0, tl_seq = 0;
-            for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x, rti++) {
+            for (int u = unit0; u < n_units; u += unit_step, rti++) {
                 // both warps look at every row tile's z chunks (even when a short codebook gives a warp no code tile in
                 // this row tile): an mbarrier parity wait must never fall a whole phase behind
 #pragma unroll
@@ -210,7 +238,8 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                         // the ring holds exactly one code tile: stage == dc, and its parity flips every tile
                         long long tb0 = 0;
                         if (kTimeline) tb0 = clock64();
-                        mbar_wait(&s.b_full[buf][dc], use & 1);
+                        if (kShare) mbar_wait_cluster(&s.b_full[buf][dc], use & 1);    // half of it was written by the peer's copy
+                        else mbar_wait(&s.b_full[buf][dc], use & 1);
                         tc_fence_after();
                         if (kTimeline) tl_bwait += clock64() - tb0;
                         const uint64_t adesc = umma_desc_sw128(smem_u32(s.a[dc]));
@@ -221,7 +250,8 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                                 // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
                                 umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dc | k) != 0);
                             }
-                            umma_commit(&s.b_empty[dc]);
+                            if (kShare) umma_commit_multicast(&s.b_empty[dc], (uint16_t)3);
+                            else umma_commit(&s.b_empty[dc]);
                             if (kt == p.k_tiles - 1) umma_commit(&s.a_empty[dc]);
                             if (dc == kNumDChunks - 1) umma_commit(&s.t_full[buf]);
                         }
@@ -255,8 +285,8 @@ vq_argmin_gemm_kernel(const GemmParams p) {
         const float e_inv = __ldg(p.cb + 2);
         uint32_t buf = 0, phase = 0;
         int rti = 0, tl_seq = 0;
-        for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x, rti++) {
-            const int64_t row = (int64_t)rt * kRowTile + trow;
+        for (int u = unit0; u < n_units; u += unit_step, rti++) {
+            const int64_t row = (kShare ? 2 * (int64_t)u + rank : (int64_t)u) * kRowTile + trow;
             const bool row_ok = row < p.N;
             const float margin = candidate_margin(row_ok ? __ldg(p.z2 + row) : 0.0f, e2max);
             // score = e2 + cscale * acc,  acc = (z * 2^a) . (e * 2^b)  ->  cscale = -2 * 2^-a * 2^-b  (exact)
@@ -401,6 +431,7 @@ vq_argmin_gemm_kernel(const GemmParams p) {
 
     tc_fence_before();
     __syncthreads();
+    if (kShare) cluster_sync_all();      // nobody leaves while the peer may still multicast into this ring or signal its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
