@@ -10,7 +10,7 @@
  *
  *   codebook.py:62-66   NCHW -> (N, D) rows, N = B*H*W in (b, h, w) order
  *   codebook.py:70-79   d[n,k] = fl( fl(|z_n|^2 + |e_k|^2) - fl(2 * fl(z_n . e_k)) )     (fp32)
- *   codebook.py:82      idx[n] = first index of the row minimum (torch.argmin)
+ *   codebook.py:82      idx[n] = first index of the row minimum (torch.argmin; a NaN distance counts as the minimum)
  *   codebook.py:85      e = E[idx]
  *   codebook.py:96-103  loss = mean((e - z)^2 + beta * mean((e - z)^2))
  *   codebook.py:106     z_q = fl(z + fl(e - z))            (straight-through value)
@@ -118,7 +118,11 @@ VQO_API int vq_oracle_forward(const float* z_nchw, int64_t B, int64_t HW, int D,
         for (int k = 0; k < K; k++) {
             const float dot = vqo_dot(zr, HW, E + (int64_t)k * D, 1, D);
             const float dist = vqo_dist(z2, e2[k], dot);
-            if (k == 0 || dist < best) { best = dist; best_k = k; n_best = 1; }
+            /* torch.argmin semantics (codebook.py:82): NaN counts as smaller than every number, the FIRST minimal
+             * element wins; n_best counts the codes attaining the minimum (NaN == NaN for this purpose) */
+            if (k == 0) { best = dist; best_k = k; n_best = 1; }
+            else if (isnan(best)) { if (isnan(dist)) n_best++; }
+            else if (isnan(dist) || dist < best) { best = dist; best_k = k; n_best = 1; }
             else if (dist == best) n_best++;
         }
         idx_local[n] = best_k;

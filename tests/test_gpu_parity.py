@@ -548,3 +548,38 @@ def test_cuda_graph_capture_and_replay(vq, oracle):
             assert np.array_equal(idx2_static.cpu().numpy(), ref["idx"])
             assert np.array_equal(zq_static.permute(0, 2, 3, 1).reshape(-1, spec["D"]).cpu().numpy(), ref["zq_nhwc"])
             assert abs(float(loss_static) - float(ref["loss"])) <= 1e-6 * float(ref["loss"])
+
+
+def test_nan_and_inf_rows_follow_the_oracle(vq, oracle):
+    """Rows containing NaN / Inf get NaN / inf distances; torch.argmin (and the oracle) return the first NaN.  Such rows take
+    the exact fallback and must not disturb their neighbours."""
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(21)
+    K, B, H, W = 700, 2, 8, 16
+    E = rng.standard_normal((K, 256)).astype(np.float32)
+    z = rng.standard_normal((B, 256, H, W)).astype(np.float32)
+    z[0, 5, 1, 3] = np.nan
+    z[1, 200, 7, 15] = np.inf
+    z[1, 17, 0, 0] = -np.inf
+    cb = vq.CodeBook(K, 256).to(dev)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(torch.from_numpy(E))
+        z_q, idx, loss = cb(torch.from_numpy(z).to(dev))
+        idx_tok = cb.encode_indices(torch.from_numpy(z).to(dev))
+    ref = oracle.forward(z, E)
+    bad_rows = [0 * H * W + 1 * W + 3, 1 * H * W + 7 * W + 15, 1 * H * W + 0]
+    assert ref["idx"][bad_rows[0]] == 0                              # all distances NaN: the first code
+    assert np.array_equal(idx.cpu().numpy(), ref["idx"])
+    assert np.array_equal(idx_tok.cpu().numpy(), ref["idx"])
+    assert cb.stats_dict()["fallback_rows"] == 3
+    assert not np.isfinite(float(loss))
+    assert ref["idx"][bad_rows[1]] == int(np.argmax(E[:, 200] > 0)) and ref["idx"][bad_rows[2]] == int(np.argmax(E[:, 17] < 0))
+    # a NaN inside the codebook makes that code every row's argmin (torch.argmin: the first NaN wins)
+    E2 = E.copy()
+    E2[433, 7] = np.nan
+    zc = np.nan_to_num(z, nan=0.0, posinf=1.0, neginf=-1.0)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(torch.from_numpy(E2))
+        idx2 = cb.encode_indices(torch.from_numpy(zc).to(dev))
+    assert (idx2 == 433).all()
+    assert np.array_equal(idx2.cpu().numpy(), oracle.forward(zc, E2, want_zq=False)["idx"])

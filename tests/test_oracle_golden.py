@@ -193,3 +193,35 @@ def test_zero_padding_changes_no_distance(name, oracle):
     b = oracle.forward(zp, tp, want_zq=False)
     assert np.array_equal(a["idx"], b["idx"]) and a["tie_rows"] == b["tie_rows"]
     assert np.array_equal(a["dist_min"], b["dist_min"])
+
+
+def test_nan_and_inf_follow_torch_argmin(oracle):
+    """torch.argmin treats a NaN distance as the minimum and returns the first one (codebook.py:82); a row with +-inf
+    gets inf / NaN distances depending on the sign of the code's element there.  The oracle must reproduce exactly
+    that -- checked against the torch-CPU port of the reference on the same inputs (no BLAS ambiguity: every affected
+    distance is inf or NaN)."""
+    import torch
+    from oracle.vq_oracle import torch_cpu_step
+    rng = np.random.default_rng(21)
+    K, B, H, W = 70, 2, 4, 8
+    E = rng.standard_normal((K, 256)).astype(np.float32)
+    z = rng.standard_normal((B, 256, H, W)).astype(np.float32)
+    z[0, 5, 1, 3] = np.nan
+    z[1, 200, 3, 7] = np.inf
+    z[1, 17, 0, 0] = -np.inf
+    ref = oracle.forward(z, E, want_zq=False)
+    idx_t = torch_cpu_step(torch.from_numpy(z), torch.from_numpy(E), None, 0.25, indices_only=True)[1].numpy()
+    bad = [0 * H * W + 1 * W + 3, 1 * H * W + 3 * W + 7, 1 * H * W + 0]
+    for r in bad:
+        assert ref["idx"][r] == idx_t[r], (r, ref["idx"][r], idx_t[r])
+    assert ref["idx"][bad[0]] == 0                                   # all-NaN row: first code
+    assert ref["idx"][bad[1]] == int(np.argmax(E[:, 200] > 0))       # +inf: first code whose element there is positive
+    assert ref["idx"][bad[2]] == int(np.argmax(E[:, 17] < 0))        # -inf: first code whose element there is negative
+    ok = np.ones(B * H * W, bool)
+    ok[bad] = False
+    cls = classify_index_mismatches(z, E, np.where(ok, ref["idx"], 0), np.where(ok, idx_t, 0), pair_dist=oracle.pair_dist)
+    assert cls["real"] == 0
+    # a NaN inside the codebook makes that code every row's argmin
+    E2 = E.copy()
+    E2[33, 7] = np.nan
+    assert (oracle.forward(z, E2, want_zq=False)["idx"][ok] == 33).all()

@@ -288,7 +288,11 @@ vq_argmin_gemm_kernel(const GemmParams p) {
         for (int u = unit0; u < n_units; u += unit_step, rti++) {
             const int64_t row = (kShare ? 2 * (int64_t)u + rank : (int64_t)u) * kRowTile + trow;
             const bool row_ok = row < p.N;
-            const float margin = candidate_margin(row_ok ? __ldg(p.z2 + row) : 0.0f, e2max);
+            const float z2row = row_ok ? __ldg(p.z2 + row) : 0.0f;
+            // Inf / NaN in the row or anywhere in the codebook: distances become NaN / inf, where torch.argmin's rule (first
+            // NaN wins) cannot be decided from approximate scores -> the row takes the exact full scan
+            const bool nonfinite = !(fabsf(z2row) < INFINITY) || !(fabsf(e2max) < INFINITY);
+            const float margin = candidate_margin(z2row, e2max);
             // score = e2 + cscale * acc,  acc = (z * 2^a) . (e * 2^b)  ->  cscale = -2 * 2^-a * 2^-b  (exact)
             const float cscale = -2.0f * (row_ok ? __ldg(p.z_inv_scale + row) : 1.0f) * e_inv;
             float m_run = INFINITY, thr = INFINITY, lost_min = INFINITY;
@@ -404,7 +408,7 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                 const float thr_fin = m_fin + margin;
                 int n_out = 0, n_codes = 0;
                 // nothing recorded at all (NaN row: group 0 reports) or a possible survivor was overwritten
-                bool bad = (cnt_all == 0 && grp == 0) || (lost_min <= thr_fin);
+                bool bad = (cnt_all == 0 && grp == 0) || (lost_min <= thr_fin) || nonfinite;
                 const int live = min(cnt, kRingCap);
                 uint2* dst = reinterpret_cast<uint2*>(p.out_q) + row * kOutCap + grp * kOutPerGroup;
                 for (int i = 0; i < live && !bad; i++) {

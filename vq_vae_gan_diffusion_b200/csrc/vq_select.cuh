@@ -72,9 +72,11 @@ __device__ __forceinline__ float exact_partial_tile(const float* tile, int r, co
     return p;
 }
 
-// total order on non-NaN floats as unsigned keys (ascending); NaN -> 0xffffffff ("never the minimum")
+// Distances as unsigned keys whose integer order is torch.argmin's order (codebook.py:82): NaN -> 0, smaller than every
+// number (torch treats a NaN as the minimum and returns the first one); -inf < ... < -0.0 == +0.0 < ... < +inf otherwise.
+// Real keys lie in [0x007fffff, 0xff800000]; 0xffffffff is free as the "no candidate" sentinel.
 __device__ __forceinline__ uint32_t dist_key(float d) {
-    if (!(d == d)) return 0xffffffffu;
+    if (!(d == d)) return 0u;
     const uint32_t b = __float_as_uint(d + 0.0f);                          // -0.0 -> +0.0
     return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
@@ -230,7 +232,6 @@ vq_select_kernel(const SelectParams p) {
                 const bool mine = lead && (rr == r2);
                 if (__ballot_sync(0xffffffffu, mine) == 0u) continue;          // warp-uniform
                 const uint32_t um = __reduce_min_sync(0xffffffffu, mine ? u : 0xffffffffu);
-                if (um == 0xffffffffu) continue;                               // only NaN distances in this pass
                 const bool at = mine && (u == um);
                 const int km = (int)__reduce_min_sync(0xffffffffu, at ? (uint32_t)k : 0x7fffffffu);
                 const int c = __popc(__ballot_sync(0xffffffffu, at));
@@ -246,7 +247,7 @@ vq_select_kernel(const SelectParams p) {
             int bk = (rr == 0) ? best_k[0] : (rr == 1) ? best_k[1] : (rr == 2) ? best_k[2] : best_k[3];
             const int na = (rr == 0) ? n_at_min[0] : (rr == 1) ? n_at_min[1] : (rr == 2) ? n_at_min[2] : n_at_min[3];
             const int my_nq = (rr == 0) ? nq[0] : (rr == 1) ? nq[1] : (rr == 2) ? nq[2] : nq[3];
-            if (bk == 0x7fffffff) bk = 0;                     // every distance NaN: torch.argmin -> 0 as well
+            if (bk == 0x7fffffff) bk = 0;                     // no candidate at all (cannot happen for a row the GEMM listed)
             if (n < p.N) {
                 idx_s[r] = bk;
                 if (p.idx_bits == 64) reinterpret_cast<int64_t*>(p.idx)[n] = (int64_t)bk;
@@ -350,8 +351,9 @@ struct FallbackParams {
     unsigned long long* stats;
 };
 
-// merge (distance, first index, multiplicity) triples: lexicographic minimum, multiplicities of equal minima add up
-__device__ __forceinline__ void merge_min(float& d, int& k, int& c, float d2, int k2, int c2) {
+// merge (distance key, first index, multiplicity) triples: lexicographic minimum, multiplicities of equal minima add up
+// (keys: dist_key -- a NaN distance is the smallest key, as in torch.argmin)
+__device__ __forceinline__ void merge_min(uint32_t& d, int& k, int& c, uint32_t d2, int k2, int c2) {
     if (d2 < d) { d = d2; k = k2; c = c2; }
     else if (d2 == d) { c += c2; k = min(k, k2); }
 }
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(kFbThreads, kFbCtasPerSm)
 vq_fallback_kernel(const FallbackParams p) {
     __shared__ float4 zr4[kFbGroup][kD / 4];
     __shared__ __align__(16) float stage[kFbThreads / 32][32 * kFbPitch];      // 36 KiB: per-warp [32 codes][32 d] transposer
-    __shared__ float sd[kFbGroup][kFbThreads / 32];
+    __shared__ uint32_t sd[kFbGroup][kFbThreads / 32];
     __shared__ int sk[kFbGroup][kFbThreads / 32], sn[kFbGroup][kFbThreads / 32];
     __shared__ int64_t row_s[kFbGroup];
     __shared__ int is_final;
@@ -393,12 +395,13 @@ vq_fallback_kernel(const FallbackParams p) {
             if (tid < kD) reinterpret_cast<float*>(zr4[r])[tid] = (n >= 0) ? __ldg(p.z + ((n / p.HW) * kD + tid) * p.HW + n % p.HW) : 0.0f;
         }
         __syncthreads();
-        float z2[kFbGroup], best_d[kFbGroup];
+        float z2[kFbGroup];
+        uint32_t best_d[kFbGroup];
         int best_k[kFbGroup], n_at_min[kFbGroup];
 #pragma unroll
         for (int r = 0; r < kFbGroup; r++) {
             z2[r] = (row_s[r] >= 0) ? __ldg(p.z2 + row_s[r]) : 0.0f;
-            best_d[r] = INFINITY; best_k[r] = 0x7fffffff; n_at_min[r] = 0;
+            best_d[r] = 0xffffffffu; best_k[r] = 0x7fffffff; n_at_min[r] = 0;
         }
         const int k_hi = min(p.K, (part0 + 1) * per_part);
         // A warp scans 32 consecutive codes at a time, one code per lane (ascending k per lane).  The code rows are
@@ -443,7 +446,7 @@ vq_fallback_kernel(const FallbackParams p) {
 #pragma unroll
                 for (int r = 0; r < kFbGroup; r++) {
                     const float dot = __fadd_rn(__fadd_rn(acc[r][0], acc[r][1]), __fadd_rn(acc[r][2], acc[r][3]));
-                    merge_min(best_d[r], best_k[r], n_at_min[r], ref_distance(z2[r], e2k, dot), k, 1);
+                    merge_min(best_d[r], best_k[r], n_at_min[r], dist_key(ref_distance(z2[r], e2k, dot)), k, 1);
                 }
             }
         }
@@ -453,7 +456,7 @@ vq_fallback_kernel(const FallbackParams p) {
             for (int r = 0; r < kFbGroup; r++) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
-                    const float d2 = __shfl_xor_sync(0xffffffffu, best_d[r], o);
+                    const uint32_t d2 = __shfl_xor_sync(0xffffffffu, best_d[r], o);
                     const int k2 = __shfl_xor_sync(0xffffffffu, best_k[r], o);
                     const int c2 = __shfl_xor_sync(0xffffffffu, n_at_min[r], o);
                     merge_min(best_d[r], best_k[r], n_at_min[r], d2, k2, c2);
@@ -462,7 +465,7 @@ vq_fallback_kernel(const FallbackParams p) {
             }
             __syncthreads();
             if (tid < kFbGroup) {
-                float d = sd[tid][0];
+                uint32_t d = sd[tid][0];
                 int k = sk[tid][0], cnt = sn[tid][0];
                 for (int v = 1; v < kFbThreads / 32; v++) merge_min(d, k, cnt, sd[tid][v], sk[tid][v], sn[tid][v]);
                 sd[tid][0] = d; sk[tid][0] = k; sn[tid][0] = cnt;
@@ -472,7 +475,7 @@ vq_fallback_kernel(const FallbackParams p) {
         if (split) {
             if (tid < kFbGroup && row_s[tid] >= 0)
                 p.part[((int64_t)g * kFbGroup + tid) * parts + part0] =
-                    make_float4(sd[tid][0], __int_as_float(sk[tid][0]), __int_as_float(sn[tid][0]), 0.0f);
+                    make_float4(__uint_as_float(sd[tid][0]), __int_as_float(sk[tid][0]), __int_as_float(sn[tid][0]), 0.0f);
             __threadfence();
             __syncthreads();
             if (tid == 0) {
@@ -485,11 +488,11 @@ vq_fallback_kernel(const FallbackParams p) {
             // the last block to arrive merges the per-block results of the group, all threads taking part
 #pragma unroll
             for (int r = 0; r < kFbGroup; r++) {
-                best_d[r] = INFINITY; best_k[r] = 0x7fffffff; n_at_min[r] = 0;
+                best_d[r] = 0xffffffffu; best_k[r] = 0x7fffffff; n_at_min[r] = 0;
                 if (row_s[r] < 0) continue;                      // block-uniform
                 for (int q = tid; q < parts; q += kFbThreads) {
                     const float4 v = __ldcg(p.part + ((int64_t)g * kFbGroup + r) * parts + q);
-                    merge_min(best_d[r], best_k[r], n_at_min[r], v.x, __float_as_int(v.y), __float_as_int(v.z));
+                    merge_min(best_d[r], best_k[r], n_at_min[r], __float_as_uint(v.x), __float_as_int(v.y), __float_as_int(v.z));
                 }
             }
             __syncthreads();
@@ -502,7 +505,7 @@ vq_fallback_kernel(const FallbackParams p) {
             const int cnt = sn[tid][0];
             // a row can be listed twice (once per epilogue group): the first finisher publishes and counts it
             if (atomicExch(p.out_cnt + 2 * n, -2) != -2) {
-                if (k == 0x7fffffff) k = 0;                      // every distance NaN: torch.argmin -> 0 as well
+                if (k == 0x7fffffff) k = 0;                      // (K >= 1: cannot happen)
                 reinterpret_cast<uint2*>(p.out_q)[n * kOutCap] = make_uint2((uint32_t)(k >> 5), 1u << (k & 31));
                 if (p.stats != nullptr) {
                     if (cnt > 1) atomicAdd(p.stats + 0, 1ull);
