@@ -235,6 +235,9 @@ def main():
     ap.add_argument("--distribution", default="init", choices=["init", "trained"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--strong", action="store_true",
+                    help="strong scaling: the workload's batch is the GLOBAL batch, split evenly over the ranks (default: weak, "
+                         "the batch is per GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -261,6 +264,10 @@ def main():
 
     wl = WORKLOADS[args.workload]
     B, H, W, K = wl["B"], wl["H"], wl["W"], wl["K"]
+    if args.strong:
+        if B % world:
+            raise SystemExit(f"--strong needs the batch ({B}) to be divisible by the number of GPUs ({world})")
+        B //= world
     tok = bool(wl.get("tokenizer"))
     N = B * H * W
     E, z, g_out = make_latents(torch, dev, B, H, W, K, args.distribution, 1234 + rank)
@@ -422,7 +429,7 @@ def main():
     line = {
         "metric": "vq_latents_per_sec_fwd_bwd" if not tok else "vq_latents_per_sec_tokenize",
         "value": N * world / (ms_step / 1e3), "unit": "latents/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak",
         "vs_baseline": None, "dtype": "f32",
         "dtype_note": "results are the reference's fp32 results; the distance GEMM that proposes candidates runs f16 operands with f32 accumulation on tcgen05, the decision is an exact f32 re-rank",
         "data": "synthetic",
