@@ -194,7 +194,7 @@ int pick_layout(const float* z, int64_t HW, bool rows) {
 }
 
 int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, const void* E_h, const float* e2, const float* cb, int K,
-             const Workspace& w, float* dbg_scores, cudaStream_t st) {
+             const Workspace& w, float* dbg_scores, int64_t* hist, unsigned long long* stats, cudaStream_t st) {
     DevInfo* dev;
     int rc = device_info(&dev);
     if (rc != VQ_OK) return rc;
@@ -202,15 +202,22 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, const void* E_h, 
     const int k_pad = vq_padded_codes(K);
 
     const unsigned pgrid = (unsigned)(n_pad / vq::kSelRows);
+    vq::PrepClear clr;
+    clr.control = w.blocks_done;                       // loss arrival counter, worklist length, group arrivals
+    clr.control_words = (int)(w.control_bytes / sizeof(unsigned int));
+    clr.hist = reinterpret_cast<unsigned long long*>(hist);
+    clr.K = K;
+    clr.stats = stats;
+    clr.n_stats = VQ_STAT_COUNT;
     switch (pick_layout(z, HW, rows)) {
         case vq::kLayoutRows:
-            vq::vq_prep_z_kernel<vq::kLayoutRows><<<pgrid, vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2, w.z_inv_scale);
+            vq::vq_prep_z_kernel<vq::kLayoutRows><<<pgrid, vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2, w.z_inv_scale, clr);
             break;
         case vq::kLayoutVec:
-            vq::vq_prep_z_kernel<vq::kLayoutVec><<<pgrid, vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2, w.z_inv_scale);
+            vq::vq_prep_z_kernel<vq::kLayoutVec><<<pgrid, vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2, w.z_inv_scale, clr);
             break;
         default:
-            vq::vq_prep_z_kernel<vq::kLayoutGeneric><<<pgrid, vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2, w.z_inv_scale);
+            vq::vq_prep_z_kernel<vq::kLayoutGeneric><<<pgrid, vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2, w.z_inv_scale, clr);
     }
     VQ_LAUNCH_CHECK("vq_prep_z_kernel");
 
@@ -231,7 +238,6 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, const void* E_h, 
     gp.dbg_scores = dbg_scores;
     gp.timeline = g_timeline;
     gp.timeline_tiles = g_timeline_tiles;
-    VQ_CUDA(cudaMemsetAsync(w.blocks_done, 0, w.control_bytes, st));     // loss arrival counter, worklist length, group arrivals
     const bool prof = g_prof.on && g_prof.n < kProfCap;
     if (prof) {
         while (g_prof.created <= g_prof.n) {
@@ -337,9 +343,10 @@ static int forward_impl(bool training, bool rows, const float* z, int64_t B, int
     if (!E || !E_h || !e2 || !cb) return fail(VQ_E_INVALID, "null codebook pointer");
     const int64_t N = B * HW;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    if (stats) VQ_CUDA(cudaMemsetAsync(stats, 0, VQ_STAT_COUNT * sizeof(unsigned long long), st));
-    if (training && hist) VQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)K * sizeof(int64_t), st));
     if (N == 0) {
+        // nothing is launched: clear the outputs directly
+        if (stats) VQ_CUDA(cudaMemsetAsync(stats, 0, VQ_STAT_COUNT * sizeof(unsigned long long), st));
+        if (training && hist) VQ_CUDA(cudaMemsetAsync(hist, 0, (size_t)K * sizeof(int64_t), st));
         // torch.mean over an empty tensor is NaN (codebook.py:96)
         if (training && loss) {
             const float nanv = __builtin_nanf("");
@@ -355,7 +362,7 @@ static int forward_impl(bool training, bool rows, const float* z, int64_t B, int
 
     if (idx_bits != 64 && idx_bits != 32 && idx_bits != 16) return fail(VQ_E_INVALID, "idx_bits must be 16, 32 or 64, got %d", idx_bits);
     if (idx_bits == 16 && K > 65536) return fail(VQ_E_INVALID, "16-bit indices need K <= 65536, got K=%d", K);
-    rc = run_gemm(z, N, HW, rows, E_h, e2, cb, K, w, nullptr, st);
+    rc = run_gemm(z, N, HW, rows, E_h, e2, cb, K, w, nullptr, training ? hist : nullptr, stats, st);
     if (rc != VQ_OK) return rc;
 
     {   // rows whose candidate list overflowed (rare): exact scan, one CTA per row; a no-op when the worklist is empty
@@ -437,7 +444,7 @@ VQ_EXPORT int vq_debug_scores(const float* z_nchw, int64_t B, int64_t HW, int D,
     Workspace w;
     rc = check_ws(workspace, workspace_bytes, N, &w);
     if (rc != VQ_OK) return rc;
-    return run_gemm(z_nchw, N, HW, false, E_h, e_norm2, cb_scalars, K, w, scores, reinterpret_cast<cudaStream_t>(stream));
+    return run_gemm(z_nchw, N, HW, false, E_h, e_norm2, cb_scalars, K, w, scores, nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
 VQ_EXPORT int vq_backward(const float* gout, const int64_t* gout_strides, float g_loss, const float* g_loss_dev,

@@ -20,13 +20,32 @@ constexpr int kCbInvScale = 2;   // 2^(ex_E - 15): inverse of the fp16 operand s
 
 // One CTA = 32 consecutive latents, tile in shared memory row-major with swizzled 16-byte pieces (vq_common.cuh
 // tile_off): column-form fill (16-byte loads along hw), then everything per latent row -- warp w owns rows 4w..4w+3.
+// Per-call scratch that later kernels of the same call accumulate into; cleared here (the first kernel of every call)
+// instead of by separate memset nodes: the control words of the workspace, the usage histogram and the counters.
+struct PrepClear {
+    unsigned int* control;          // blocks_done | fb_count | fb_arrive (contiguous)
+    int control_words;
+    unsigned long long* hist;       // (K) or null
+    int K;
+    unsigned long long* stats;      // (VQ_STAT_COUNT) or null
+    int n_stats;
+};
+
 template <int kLayout>
 __global__ void __launch_bounds__(kPrepThreads)
 vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_pad,
-                 __half* __restrict__ z_h, float* __restrict__ z2, float* __restrict__ z_inv_scale) {
+                 __half* __restrict__ z_h, float* __restrict__ z2, float* __restrict__ z_inv_scale, const PrepClear clr) {
     __shared__ __align__(16) float tile[kSelRows * kD];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n0 = (int64_t)blockIdx.x * kSelRows;
+
+    {   // grid-strided clears (a few KiB in total)
+        const int64_t gtid = (int64_t)blockIdx.x * kPrepThreads + tid, gsz = (int64_t)gridDim.x * kPrepThreads;
+        for (int64_t i = gtid; i < clr.control_words; i += gsz) clr.control[i] = 0u;
+        if (clr.hist != nullptr)
+            for (int64_t i = gtid; i < clr.K; i += gsz) clr.hist[i] = 0ull;
+        if (clr.stats != nullptr && gtid < clr.n_stats) clr.stats[gtid] = 0ull;
+    }
 
     if (kLayout != kLayoutGeneric && n0 >= N) {                                   // pad rows of the last GEMM row tile: zero operand rows
         // (a 32-row slab of a row tile is not contiguous in the operand image: zero it piecewise)
