@@ -42,6 +42,10 @@ typedef struct CUstream_st* vq_stream_t; /* == cudaStream_t */
 #define VQ_STAT_CANDIDATES    3  /* total candidates that survived the margin filter */
 #define VQ_STAT_COUNT         4
 
+/* fp32 distance recipes of the reference's nearest-code searches (vq_argmin_rows) */
+#define VQ_RECIPE_EXPANDED 0  /* |x|^2 + |e|^2 - 2 x.e   codebook.py:70-79, diffusion_gaussian2d.py:334-339 */
+#define VQ_RECIPE_DIFFSQ   1  /* sum_d (x_d - e_d)^2     continous_vq_diffusion/v_vq_diffusion.py:114-123 */
+
 int         vq_abi_version(void);
 const char* vq_last_error(void);
 
@@ -92,18 +96,22 @@ int vq_argmin_narrow(const float* z_nchw, int64_t B, int64_t HW, int D,
                      void* workspace, size_t workspace_bytes, vq_stream_t stream);
 
 /*
- * Nearest-code search over ROW-MAJOR vectors.  Same fp32 distance formula
- * |x|^2 + |e|^2 - 2 x.e and first-minimum argmin as vq_argmin, for callers that hold (N, D) rows instead of an
- * NCHW latent grid.  Replaces GaussianDiffusion2D.gaussian_to_indices
- * (network/vqDiffusion/submodule/diffusion_gaussian2d.py:322-347: gaussian_flat (B*L, gaussian_dim) against
- * gaussian_lookup_table (K, gaussian_dim)).  D must be 256 here; narrower vectors (gaussian_dim = 96 in
+ * Nearest-code search over ROW-MAJOR vectors, first-minimum argmin (torch.argmin), for callers
+ * that hold (N, D) rows instead of an NCHW latent grid.  `recipe` selects the reference's fp32 formula:
+ *   VQ_RECIPE_EXPANDED  replaces GaussianDiffusion2D.gaussian_to_indices
+ *                       (network/vqDiffusion/submodule/diffusion_gaussian2d.py:322-347: gaussian_flat (B*L, gaussian_dim)
+ *                       against gaussian_lookup_table (K, gaussian_dim)) -- the CodeBook's own formula;
+ *   VQ_RECIPE_DIFFSQ    replaces the search at the end of V_VQDiffusion.sample
+ *                       (network/continous_vq_diffusion/v_vq_diffusion.py:114-123: sum((x - e)^2) over a broadcast
+ *                       (B, L, K, D) difference, which this path never materialises).
+ * D must be 256 here; narrower vectors (gaussian_dim = 96 in
  * configs/*.yml) are zero-padded by the caller, which changes no distance (see nearest.py).
  *   x_rows  (N, D) fp32, contiguous
  *   idx     (N) integers of idx_bits (64 / 32 / 16)
  */
 int vq_argmin_rows(const float* x_rows, int64_t N, int D,
                    const float* E, const void* E_h, const float* e_norm2, const float* cb_scalars, int K,
-                   void* idx, int idx_bits, unsigned long long* stats,
+                   int recipe, void* idx, int idx_bits, unsigned long long* stats,
                    void* workspace, size_t workspace_bytes, vq_stream_t stream);
 
 /*

@@ -153,6 +153,52 @@ VQO_API int vq_oracle_forward(const float* z_nchw, int64_t B, int64_t HW, int D,
 }
 
 /*
+ * Nearest code of row-major vectors under the broadcast-difference recipe of
+ * /root/reference/network/continous_vq_diffusion/v_vq_diffusion.py:114-123:
+ *     distances = torch.sum((x.unsqueeze(2) - codebook.unsqueeze(0).unsqueeze(0)) ** 2, dim=-1);  distances.argmin(-1)
+ * i.e. d[n,k] = sum_d fl(fl(x_nd - e_kd)^2), each term rounded before it is added (no fused multiply-add), summed here
+ * in the canonical order (four partial sums over d == j (mod 4), ascending, (p0 + p1) + (p2 + p3)); first minimum,
+ * NaN counts as the minimum (torch.argmin).
+ *   x_rows (N, D) row-major, E (K, D); idx (N) int64; dist_min (N) and tie_rows optional.
+ */
+static inline float vqo_diffsq(const float* x, const float* y, int D) {
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int d = 0; d < D; d++) {
+        volatile float diff = x[d] - y[d];
+        volatile float sq = diff * diff;
+        volatile float acc = p[d & 3] + sq;
+        p[d & 3] = acc;
+    }
+    volatile float a = p[0] + p[1], b = p[2] + p[3];
+    return a + b;
+}
+
+VQO_API int vq_oracle_nearest_diffsq(const float* x_rows, int64_t N, int D, const float* E, int K,
+                                     int64_t* idx, float* dist_min, uint64_t* tie_rows) {
+    if (N < 0 || D <= 0 || K <= 0 || !idx) return -1;
+    uint64_t ties = 0;
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : ties)
+    for (int64_t n = 0; n < N; n++) {
+        const float* x = x_rows + n * (int64_t)D;
+        float best = INFINITY;
+        int64_t best_k = 0;
+        int n_best = 0;
+        for (int k = 0; k < K; k++) {
+            const float dist = vqo_diffsq(x, E + (int64_t)k * D, D);
+            if (k == 0) { best = dist; best_k = k; n_best = 1; }
+            else if (isnan(best)) { if (isnan(dist)) n_best++; }
+            else if (isnan(dist) || dist < best) { best = dist; best_k = k; n_best = 1; }
+            else if (dist == best) n_best++;
+        }
+        idx[n] = best_k;
+        if (dist_min) dist_min[n] = best;
+        if (n_best > 1) ties++;
+    }
+    if (tie_rows) *tie_rows = ties;
+    return 0;
+}
+
+/*
  * Distances of selected (row, code) pairs in canonical order -- lets the tests classify a
  * disagreement without recomputing whole rows.
  */

@@ -59,6 +59,8 @@ class COracle:
         L.vq_oracle_pair_dist.argtypes = [_f32p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _f32p, _i64p, _i64p,
                                           ctypes.c_int64, _f32p]
         L.vq_oracle_pair_dist.restype = None
+        L.vq_oracle_nearest_diffsq.argtypes = [_f32p, ctypes.c_int64, ctypes.c_int, _f32p, ctypes.c_int, _i64p, _f32p, _u64p]
+        L.vq_oracle_nearest_diffsq.restype = ctypes.c_int
         L.vq_oracle_backward.argtypes = [_f32p, _i64p, ctypes.c_float, _f32p, _i64p, _f32p, ctypes.c_int64,
                                          ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int64,
                                          _f32p, _f32p]
@@ -94,6 +96,21 @@ class COracle:
         if rc != 0:
             raise RuntimeError(f"vq_oracle_forward rc={rc}")
         return dict(zq_nhwc=zq, idx=idx, loss=np.float32(loss[0]), hist=hist, dist_min=dmin, tie_rows=int(ties.value))
+
+    def nearest_diffsq(self, x: np.ndarray, E: np.ndarray):
+        """x: (..., D) fp32 rows, E: (K, D) -> dict(idx (N,), dist_min, tie_rows) under the sum((x - e)**2) recipe of
+        v_vq_diffusion.py:114-123 (canonical order)."""
+        E = np.ascontiguousarray(E, dtype=np.float32)
+        rows = np.ascontiguousarray(np.asarray(x, dtype=np.float32).reshape(-1, E.shape[1]))
+        N = rows.shape[0]
+        idx = np.empty(N, np.int64)
+        dmin = np.empty(N, np.float32)
+        ties = ctypes.c_uint64(0)
+        rc = self.lib.vq_oracle_nearest_diffsq(_p(rows, _f32p), N, E.shape[1], _p(E, _f32p), E.shape[0], _p(idx, _i64p),
+                                               _p(dmin, _f32p), ctypes.byref(ties))
+        if rc != 0:
+            raise RuntimeError(f"vq_oracle_nearest_diffsq rc={rc}")
+        return dict(idx=idx, dist_min=dmin, tie_rows=int(ties.value))
 
     def pair_dist(self, z: np.ndarray, E: np.ndarray, rows, codes) -> np.ndarray:
         z = np.ascontiguousarray(z, dtype=np.float32)

@@ -96,3 +96,25 @@ def make_nn_inputs(spec: dict):
     table = rng.random((K, D), dtype=np.float32)
     x = table[rng.integers(0, K, size=B * L)] + np.float32(spec["noise"]) * rng.standard_normal((B * L, D), dtype=np.float32)
     return np.ascontiguousarray(x.reshape(B, L, D), dtype=np.float32), table
+
+
+# Broadcast-difference search at the end of V_VQDiffusion.sample (v_vq_diffusion.py:114-123): sampled embeddings
+# (B, L, 256) against the VQVAE codebook (K, 256).
+DIFFSQ_CASES = {
+    "dsq_trained":  dict(B=2, L=64, K=512, D=256, dist="trained", noise=0.3, seed=301),
+    "dsq_init":     dict(B=2, L=48, K=1024, D=256, dist="init", noise=1.0, seed=302),     # codebook at its U(-1/K, 1/K) init
+    "dsq_ragged":   dict(B=3, L=37, K=333, D=256, dist="trained", noise=0.6, seed=303),
+}
+
+
+def make_diffsq_inputs(spec: dict):
+    """-> x (B, L, D) fp32, codebook (K, D) fp32."""
+    rng = np.random.default_rng(spec["seed"])
+    B, L, K, D = spec["B"], spec["L"], spec["K"], spec["D"]
+    if spec["dist"] == "init":
+        E = rng.uniform(-1.0 / K, 1.0 / K, size=(K, D)).astype(np.float32)
+        x = rng.standard_normal((B * L, D), dtype=np.float32) * np.float32(spec["noise"])
+    else:
+        E = rng.standard_normal((K, D), dtype=np.float32)
+        x = E[rng.integers(0, K, size=B * L)] + np.float32(spec["noise"]) * rng.standard_normal((B * L, D), dtype=np.float32)
+    return np.ascontiguousarray(x.reshape(B, L, D), dtype=np.float32), E

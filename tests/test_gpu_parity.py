@@ -583,3 +583,53 @@ def test_nan_and_inf_rows_follow_the_oracle(vq, oracle):
         idx2 = cb.encode_indices(torch.from_numpy(zc).to(dev))
     assert (idx2 == 433).all()
     assert np.array_equal(idx2.cpu().numpy(), oracle.forward(zc, E2, want_zq=False)["idx"])
+
+
+from cases import DIFFSQ_CASES, make_diffsq_inputs  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(DIFFSQ_CASES))
+def test_nearest_rows_diffsq_vs_oracle_and_reference(name, vq, oracle):
+    """The broadcast-difference recipe of V_VQDiffusion.sample (v_vq_diffusion.py:114-123) on the same GEMM + exact stage."""
+    spec = DIFFSQ_CASES[name]
+    dev = torch.device("cuda:0")
+    x, E = make_diffsq_inputs(spec)
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    tab = vq.CodeTable(torch.from_numpy(E).to(dev))
+    idx = tab.nearest(torch.from_numpy(x).to(dev), recipe="diffsq")
+    assert idx.shape == (spec["B"], spec["L"])
+    ref = oracle.nearest_diffsq(x, E)
+    got = idx.reshape(-1).cpu().numpy()
+    assert np.array_equal(got, ref["idx"])
+    st = dict(zip(vq._native.VQ_STAT_NAMES, tab.last_stats.tolist()))
+    assert st["tie_rows"] == ref["tie_rows"]
+    gidx = gold["idx"].reshape(-1).astype(np.int64)
+    rows = x.reshape(-1, 256).astype(np.float64)
+    for r in np.nonzero(got != gidx)[0]:
+        da = ((rows[r] - E[got[r]].astype(np.float64)) ** 2).sum()
+        db = ((rows[r] - E[gidx[r]].astype(np.float64)) ** 2).sum()
+        assert abs(da - db) <= 70 * 2.0 ** -24 * max(da, db), (r, da, db)
+    with pytest.raises(ValueError):
+        tab.nearest(torch.from_numpy(x).to(dev), recipe="cosine")
+
+
+def test_diffsq_large_and_fallback(vq, oracle):
+    """Ragged N, duplicated codes (ties -> lowest index) and a cluster of near-identical codes (exact fallback) under the
+    broadcast-difference recipe."""
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(31)
+    N, K = 2051, 1500
+    E = rng.standard_normal((K, 256)).astype(np.float32)
+    E[700:760] = E[40]                                                # 60 copies of code 40
+    v = rng.standard_normal(256).astype(np.float32)
+    E[1000:1100] = v + 1e-4 * rng.standard_normal((100, 256)).astype(np.float32)
+    x = E[rng.integers(0, K, N)] + 0.4 * rng.standard_normal((N, 256)).astype(np.float32)
+    x[:7] = v + 0.05 * rng.standard_normal((7, 256)).astype(np.float32)
+    x[7:12] = E[40]
+    tab = vq.CodeTable(torch.from_numpy(E).to(dev))
+    idx = tab.nearest(torch.from_numpy(x).to(dev), recipe="diffsq")
+    ref = oracle.nearest_diffsq(x, E)
+    assert np.array_equal(idx.cpu().numpy(), ref["idx"])
+    assert (idx[7:12] == 40).all()
+    st = dict(zip(vq._native.VQ_STAT_NAMES, tab.last_stats.tolist()))
+    assert st["fallback_rows"] >= 7 and st["tie_rows"] == ref["tie_rows"]

@@ -225,3 +225,42 @@ def test_nan_and_inf_follow_torch_argmin(oracle):
     E2 = E.copy()
     E2[33, 7] = np.nan
     assert (oracle.forward(z, E2, want_zq=False)["idx"][ok] == 33).all()
+
+
+# Broadcast-difference recipe (V_VQDiffusion.sample, v_vq_diffusion.py:114-123)
+from cases import DIFFSQ_CASES, make_diffsq_inputs  # noqa: E402
+
+
+def _classify_diffsq(x, E, idx_a, idx_b):
+    """Mismatching rows: exact tie in float64 distance terms or inside the rounding band of a 256-term fp32 sum."""
+    rows = x.reshape(-1, x.shape[-1]).astype(np.float64)
+    bad = np.nonzero(idx_a != idx_b)[0]
+    real = 0
+    for r in bad:
+        da = ((rows[r] - E[idx_a[r]].astype(np.float64)) ** 2).sum()
+        db = ((rows[r] - E[idx_b[r]].astype(np.float64)) ** 2).sum()
+        if abs(da - db) > 70 * 2.0 ** -24 * max(da, db):
+            real += 1
+    return dict(mismatch=int(bad.size), real=real)
+
+
+@pytest.mark.parametrize("name", sorted(DIFFSQ_CASES))
+def test_oracle_matches_reference_diffsq(name, oracle):
+    spec = DIFFSQ_CASES[name]
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    x, E = make_diffsq_inputs(spec)
+    ref = oracle.nearest_diffsq(x, E)
+    cls = _classify_diffsq(x, E, ref["idx"], gold["idx"].reshape(-1).astype(np.int64))
+    assert cls["real"] == 0, cls
+    assert cls["mismatch"] <= int(gold["ref_tie_rows"]) + int(gold["ref_ne_fp64"]) + 2, cls
+
+
+def test_diffsq_known_answers(oracle):
+    E = np.array([[0.0, 0.0], [1.0, 0.0], [0.0, 1.0], [1.0, 1.0], [1.0, 1.0]], np.float32)
+    x = np.array([[0.1, 0.2], [0.9, 0.2], [0.6, 0.9], [1.0, 1.0]], np.float32)
+    out = oracle.nearest_diffsq(x, E)
+    assert out["idx"].tolist() == [0, 1, 3, 3]                      # duplicate codes 3 and 4: the lower index wins
+    assert out["tie_rows"] == 2 and out["dist_min"][3] == 0.0
+    xn = x.copy()
+    xn[1, 0] = np.nan
+    assert oracle.nearest_diffsq(xn, E)["idx"].tolist() == [0, 0, 3, 3]   # all distances NaN -> first code

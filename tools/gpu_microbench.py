@@ -131,9 +131,12 @@ def main():
             gm = _native.profile_collect()
             _native.profile_enable(False)
             t_i32 = timed(lambda: tab.nearest(x, dtype=torch.int32), args.reps, flush)[0]
+            t_dsq = timed(lambda: tab.nearest(x, recipe="diffsq"), args.reps, flush)[0]
+            dsq_stats = dict(zip(_native.VQ_STAT_NAMES, tab.last_stats.tolist()))
+            tab.nearest(x)
             flops = 2.0 * N * K * 256
             print(json.dumps({"config": "rows: " + label, "N": N, "K": K, "D": Dn, "nearest_ms": round(t_all, 4),
-                              "nearest_int32_ms": round(t_i32, 4), "gemm_kernel_ms": round(statistics.median(gm), 4),
+                              "nearest_int32_ms": round(t_i32, 4), "nearest_diffsq_ms": round(t_dsq, 4), "diffsq_stats": dsq_stats, "gemm_kernel_ms": round(statistics.median(gm), 4),
                               "gemm_frac_of_bf16_peak": round(flops / statistics.median(gm) / 1e9 / peaks["bf16_tflops"], 4),
                               "Mrows_s": round(N / t_all / 1e3, 2), "stats": dict(zip(_native.VQ_STAT_NAMES, tab.last_stats.tolist()))}))
 

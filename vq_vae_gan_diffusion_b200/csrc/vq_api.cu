@@ -193,7 +193,7 @@ int pick_layout(const float* z, int64_t HW, bool rows) {
     return (HW % vq::kSelRows == 0 && aligned) ? vq::kLayoutVec : vq::kLayoutGeneric;
 }
 
-int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, const void* E_h, const float* e2, const float* cb, int K,
+int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, int recipe, const void* E_h, const float* e2, const float* cb, int K,
              const Workspace& w, float* dbg_scores, int64_t* hist, unsigned long long* stats, cudaStream_t st) {
     DevInfo* dev;
     int rc = device_info(&dev);
@@ -236,6 +236,7 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, const void* E_h, 
     gp.fb_rows = w.fb_rows;
     gp.fb_count = w.fb_count;
     gp.dbg_scores = dbg_scores;
+    gp.recipe = recipe;
     gp.timeline = g_timeline;
     gp.timeline_tiles = g_timeline_tiles;
     const bool prof = g_prof.on && g_prof.n < kProfCap;
@@ -268,6 +269,8 @@ int check_ws(void* ws, size_t ws_bytes, int64_t N, Workspace* w) {
         return fail(VQ_E_WORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, w->bytes);
     return VQ_OK;
 }
+
+static_assert(VQ_RECIPE_EXPANDED == vq::kRecipeExpanded && VQ_RECIPE_DIFFSQ == vq::kRecipeDiffSq, "header and kernels disagree");
 
 }  // namespace
 
@@ -334,7 +337,7 @@ VQ_EXPORT int vq_prepare_codebook(const float* E, int K, int D, void* E_h, float
     return VQ_OK;
 }
 
-static int forward_impl(bool training, bool rows, const float* z, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
+static int forward_impl(bool training, bool rows, int recipe, const float* z, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
                         const float* e2, const float* cb, int K, float beta, float* zq, void* idx, int idx_bits, float* loss,
                         int64_t* hist, unsigned long long* stats, void* ws, size_t ws_bytes, vq_stream_t stream) {
     g_launches = 0;
@@ -362,14 +365,15 @@ static int forward_impl(bool training, bool rows, const float* z, int64_t B, int
 
     if (idx_bits != 64 && idx_bits != 32 && idx_bits != 16) return fail(VQ_E_INVALID, "idx_bits must be 16, 32 or 64, got %d", idx_bits);
     if (idx_bits == 16 && K > 65536) return fail(VQ_E_INVALID, "16-bit indices need K <= 65536, got K=%d", K);
-    rc = run_gemm(z, N, HW, rows, E_h, e2, cb, K, w, nullptr, training ? hist : nullptr, stats, st);
+    if (recipe != vq::kRecipeExpanded && recipe != vq::kRecipeDiffSq) return fail(VQ_E_INVALID, "unknown distance recipe %d", recipe);
+    rc = run_gemm(z, N, HW, rows, recipe, E_h, e2, cb, K, w, nullptr, training ? hist : nullptr, stats, st);
     if (rc != VQ_OK) return rc;
 
     {   // rows whose candidate list overflowed (rare): exact scan, one CTA per row; a no-op when the worklist is empty
         vq::FallbackParams fp;
         fp.z = z; fp.E = E; fp.e2 = e2; fp.z2 = w.z2;
         fp.fb_rows = w.fb_rows; fp.fb_count = w.fb_count;
-        fp.HW = HW; fp.K = K;
+        fp.HW = HW; fp.K = K; fp.recipe = recipe;
         fp.out_cnt = w.out_cnt; fp.out_q = w.out_q; fp.stats = stats;
         fp.part = w.fb_part; fp.arrive = w.fb_arrive;
         DevInfo* dev;
@@ -385,7 +389,7 @@ static int forward_impl(bool training, bool rows, const float* z, int64_t B, int
     sp.z = z; sp.E = E; sp.e2 = e2; sp.z2 = w.z2;
     sp.out_cnt = w.out_cnt; sp.out_q = w.out_q;
     sp.N = N; sp.HW = HW; sp.K = K; sp.beta = beta;
-    sp.idx = idx; sp.idx_bits = idx_bits; sp.zq = zq;
+    sp.idx = idx; sp.idx_bits = idx_bits; sp.recipe = recipe; sp.zq = zq;
     sp.hist = reinterpret_cast<unsigned long long*>(hist);
     sp.loss_partial = w.loss_partial; sp.blocks_done = w.blocks_done; sp.loss = loss;
     sp.stats = stats;
@@ -406,30 +410,30 @@ static int forward_impl(bool training, bool rows, const float* z, int64_t B, int
 VQ_EXPORT int vq_argmin(const float* z_nchw, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
                         const float* e_norm2, const float* cb_scalars, int K, int64_t* idx, unsigned long long* stats,
                         void* workspace, size_t workspace_bytes, vq_stream_t stream) {
-    return forward_impl(false, false, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, 0.0f, nullptr, idx, 64, nullptr, nullptr,
-                        stats, workspace, workspace_bytes, stream);
+    return forward_impl(false, false, VQ_RECIPE_EXPANDED, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, 0.0f, nullptr, idx, 64, nullptr,
+                        nullptr, stats, workspace, workspace_bytes, stream);
 }
 
 VQ_EXPORT int vq_argmin_narrow(const float* z_nchw, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
                                const float* e_norm2, const float* cb_scalars, int K, void* idx, int idx_bits,
                                unsigned long long* stats, void* workspace, size_t workspace_bytes, vq_stream_t stream) {
-    return forward_impl(false, false, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, 0.0f, nullptr, idx, idx_bits, nullptr,
-                        nullptr, stats, workspace, workspace_bytes, stream);
+    return forward_impl(false, false, VQ_RECIPE_EXPANDED, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, 0.0f, nullptr, idx, idx_bits,
+                        nullptr, nullptr, stats, workspace, workspace_bytes, stream);
 }
 
 VQ_EXPORT int vq_argmin_rows(const float* x_rows, int64_t N, int D, const float* E, const void* E_h, const float* e_norm2,
-                             const float* cb_scalars, int K, void* idx, int idx_bits, unsigned long long* stats,
+                             const float* cb_scalars, int K, int recipe, void* idx, int idx_bits, unsigned long long* stats,
                              void* workspace, size_t workspace_bytes, vq_stream_t stream) {
-    return forward_impl(false, true, x_rows, N, 1, D, E, E_h, e_norm2, cb_scalars, K, 0.0f, nullptr, idx, idx_bits, nullptr, nullptr,
-                        stats, workspace, workspace_bytes, stream);
+    return forward_impl(false, true, recipe, x_rows, N, 1, D, E, E_h, e_norm2, cb_scalars, K, 0.0f, nullptr, idx, idx_bits, nullptr,
+                        nullptr, stats, workspace, workspace_bytes, stream);
 }
 
 VQ_EXPORT int vq_forward(const float* z_nchw, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
                          const float* e_norm2, const float* cb_scalars, int K, float beta, float* zq_nhwc, int64_t* idx,
                          float* loss, int64_t* hist, unsigned long long* stats, void* workspace, size_t workspace_bytes,
                          vq_stream_t stream) {
-    return forward_impl(true, false, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, beta, zq_nhwc, idx, 64, loss, hist, stats,
-                        workspace, workspace_bytes, stream);
+    return forward_impl(true, false, VQ_RECIPE_EXPANDED, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, beta, zq_nhwc, idx, 64, loss, hist,
+                        stats, workspace, workspace_bytes, stream);
 }
 
 VQ_EXPORT int vq_debug_scores(const float* z_nchw, int64_t B, int64_t HW, int D, const void* E_h, const float* e_norm2,
@@ -444,7 +448,7 @@ VQ_EXPORT int vq_debug_scores(const float* z_nchw, int64_t B, int64_t HW, int D,
     Workspace w;
     rc = check_ws(workspace, workspace_bytes, N, &w);
     if (rc != VQ_OK) return rc;
-    return run_gemm(z_nchw, N, HW, false, E_h, e_norm2, cb_scalars, K, w, scores, nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream));
+    return run_gemm(z_nchw, N, HW, false, VQ_RECIPE_EXPANDED, E_h, e_norm2, cb_scalars, K, w, scores, nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
 VQ_EXPORT int vq_backward(const float* gout, const int64_t* gout_strides, float g_loss, const float* g_loss_dev,

@@ -93,6 +93,7 @@ struct GemmParams {
     int32_t* fb_rows;          // (2N) worklist of the rows flagged -1 (for vq_fallback_kernel)
     int32_t* fb_count;         // (1)  its length, zeroed before launch
     float* dbg_scores;         // (N, K_pad) or null
+    int recipe;                // kRecipeExpanded / kRecipeDiffSq: selects the candidate threshold (vq_common.cuh)
     long long* timeline;       // debug: per-tile clock64 stamps of CTA 0 (kTimeline builds), [tile][8]
     int timeline_tiles;
 };
@@ -292,7 +293,9 @@ vq_argmin_gemm_kernel(const GemmParams p) {
             // Inf / NaN in the row or anywhere in the codebook: distances become NaN / inf, where torch.argmin's rule (first
             // NaN wins) cannot be decided from approximate scores -> the row takes the exact full scan
             const bool nonfinite = !(fabsf(z2row) < INFINITY) || !(fabsf(e2max) < INFINITY);
-            const float margin = candidate_margin(z2row, e2max);
+            // threshold for a minimum m: fma(m, cmul, margin0); for the CodeBook's recipe cmul == 1 and this is m + margin
+            float cmul, margin;
+            candidate_threshold(p.recipe, z2row, e2max, cmul, margin);
             // score = e2 + cscale * acc,  acc = (z * 2^a) . (e * 2^b)  ->  cscale = -2 * 2^-a * 2^-b  (exact)
             const float cscale = -2.0f * (row_ok ? __ldg(p.z_inv_scale + row) : 1.0f) * e_inv;
             float m_run = INFINITY, thr = INFINITY, lost_min = INFINITY;
@@ -309,7 +312,7 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                 const uint32_t e2a = e2_sa[buf];
                 // the other column group's running minimum (possibly one tile stale: still an upper bound of the row
                 // minimum) tightens this group's threshold
-                thr = fminf(thr, fminf(m_run, lds_f32(live_other_sa)) + margin);
+                thr = fminf(thr, __fmaf_rn(fminf(m_run, lds_f32(live_other_sa)), cmul, margin));
 
                 // The accumulator buffer must go back to the MMA warps EARLY: a buffer cycles MMA -> drain -> MMA and the
                 // next MMA on it is due one tile time after the previous one ended.  All four 32-column loads of this
@@ -370,7 +373,7 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                         // slow path: this chunk holds a code within the running threshold -> one ring entry with the
                         // mask of all such codes (only quads whose minimum passes are looked into)
                         m_run = fminf(m_run, cm);
-                        thr = fminf(thr, m_run + margin);
+                        thr = fminf(thr, __fmaf_rn(m_run, cmul, margin));
                         uint32_t cmask = 0;
 #pragma unroll
                         for (int q = 0; q < 8; q++) {
@@ -405,7 +408,7 @@ vq_argmin_gemm_kernel(const GemmParams p) {
             const float m_fin = fminf(m_run, s.m_part[pb][grp ^ 1][trow]);
             const int cnt_all = cnt + s.c_part[pb][grp ^ 1][trow];
             if (row_ok) {
-                const float thr_fin = m_fin + margin;
+                const float thr_fin = __fmaf_rn(m_fin, cmul, margin);
                 int n_out = 0, n_codes = 0;
                 // nothing recorded at all (NaN row: group 0 reports) or a possible survivor was overwritten
                 bool bad = (cnt_all == 0 && grp == 0) || (lost_min <= thr_fin) || nonfinite;

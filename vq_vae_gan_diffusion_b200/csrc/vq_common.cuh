@@ -142,4 +142,38 @@ __device__ __forceinline__ float candidate_margin(float z2, float e2max) {
     return 2.0f * eps * 1.0625f + 1e-37f;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Distance recipes.  The reference computes nearest codes with two different fp32 formulas:
+//   kRecipeExpanded  |x|^2 + |e|^2 - 2 x.e     codebook.py:70-79, diffusion_gaussian2d.py:334-339
+//   kRecipeDiffSq    sum_d (x_d - e_d)^2       v_vq_diffusion.py:114-123 (broadcast difference, squared, torch.sum)
+// Both are decided by the same approximate scores from the tensor cores plus an exact fp32 stage that evaluates the
+// recipe in the oracle's canonical order; only the exact stage and the candidate threshold differ.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRecipeExpanded = 0;
+constexpr int kRecipeDiffSq = 1;
+
+// Candidate threshold as a function of the (running or final) minimal score m:  thr(m) = fma(m, cmul, margin0).
+//   expanded: cmul = 1, margin0 = candidate_margin()  -- thr = m + margin, bit-identical to the plain add.
+//   diffsq:   with D_k the true squared distance, the canonical fp32 value d_k has |d_k - D_k| <= g D_k, g <= 69 * 2^-24
+//             (difference, square, 64 + 2 additions), and S_k = score_k + |x|^2 has |S_k - D_k| <= eps1,
+//             eps1 = (2^-9 + 2^-12) a + 2^-17.9 (|x|^2 + max|e|^2) + 2^-22 r  (operand rounding and tensor-core accumulation
+//             as above; the canonical norms' own rounding, 66 * 2^-24 relative, no longer cancels; score arithmetic).
+//             For k* = argmin d and j = argmin S:  D_k* (1-g) <= d_k* <= d_j <= (S_j + eps1)(1+g), hence
+//             score_k* <= score_j + 2 eps1 + c (score_j + |x|^2 + eps1) with c = 2^-16 >= ((1+g)/(1-g) - 1) -- every code that can
+//             be the exact argmin (or tie with it) satisfies it.
+__device__ __forceinline__ void candidate_threshold(int recipe, float z2, float e2max, float& cmul, float& margin0) {
+    if (recipe == kRecipeExpanded) {
+        cmul = 1.0f;
+        margin0 = candidate_margin(z2, e2max);
+        return;
+    }
+    const float a = sqrtf(z2) * sqrtf(e2max) * 1.000001f;
+    const float r = z2 + e2max + 2.0f * a;
+    const float eps1 = a * (0.001953125f + 0.000244140625f) + (z2 + e2max) * 4.1e-6f + r * 2.384185791015625e-07f;
+    const float c = 1.52587890625e-05f;                      // 2^-16
+    cmul = 1.0f + c;
+    margin0 = 2.0f * eps1 * 1.0625f + c * (z2 + eps1) * 1.0625f + 1e-37f;
+}
+
 }  // namespace vq

@@ -42,6 +42,7 @@ struct SelectParams {
     float beta;
     void* idx;                 // (N) int64 / int32 / uint16 according to idx_bits
     int idx_bits;
+    int recipe;                // kRecipeExpanded / kRecipeDiffSq
     float* zq;                 // (N, D) or null
     unsigned long long* hist;  // (K) or null
     double* loss_partial;      // (gridDim.x)
@@ -53,6 +54,8 @@ struct SelectParams {
 // One canonical partial sum of the dot product of latent row r (tile row) with code k: the terms d == j (mod 4) in
 // ascending d, one fma each (oracle/vq_oracle.c: vqo_dot).  Four lanes (j = 0..3) share a (row, code) pair; all 64
 // code-row loads of a lane are independent and issued in two batches of 32, so a pass costs two L2 round trips.
+// kDiffSq: the terms are fl(fl(z - e)^2) added one by one (v_vq_diffusion.py:121) instead of fused z * e products.
+template <bool kDiffSq>
 __device__ __forceinline__ float exact_partial_tile(const float* tile, int r, const float* __restrict__ E, int k, int j) {
     const float* e = E + (int64_t)k * kD + j;
     const int g = tile_swz(r);
@@ -67,7 +70,15 @@ __device__ __forceinline__ float exact_partial_tile(const float* tile, int r, co
 #pragma unroll
         for (int i = 0; i < 32; i++) ev[i] = __ldg(e + 4 * (32 * h + i));
 #pragma unroll
-        for (int i = 0; i < 32; i++) p = __fmaf_rn(zrow[32 * (4 * h + (i >> 3)) + zo[i & 7]], ev[i], p);
+        for (int i = 0; i < 32; i++) {
+            const float zv = zrow[32 * (4 * h + (i >> 3)) + zo[i & 7]];
+            if (kDiffSq) {
+                const float diff = __fsub_rn(zv, ev[i]);
+                p = __fadd_rn(p, __fmul_rn(diff, diff));
+            } else {
+                p = __fmaf_rn(zv, ev[i], p);
+            }
+        }
     }
     return p;
 }
@@ -222,11 +233,12 @@ vq_select_kernel(const SelectParams p) {
             if (k >= p.K) k = -1;                              // pad codes of the last chunk
             const int r = warp * 4 + rr;
             float pj = 0.0f;
-            if (k >= 0) pj = exact_partial_tile(tile, r, p.E, k, j);
+            if (k >= 0) pj = (p.recipe == kRecipeDiffSq) ? exact_partial_tile<true>(tile, r, p.E, k, j)
+                                                         : exact_partial_tile<false>(tile, r, p.E, k, j);
             const float dot = combine4(pj);                    // (p0 + p1) + (p2 + p3) on all four lanes
             const bool lead = (k >= 0) && (j == 0);
             uint32_t u = 0xffffffffu;
-            if (lead) u = dist_key(ref_distance(__ldg(p.z2 + n0 + r), __ldg(p.e2 + k), dot));
+            if (lead) u = dist_key(p.recipe == kRecipeDiffSq ? dot : ref_distance(__ldg(p.z2 + n0 + r), __ldg(p.e2 + k), dot));
 #pragma unroll
             for (int r2 = 0; r2 < 4; r2++) {
                 const bool mine = lead && (rr == r2);
@@ -344,6 +356,7 @@ struct FallbackParams {
     const int32_t* fb_count;
     int64_t HW;
     int K;
+    int recipe;                // kRecipeExpanded / kRecipeDiffSq
     int32_t* out_cnt;
     uint32_t* out_q;
     float4* part;              // (kFbMaxGroups * kFbGroup, parts) partial (distance, index, multiplicity) results
@@ -376,6 +389,7 @@ vq_fallback_kernel(const FallbackParams p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int count = __ldg(p.fb_count);
     if (count == 0) return;
+    const bool diffsq = p.recipe == kRecipeDiffSq;           // block-uniform
     const int groups = (count + kFbGroup - 1) / kFbGroup;
     // code blocks per group: fill the grid once; a multiple of kFbThreads codes each; never more than kFbMaxParts
     int parts = max(1, min(min(kFbMaxParts, (int)gridDim.x / groups), (p.K + kFbThreads - 1) / kFbThreads));
@@ -433,10 +447,19 @@ vq_fallback_kernel(const FallbackParams p) {
 #pragma unroll
                     for (int r = 0; r < kFbGroup; r++) {
                         const float4 zv = zr4[r][8 * db + j];
-                        acc[r][0] = __fmaf_rn(zv.x, e.x, acc[r][0]);
-                        acc[r][1] = __fmaf_rn(zv.y, e.y, acc[r][1]);
-                        acc[r][2] = __fmaf_rn(zv.z, e.z, acc[r][2]);
-                        acc[r][3] = __fmaf_rn(zv.w, e.w, acc[r][3]);
+                        if (diffsq) {
+                            const float dx = __fsub_rn(zv.x, e.x), dy = __fsub_rn(zv.y, e.y);
+                            const float dz = __fsub_rn(zv.z, e.z), dw = __fsub_rn(zv.w, e.w);
+                            acc[r][0] = __fadd_rn(acc[r][0], __fmul_rn(dx, dx));
+                            acc[r][1] = __fadd_rn(acc[r][1], __fmul_rn(dy, dy));
+                            acc[r][2] = __fadd_rn(acc[r][2], __fmul_rn(dz, dz));
+                            acc[r][3] = __fadd_rn(acc[r][3], __fmul_rn(dw, dw));
+                        } else {
+                            acc[r][0] = __fmaf_rn(zv.x, e.x, acc[r][0]);
+                            acc[r][1] = __fmaf_rn(zv.y, e.y, acc[r][1]);
+                            acc[r][2] = __fmaf_rn(zv.z, e.z, acc[r][2]);
+                            acc[r][3] = __fmaf_rn(zv.w, e.w, acc[r][3]);
+                        }
                     }
                 }
                 __syncwarp();
@@ -446,7 +469,7 @@ vq_fallback_kernel(const FallbackParams p) {
 #pragma unroll
                 for (int r = 0; r < kFbGroup; r++) {
                     const float dot = __fadd_rn(__fadd_rn(acc[r][0], acc[r][1]), __fadd_rn(acc[r][2], acc[r][3]));
-                    merge_min(best_d[r], best_k[r], n_at_min[r], dist_key(ref_distance(z2[r], e2k, dot)), k, 1);
+                    merge_min(best_d[r], best_k[r], n_at_min[r], dist_key(diffsq ? dot : ref_distance(z2[r], e2k, dot)), k, 1);
                 }
             }
         }

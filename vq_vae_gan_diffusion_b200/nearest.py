@@ -69,8 +69,14 @@ class CodeTable:
         _native.check(rc, "vq_prepare_codebook")
 
     @torch.no_grad()
-    def nearest(self, x: torch.Tensor, dtype=torch.int64) -> torch.Tensor:
-        """``argmin_k |x - table[k]|^2`` for every vector along the last axis of ``x`` -> indices of shape x.shape[:-1]."""
+    def nearest(self, x: torch.Tensor, dtype=torch.int64, recipe: str = "expanded") -> torch.Tensor:
+        """``argmin_k |x - table[k]|^2`` for every vector along the last axis of ``x`` -> indices of shape x.shape[:-1].
+
+        ``recipe`` names the reference's fp32 formula whose argmin (ties, rounding and all) is reproduced:
+        ``"expanded"`` = ``|x|^2 + |e|^2 - 2 x.e`` (codebook.py:70-79, diffusion_gaussian2d.py:334-339), ``"diffsq"`` =
+        ``sum((x - e)**2)`` (v_vq_diffusion.py:114-123)."""
+        if recipe not in _native.VQ_RECIPES:
+            raise ValueError(f"recipe must be one of {sorted(_native.VQ_RECIPES)}, got {recipe!r}")
         if x.shape[-1] != self.D:
             raise ValueError(f"last dimension {x.shape[-1]} != table width {self.D}")
         if not x.is_cuda or x.dtype != torch.float32 or x.device != self._E.device:
@@ -91,7 +97,8 @@ class CodeTable:
             self._ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             rc = _native.lib().vq_argmin_rows(xr.data_ptr(), N, _D, self._E.data_ptr(), self._E_h.data_ptr(),
-                                              self._e2.data_ptr(), self._cb.data_ptr(), self.K, idx.data_ptr(), bits,
+                                              self._e2.data_ptr(), self._cb.data_ptr(), self.K, _native.VQ_RECIPES[recipe],
+                                              idx.data_ptr(), bits,
                                               stats.data_ptr(), self._ws.data_ptr(), self._ws.numel(),
                                               int(torch.cuda.current_stream(dev).cuda_stream))
         _native.check(rc, "vq_argmin_rows")
@@ -99,6 +106,6 @@ class CodeTable:
         return idx.reshape(x.shape[:-1])
 
 
-def nearest_indices(x: torch.Tensor, table: torch.Tensor, dtype=torch.int64) -> torch.Tensor:
+def nearest_indices(x: torch.Tensor, table: torch.Tensor, dtype=torch.int64, recipe: str = "expanded") -> torch.Tensor:
     """One-shot form of :class:`CodeTable` (prepares the table on every call)."""
-    return CodeTable(table).nearest(x, dtype=dtype)
+    return CodeTable(table).nearest(x, dtype=dtype, recipe=recipe)
