@@ -274,6 +274,7 @@ def main():
     cb = vq.CodeBook(K, D, BETA).to(dev)
     with torch.no_grad():
         cb.codebook.weight.copy_(E)
+    cb.count_launches = True
     dp = DataParallelVQ(cb) if world > 1 else None
     z_req = z.clone().requires_grad_(not tok)
     g_loss = torch.ones((), device=dev)

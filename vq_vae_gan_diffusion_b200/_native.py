@@ -132,3 +132,16 @@ def workspace_bytes(N: int, K: int, D: int) -> int:
     out = _sz(0)
     check(lib().vq_workspace_bytes(int(N), int(K), int(D), ctypes.byref(out)), "vq_workspace_bytes")
     return int(out.value)
+
+
+_ws_cache = {}
+
+
+def workspace_bytes_cached(N: int, K: int, D: int) -> int:
+    key = (N, K, D)
+    v = _ws_cache.get(key)
+    if v is None:
+        if len(_ws_cache) > 256:
+            _ws_cache.clear()
+        v = _ws_cache[key] = workspace_bytes(N, K, D)
+    return v

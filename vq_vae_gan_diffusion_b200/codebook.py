@@ -37,6 +37,24 @@ def _ptr(t) -> int:
     return 0 if t is None else int(t.data_ptr())
 
 
+class _on_device:
+    """``torch.cuda.device(dev)`` only when ``dev`` is not already current (the context manager costs ~10 us of host
+    time, which is visible on the small, launch-bound shapes)."""
+
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev):
+        self.ctx = None if dev.index is None or dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
 class _Workspace:
     """Grow-only scratch buffer, one per (module, device)."""
 
@@ -58,20 +76,21 @@ class _VQFunction(torch.autograd.Function):
         K = weight.shape[0]
         dev = z.device
         zc = z.contiguous()                                  # NCHW; the kernels read it in place
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             E_h, e2, cb = module._derived(weight, force=refresh)
             zq = torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
             idx = torch.empty((B * H * W,), dtype=torch.int64, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             hist = torch.empty((K,), dtype=torch.int64, device=dev)
             stats = torch.empty((4,), dtype=torch.int64, device=dev)
-            nbytes = _native.workspace_bytes(B * H * W, K, D)
-            ws = module._workspace.get(nbytes, dev)
+            ws = module._workspace.get(_native.workspace_bytes_cached(B * H * W, K, D), dev)
             rc = _native.lib().vq_forward(_ptr(zc), B, H * W, D, _ptr(weight), _ptr(E_h), _ptr(e2), _ptr(cb), K,
                                           float(module.beta), _ptr(zq), _ptr(idx), _ptr(loss), _ptr(hist),
                                           _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr(dev))
-            _native.check(rc, "vq_forward")
-            module._launches = int(_native.lib().vq_last_launch_count())
+            if rc != 0:
+                _native.check(rc, "vq_forward")
+            if module.count_launches:
+                module._launches = int(_native.lib().vq_last_launch_count())
         module.last_histogram = hist
         module.last_stats = stats
         ctx.save_for_backward(zc, idx, weight)
@@ -103,15 +122,17 @@ class _VQFunction(torch.autograd.Function):
         g_loss_t = None
         if g_loss is not None:
             g_loss_t = g_loss.to(device=dev, dtype=torch.float32).contiguous()
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             grad_z = torch.empty((B, D, H, W), dtype=torch.float32, device=dev) if need_z else None
             grad_E = torch.empty((K, D), dtype=torch.float32, device=dev) if need_w else None
             n_global = B * H * W * int(module.grad_world_size)
             rc = _native.lib().vq_backward(_ptr(g_zq), strides, 0.0, _ptr(g_loss_t), _ptr(zc), _ptr(idx), _ptr(weight),
                                            B, H * W, D, K, float(module.beta), n_global, _ptr(grad_z), _ptr(grad_E),
                                            _stream_ptr(dev))
-            _native.check(rc, "vq_backward")
-            module._launches_bwd = int(_native.lib().vq_last_launch_count())
+            if rc != 0:
+                _native.check(rc, "vq_backward")
+            if module.count_launches:
+                module._launches_bwd = int(_native.lib().vq_last_launch_count())
         if grad_E is not None and module.grad_hook is not None:
             grad_E = module.grad_hook(grad_E)
         return grad_z, grad_E, None, None
@@ -144,6 +165,7 @@ class CodeBook(nn.Module):
         self._workspace = _Workspace()
         self._launches = 0
         self._launches_bwd = 0
+        self.count_launches = False      # bench.py: record how many kernels each call enqueued
         # data-parallel plumbing (see dist.py): loss mean runs over N_local * grad_world_size latents
         self.grad_world_size = 1
         self.grad_hook = None
@@ -222,19 +244,21 @@ class CodeBook(nn.Module):
         K = weight.shape[0]
         dev = z.device
         zc = z.contiguous()
-        with torch.cuda.device(dev):
+        with _on_device(dev):
             E_h, e2, cb = self._derived(weight)
             idx = torch.empty((B * H * W,), dtype=dtype, device=dev)
             stats = torch.empty((4,), dtype=torch.int64, device=dev)
-            ws = self._workspace.get(_native.workspace_bytes(B * H * W, K, D), dev)
+            ws = self._workspace.get(_native.workspace_bytes_cached(B * H * W, K, D), dev)
             if bits == 64:
                 rc = _native.lib().vq_argmin(_ptr(zc), B, H * W, D, _ptr(weight), _ptr(E_h), _ptr(e2), _ptr(cb), K,
                                              _ptr(idx), _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr(dev))
             else:
                 rc = _native.lib().vq_argmin_narrow(_ptr(zc), B, H * W, D, _ptr(weight), _ptr(E_h), _ptr(e2), _ptr(cb), K,
                                                     _ptr(idx), bits, _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr(dev))
-            _native.check(rc, "vq_argmin")
-            self._launches = int(_native.lib().vq_last_launch_count())
+            if rc != 0:
+                _native.check(rc, "vq_argmin")
+            if self.count_launches:
+                self._launches = int(_native.lib().vq_last_launch_count())
         self.last_stats = stats
         return idx
 
