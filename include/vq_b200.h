@@ -33,7 +33,7 @@ typedef struct CUstream_st* vq_stream_t; /* == cudaStream_t */
 #define VQ_E_INVALID     -1   /* bad argument (null pointer, negative size, misaligned pointer) */
 #define VQ_E_UNSUPPORTED -2   /* D != 256, K < 1, ... */
 #define VQ_E_WORKSPACE   -3   /* workspace too small */
-#define VQ_E_DEVICE      -4   /* current device is not sm_100 / driver entry point missing */
+#define VQ_E_DEVICE      -4   /* current device is not sm_100 */
 
 /* stats[] slots written by vq_argmin / vq_forward (uint64 each, overwritten) */
 #define VQ_STAT_TIE_ROWS      0  /* rows whose minimal fp32 distance is attained by >= 2 codes */

@@ -72,10 +72,3 @@ def assert_close(a, b, what: str, rtol: float = FLOAT_RTOL):
     assert err <= rtol, f"{what}: max-norm relative error {err:.3e} > {rtol:.1e}"
     assert np.allclose(a, b, rtol=rtol, atol=1e-7 * max(scale, 1e-30) + 1e-37), f"{what}: elementwise allclose failed"
     return err
-
-
-def substitute_rows(arr_rows: np.ndarray, rows_bad: np.ndarray):
-    """Mask helper: floats are compared on rows where the indices agree (SURVEY 8(c) rule 2)."""
-    keep = np.ones(arr_rows.shape[0], bool)
-    keep[rows_bad] = False
-    return keep

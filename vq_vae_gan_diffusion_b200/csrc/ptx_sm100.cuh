@@ -1,4 +1,4 @@
-// ptx_sm100.cuh -- thin inline-PTX wrappers for sm_100a: mbarrier, TMA, tcgen05 (MMA / TMEM / commit).
+// ptx_sm100.cuh -- thin inline-PTX wrappers for sm_100a: mbarrier, bulk async copies, clusters, tcgen05 (MMA / TMEM / commit).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -50,9 +50,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void fence_mbar_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
@@ -88,25 +85,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// ---------------------------------------------------------------- TMA
-__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
-}
-// 2-D tiled load, completion signalled on an mbarrier of this CTA.
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* tmap, int32_t c0, int32_t c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const void* tmap, int32_t c0, int32_t c1,
-                                                 uint64_t* bar, uint64_t policy) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
-        : "memory");
-}
+// ---------------------------------------------------------------- bulk async copies (TMA engine, no tensor map)
 // 1-D bulk copy global -> shared (size multiple of 16 B, both sides 16-B aligned), completion on an mbarrier.
 __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"

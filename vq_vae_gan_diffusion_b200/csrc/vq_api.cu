@@ -1,9 +1,8 @@
 // vq_api.cu -- C-ABI entry points of libvq_b200.so (declared in include/vq_b200.h).
 //
-// Host side only: argument checks, workspace carving, TMA descriptor encoding and kernel launches.  Nothing here
+// Host side only: argument checks, workspace carving and kernel launches.  Nothing here
 // allocates device memory or synchronises; every launch goes to the caller's stream.  There is no CPU fallback:
 // on anything but an sm_100 device the compute entry points return VQ_E_DEVICE.
-#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdarg>
@@ -369,7 +368,7 @@ static int forward_impl(bool training, bool rows, int recipe, const float* z, in
     rc = run_gemm(z, N, HW, rows, recipe, E_h, e2, cb, K, w, nullptr, training ? hist : nullptr, stats, st);
     if (rc != VQ_OK) return rc;
 
-    {   // rows whose candidate list overflowed (rare): exact scan, one CTA per row; a no-op when the worklist is empty
+    {   // rows whose candidate list overflowed (rare) or that hold Inf / NaN: exact scan; a no-op when the worklist is empty
         vq::FallbackParams fp;
         fp.z = z; fp.E = E; fp.e2 = e2; fp.z2 = w.z2;
         fp.fb_rows = w.fb_rows; fp.fb_count = w.fb_count;

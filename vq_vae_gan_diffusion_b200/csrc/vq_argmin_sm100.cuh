@@ -33,7 +33,6 @@
 //               only while drain + hand-off latency <= one MMA tile time; splitting the columns over two warps per
 //               SM sub-partition halves the drain and lets the two hide each other's latencies.
 #pragma once
-#include <cuda.h>
 
 #include "ptx_sm100.cuh"
 #include "vq_common.cuh"

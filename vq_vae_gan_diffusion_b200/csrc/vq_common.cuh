@@ -12,7 +12,6 @@ constexpr int kRowTile = 128;       // latents per GEMM tile  (UMMA M, one TMEM 
 constexpr int kCodeTile = 256;      // codes per GEMM tile    (UMMA N)
 constexpr int kDChunk = 64;         // 16-bit elements per 128-byte swizzle row
 constexpr int kNumDChunks = kD / kDChunk;
-constexpr int kQuad = 4;            // candidate granularity: 4 consecutive codes
 constexpr int kRingCap = 8;      // candidate ring per (row, epilogue group) in shared memory inside the GEMM epilogue
 constexpr int kOutCap = 16;         // surviving candidate quads handed to the exact stage, per row (half per group)
 constexpr int kSelRows = 32;        // latents per CTA in the fp32 kernels (prep / select / backward)
@@ -27,46 +26,6 @@ __device__ __forceinline__ int exponent_of(float maxabs) {
     return max(-100, min(100, ex));
 }
 __device__ __forceinline__ float pow2f(int e) { return __int_as_float((e + 127) << 23); }   // -126 <= e <= 127
-
-// ---------------------------------------------------------------------------------------------------------------
-// [kD x 32] fp32 tiles of NCHW latents <-> shared memory t[d][row] (row stride 33 words: conflict-free for lanes
-// over rows AND for lanes over d).  256 threads.  kVec (HW % 32 == 0: the 32 latents of a tile are 32 consecutive,
-// 128-byte aligned hw positions of one batch item) moves 16 bytes per thread per request -- lane = (d mod 4, group of
-// 4 rows), so a warp request covers four full 128-byte lines -- and keeps 8 requests (128 B) per thread in flight,
-// which is what an HBM-bound kernel needs to cover DRAM latency.  The generic path handles any HW (e.g. HW = 1).
-// ---------------------------------------------------------------------------------------------------------------
-using TileRow = float[kSelRows + 1];
-
-template <bool kVec, bool kStreaming>
-__device__ __forceinline__ void load_tile_nchw(TileRow* t, const float* __restrict__ x, int64_t n0, int64_t N, int64_t HW,
-                                               int warp, int lane) {
-    if (kVec) {
-        const int64_t b = n0 / HW, hw0 = n0 % HW;
-        const int dsub = lane >> 3, hq = lane & 7;
-        const float* src = x + (b * kD + dsub) * HW + hw0 + 4 * hq;
-        float4 v[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const float4* ptr = reinterpret_cast<const float4*>(src + (int64_t)((warp * 8 + i) * 4) * HW);
-            v[i] = kStreaming ? __ldcs(ptr) : __ldg(ptr);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            float* dst = &t[(warp * 8 + i) * 4 + dsub][4 * hq];
-            dst[0] = v[i].x; dst[1] = v[i].y; dst[2] = v[i].z; dst[3] = v[i].w;
-        }
-    } else {
-        const int64_t n = n0 + lane;
-        const bool ok = n < N;
-        const int64_t b = ok ? n / HW : 0, hw = ok ? n % HW : 0;
-        const float* src = x + (b * kD) * HW + hw;
-#pragma unroll 8
-        for (int i = 0; i < kD / 8; i++) {
-            const int d = warp + 8 * i;
-            t[d][lane] = ok ? (kStreaming ? __ldcs(src + (int64_t)d * HW) : __ldg(src + (int64_t)d * HW)) : 0.0f;
-        }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Row-major [32 latents x 256] fp32 tile in shared memory with the 16-byte pieces of row r XOR-swizzled by

@@ -1,19 +1,21 @@
 // vq_select.cuh -- exact fp32 decision + fused forward tail, and the exact full-row fallback.
 //
-// vq_select_kernel<kForward>: one CTA = 32 latents (8 warps, 4 rows per warp).
-//   1. expand the candidate entries, then load the fp32 z tile once (16-byte loads along hw) into shared memory
-//      (skipped in tokeniser mode when every row of the CTA has a single candidate)
-//   2. expand the candidate entries (32-code chunk + quad mask) written by the GEMM epilogue into quads, then
-//      recompute the distance of every candidate code with the reference's fp32 formula (codebook.py:70-79) in
-//      the oracle's canonical accumulation order -- one thread per (row, code): a warp pass covers 4 rows x 8 codes,
-//      each thread streaming its code row with 128-bit loads into the four canonical partial sums -- and take the
-//      first minimum (torch.argmin semantics, codebook.py:82)
+// vq_select_kernel<kForward, kLayout>: one CTA = 32 latents (8 warps, 4 rows per warp), tile in shared memory row-major
+// with swizzled 16-byte pieces (vq_common.cuh tile_off).
+//   1. forward mode: the fp32 z tile's global loads are issued first (16-byte loads along hw / along d for row-major
+//      input); tokeniser mode loads it only when some row of the CTA has more than one candidate
+//   2. expand the candidate entries (32-code chunk + code mask) written by the GEMM epilogue -- counts and entries are
+//      fetched together, one round trip --, then evaluate every candidate of the rows that need a decision with the
+//      reference's fp32 formula in the oracle's canonical accumulation order: the warp's candidates are pooled, four
+//      lanes share a (row, code) pair, each lane one canonical partial sum with all its 64 code-row loads independent;
+//      first minimum by torch.argmin's rules (NaN is the minimum; lowest index on ties) with redux.sync on distance keys
 //   3. kForward only: gather e = E[idx] (codebook.py:85), write z_q = fl(z + fl(e - z)) as NHWC rows
-//      (codebook.py:106-109), accumulate sum (e - z)^2 for the loss (codebook.py:96-103) and the usage histogram.
-// HBM traffic per latent: read z 4D (+ 72 B of candidates), write idx 8 (+ z_q 4D when kForward).
+//      (codebook.py:106-109), accumulate sum (e - z)^2 for the loss (codebook.py:96-103) and the usage histogram;
+//      16 bytes per lane and request throughout.
+// HBM traffic per latent: read z 4D (+ candidates), write idx 8 (+ z_q 4D when kForward).
 //
-// vq_fallback_kernel: the (rare) rows whose candidate ring overflowed in the GEMM epilogue get an exact scan of the
-// whole codebook, one 1024-thread CTA per row, one thread per code; the winner is written back as a one-quad
+// vq_fallback_kernel: the (rare) rows whose candidate ring overflowed in the GEMM epilogue, and rows / codebooks with
+// Inf or NaN, get an exact scan of the whole codebook (see the kernel); the winner is written back as a one-code
 // candidate entry so vq_select_kernel finishes the row like any other.
 #pragma once
 #include "vq_common.cuh"
