@@ -38,6 +38,37 @@ __device__ __forceinline__ int tile_off(int r, int d) {                    // wo
     return r * kD + ((((d >> 2) ^ tile_swz(r)) << 2) | (d & 3));
 }
 
+// Column-form side of the tile (NCHW, HW % 32 == 0): thread (warp, lane) handles the latents 4 hq .. 4 hq + 3 (hq = lane & 7)
+// at d = 4 (8 warp + i) + dsub (dsub = lane >> 3) for i = 0 .. 7 -- one 16-byte global access along hw per i, a warp
+// request covering four full 128-byte lines.  ColForm precomputes everything that does not depend on i, so that a
+// shared-memory access costs one LOP3 and one add on top of the LDS / STS (the kernels are issue-bound otherwise).
+struct ColForm {
+    int base[4];      // word offset of (row 4 hq + c, d = 32 warp + dsub) with the piece index zeroed
+    int gx[4];        // swizzle of row 4 hq + c, pre-shifted to word units (<< 2)
+    __device__ __forceinline__ ColForm(int warp, int lane) {
+        const int hq = lane & 7, dsub = lane >> 3;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const int r = 4 * hq + c;
+            base[c] = r * kD + warp * 32 + dsub;
+            gx[c] = tile_swz(r) << 2;
+        }
+    }
+    __device__ __forceinline__ int off(int c, int i) const { return base[c] + ((i << 2) ^ gx[c]); }   // i in [0, 8)
+    __device__ __forceinline__ void store(float* tile, int i, const float4& v) const {
+        tile[off(0, i)] = v.x; tile[off(1, i)] = v.y; tile[off(2, i)] = v.z; tile[off(3, i)] = v.w;
+    }
+    __device__ __forceinline__ float4 load(const float* tile, int i) const {
+        return make_float4(tile[off(0, i)], tile[off(1, i)], tile[off(2, i)], tile[off(3, i)]);
+    }
+};
+// element offset of this thread's first column-form access (i = 0) in an NCHW tensor with `HW` positions per channel
+// plane; access i is (4 i) channel planes further.  (N < 2^31 is enforced by the API: 32-bit division.)
+__device__ __forceinline__ int64_t col_form_origin(int64_t n0, int64_t HW, int warp, int lane) {
+    const uint32_t b = (uint32_t)n0 / (uint32_t)HW, hw0 = (uint32_t)n0 % (uint32_t)HW;
+    return ((int64_t)b * kD + warp * 32 + (lane >> 3)) * HW + hw0 + 4 * (lane & 7);
+}
+
 // Input layouts of the latent tensor, as seen by the tile kernels.
 constexpr int kLayoutGeneric = 0;   // NCHW (B, D, HW), any HW: lanes over latents, scalar accesses
 constexpr int kLayoutVec = 1;       // NCHW with HW % 32 == 0 and 16-byte aligned base: 16-byte accesses along hw

@@ -61,20 +61,13 @@ vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_p
     if (kLayout == kLayoutRows) {
         fill_tile_rows(tile, z, n0, N, warp, lane);
     } else if (kLayout == kLayoutVec) {
-        const int dsub = lane >> 3, hq = lane & 7;
-        const int64_t b = n0 / HW, hw0 = n0 % HW;
-        const float* src = z + (b * kD + dsub) * HW + hw0 + 4 * hq;
+        const ColForm cf(warp, lane);
+        const float* src = z + col_form_origin(n0, HW, warp, lane);
         float4 v[8];
 #pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)((warp * 8 + i) * 4) * HW));
+        for (int i = 0; i < 8; i++) v[i] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)(4 * i) * HW));
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int d = (warp * 8 + i) * 4 + dsub;
-            tile[tile_off(4 * hq + 0, d)] = v[i].x;
-            tile[tile_off(4 * hq + 1, d)] = v[i].y;
-            tile[tile_off(4 * hq + 2, d)] = v[i].z;
-            tile[tile_off(4 * hq + 3, d)] = v[i].w;
-        }
+        for (int i = 0; i < 8; i++) cf.store(tile, i, v[i]);
     } else {
         const int64_t n = n0 + lane;
         const bool ok = n < N;
@@ -96,11 +89,14 @@ vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_p
         const int r = warp * 4 + rr;
         const float* zrow = tile + r * kD + j;
         const int g = tile_swz(r);
+        int zo[8];
+#pragma unroll
+        for (int b = 0; b < 8; b++) zo[b] = (b ^ g) << 2;
         float p = 0.0f, mx = 0.0f;
         if (lane < 16) {
-#pragma unroll 16
+#pragma unroll
             for (int q = 0; q < kD / 4; q++) {
-                const float v = zrow[(q ^ g) << 2];
+                const float v = zrow[32 * (q >> 3) + zo[q & 7]];
                 p = __fmaf_rn(v, v, p);
                 mx = fmaxf(mx, fabsf(v));
             }
@@ -117,6 +113,9 @@ vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_p
     // stores per row; lanes 0..15 / 16..31 of a store cover one full 128-byte row of two D chunks of the operand image
     // ([row tile][64-wide D chunk][128 rows][128 B], 16-byte pieces XOR-swizzled by (row & 7): the exact shared-memory
     // image of a SWIZZLE_128B K-major UMMA operand, so the GEMM loads a chunk with ONE contiguous bulk copy)
+    // (lane part of the operand-image offset: D chunk (lane >> 4) + 2 h, piece (lane & 15) >> 1, low half 4 (lane & 1))
+    const int img_lane = (lane >> 4) * (kRowTile * kDChunk) + 4 * (lane & 1);
+    const int img_piece = (lane & 15) >> 1;
 #pragma unroll
     for (int rr = 0; rr < 4; rr++) {
         const int r = warp * 4 + rr;
@@ -125,18 +124,17 @@ vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_p
         if (n >= n_pad) continue;                            // warp-uniform
         const float4* zrow4 = reinterpret_cast<const float4*>(tile + r * kD);
         const int g = tile_swz(r);
-        const int64_t rt = n / kRowTile;
-        const int rr_t = (int)(n % kRowTile);
+        const int rr_t = (int)((uint32_t)n % kRowTile);
+        __half* row_img = z_h + ((int64_t)((uint32_t)n / kRowTile) * kNumDChunks) * (kRowTile * kDChunk) + rr_t * kDChunk + img_lane +
+                          ((img_piece ^ (rr_t & 7)) << 3);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-            const int q = lane + 32 * h;                     // d = 4q .. 4q + 3
-            const float4 v = zrow4[q ^ g];
-            const int d = 4 * q;
+            const float4 v = zrow4[(lane + 32 * h) ^ g];     // d = 4 (lane + 32 h) .. + 3
             __half2 lo = __floats2half2_rn(v.x * sc, v.y * sc), hi = __floats2half2_rn(v.z * sc, v.w * sc);
             uint2 pk;
             pk.x = *reinterpret_cast<uint32_t*>(&lo);
             pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(z_h + operand_image_offset(rt * kNumDChunks + d / kDChunk, kRowTile, rr_t, d % kDChunk)) = pk;
+            *reinterpret_cast<uint2*>(row_img + h * 2 * (kRowTile * kDChunk)) = pk;
         }
     }
 }

@@ -176,19 +176,13 @@ vq_select_kernel(const SelectParams p) {
             fill_tile_rows(tile, p.z, n0, p.N, warp, lane);
         } else if (kVec) {
             if (!kForward) {
-                const int64_t b = n0 / p.HW, hw0 = n0 % p.HW;
-                const float* src = p.z + (b * kD + dsub) * p.HW + hw0 + 4 * hq;
+                const float* src = p.z + col_form_origin(n0, p.HW, warp, lane);
 #pragma unroll
-                for (int i = 0; i < 8; i++) zreg[i] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)((warp * 8 + i) * 4) * p.HW));
+                for (int i = 0; i < 8; i++) zreg[i] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)(4 * i) * p.HW));
             }
+            const ColForm cf(warp, lane);
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int d = (warp * 8 + i) * 4 + dsub;
-                tile[tile_off(4 * hq + 0, d)] = zreg[i].x;
-                tile[tile_off(4 * hq + 1, d)] = zreg[i].y;
-                tile[tile_off(4 * hq + 2, d)] = zreg[i].z;
-                tile[tile_off(4 * hq + 3, d)] = zreg[i].w;
-            }
+            for (int i = 0; i < 8; i++) cf.store(tile, i, zreg[i]);
         } else {
             const int64_t n = n0 + lane;
             const bool ok = n < p.N;
