@@ -39,7 +39,8 @@ typedef struct CUstream_st* vq_stream_t; /* == cudaStream_t */
 #define VQ_STAT_TIE_ROWS      0  /* rows whose minimal fp32 distance is attained by >= 2 codes */
 #define VQ_STAT_RERANK_ROWS   1  /* rows that needed the exact-fp32 re-rank (>= 2 candidates within the margin) */
 #define VQ_STAT_FALLBACK_ROWS 2  /* rows resolved by the full fp32 row scan (candidate list overflow) */
-#define VQ_STAT_CANDIDATES    3  /* total candidates that survived the margin filter */
+#define VQ_STAT_CANDIDATES    3  /* candidates that survived the margin filter, summed over the rows the exact stage
+                                    decided (rows resolved by the full scan are counted in FALLBACK_ROWS only) */
 #define VQ_STAT_COUNT         4
 
 /* fp32 distance recipes of the reference's nearest-code searches (vq_argmin_rows) */

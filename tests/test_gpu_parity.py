@@ -633,3 +633,38 @@ def test_diffsq_large_and_fallback(vq, oracle):
     assert (idx[7:12] == 40).all()
     st = dict(zip(vq._native.VQ_STAT_NAMES, tab.last_stats.tolist()))
     assert st["fallback_rows"] >= 7 and st["tie_rows"] == ref["tie_rows"]
+
+
+@pytest.mark.parametrize("D,K", [(64, 300), (96, 1000), (128, 64), (3, 5)])
+def test_narrow_latent_dim_runs_zero_padded(D, K, vq, oracle):
+    """latent_dim < 256 (not used by any reference config, but a legal constructor argument, codebook.py:30-32): the module
+    zero-pads to the kernels' 256 channels.  Everything must equal the oracle evaluated at the NATIVE width."""
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(500 + D)
+    B, H, W = 2, 8, 8
+    E = rng.standard_normal((K, D)).astype(np.float32)
+    z = (E[rng.integers(0, K, B * H * W)] + 0.4 * rng.standard_normal((B * H * W, D)).astype(np.float32))
+    z = np.ascontiguousarray(z.reshape(B, H, W, D).transpose(0, 3, 1, 2))
+    g = rng.standard_normal((B, H, W, D)).astype(np.float32)
+    cb = vq.CodeBook(K, D).to(dev)
+    assert cb.codebook.weight.shape == (K, D)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(torch.from_numpy(E))
+    zt = torch.from_numpy(z).to(dev).requires_grad_(True)
+    z_q, idx, loss = cb(zt)
+    assert z_q.shape == (B, D, H, W) and z_q.stride() == (H * W * D, 1, W * D, D)
+    gt = torch.from_numpy(g).to(dev).permute(0, 3, 1, 2)
+    (loss + (z_q * gt).sum()).backward()
+    ref = oracle.forward(z, E)
+    assert np.array_equal(idx.cpu().numpy(), ref["idx"])
+    assert np.array_equal(cb.last_histogram.cpu().numpy(), ref["hist"])
+    assert np.array_equal(z_q.detach().permute(0, 2, 3, 1).reshape(-1, D).cpu().numpy(), ref["zq_nhwc"])
+    assert abs(float(loss.detach()) - float(ref["loss"])) <= 1e-6 * float(ref["loss"])
+    gz, gE = oracle.backward(np.transpose(g, (0, 3, 1, 2)), 1.0, z, ref["idx"], E)
+    assert zt.grad.shape == (B, D, H, W) and cb.codebook.weight.grad.shape == (K, D)
+    assert_close(zt.grad.cpu().numpy(), gz, "grad_z")
+    assert_close(cb.codebook.weight.grad.cpu().numpy(), gE, "grad_E")
+    with torch.no_grad():
+        assert np.array_equal(cb.encode_indices(zt.detach()).cpu().numpy(), ref["idx"])
+    with pytest.raises(ValueError):
+        vq.CodeBook(16, 512).to(dev)(torch.zeros(1, 512, 2, 2, device=dev))

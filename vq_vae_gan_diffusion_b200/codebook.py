@@ -9,7 +9,8 @@ kernels behind the C-ABI of ``include/vq_b200.h``; PyTorch only owns memory, str
 There is no CPU or eager fallback: a CPU tensor, a missing library or a non-sm_100 device raises.
 
 Stricter than the reference on purpose (documented in DESIGN.md): inputs must be CUDA fp32 of rank 4 with
-``C == latent_dim == 256``; the reference silently re-chunks rows when ``C != latent_dim`` (codebook.py:64-66).
+``C == latent_dim <= 256``; the reference silently re-chunks rows when ``C != latent_dim`` (codebook.py:64-66).
+The kernels are specialised for 256 channels (every reference config); narrower codebooks run zero-padded (exact).
 
 Extras that do not change the 3-tuple: ``last_histogram`` (codebook usage, ``bincount(indices, K)``),
 ``last_stats`` (tie / re-rank / fallback row counts) and the keyword-only ``indices_only=True`` fast path used by
@@ -27,6 +28,7 @@ from . import _native
 __all__ = ["CodeBook", "vq_embed_nchw"]
 
 _DERIVED_ATTRS = ("_E_h", "_e2", "_cb", "_derived_key")
+_KERNEL_D = 256          # channel width the kernels are specialised for (latent_dim of every reference config)
 
 
 def _stream_ptr(device) -> int:
@@ -210,6 +212,8 @@ class CodeBook(nn.Module):
             raise RuntimeError(f"CodeBook expects float32 latents, got {z.dtype}")
         if z.shape[1] != self.latent_dim:
             raise ValueError(f"channel dimension {z.shape[1]} != latent_dim {self.latent_dim}")
+        if self.latent_dim > _KERNEL_D:
+            raise ValueError(f"latent_dim {self.latent_dim} > {_KERNEL_D} is not supported by the sm_100a kernels")
         w = self.codebook.weight
         if w.device != z.device:
             raise RuntimeError(f"codebook weight on {w.device}, input on {z.device}")
@@ -228,7 +232,19 @@ class CodeBook(nn.Module):
             return None, self.encode_indices(z), None
         weight = self.codebook.weight
         # (grad mode is off inside autograd.Function.forward, so "is the codebook being trained" is decided here)
-        return _VQFunction.apply(z, weight, self, weight.requires_grad and torch.is_grad_enabled())
+        refresh = weight.requires_grad and torch.is_grad_enabled()
+        if self.latent_dim == _KERNEL_D:
+            return _VQFunction.apply(z, weight, self, refresh)
+        # Narrower latents run zero-padded to the kernels' 256 channels.  Exact: a zero channel adds fma(0, 0, p) == p to
+        # every norm and dot product, 0 to (e - z)^2 and to every gradient; only the means run over 256 / D times too
+        # many elements, which the factor below undoes (a power of two for D = 32, 64, 128: bit-exact).  Costs 256 / D
+        # times the memory traffic and FLOPs of a native kernel -- a compatibility path, every reference config is 256.
+        pad = _KERNEL_D - self.latent_dim
+        zp = torch.nn.functional.pad(z, (0, 0, 0, 0, 0, pad))
+        wp = torch.nn.functional.pad(weight, (0, pad))
+        zq_p, idx, loss_p = _VQFunction.apply(zp, wp, self, True)
+        z_q = zq_p.permute(0, 2, 3, 1)[..., : self.latent_dim].contiguous().permute(0, 3, 1, 2)   # strides of codebook.py:109
+        return z_q, idx, loss_p * (_KERNEL_D / self.latent_dim)
 
     @torch.no_grad()
     def encode_indices(self, z: torch.Tensor, dtype=torch.int64) -> torch.Tensor:
@@ -239,13 +255,20 @@ class CodeBook(nn.Module):
         from .nearest import _index_bits
         self._check_input(z)
         bits = _index_bits(dtype, self.codebook.weight.shape[0])
+        if self.latent_dim != _KERNEL_D:                     # zero-padded compatibility path (see forward)
+            pad = _KERNEL_D - self.latent_dim
+            z = torch.nn.functional.pad(z, (0, 0, 0, 0, 0, pad))
+            weight_p = torch.nn.functional.pad(self.codebook.weight.detach(), (0, pad))
+            return self._encode_indices_256(z, weight_p, dtype, bits, force=True)
+        return self._encode_indices_256(z, self.codebook.weight, dtype, bits, force=False)
+
+    def _encode_indices_256(self, z, weight, dtype, bits, force):
         B, D, H, W = z.shape
-        weight = self.codebook.weight
         K = weight.shape[0]
         dev = z.device
         zc = z.contiguous()
         with _on_device(dev):
-            E_h, e2, cb = self._derived(weight)
+            E_h, e2, cb = self._derived(weight, force=force)
             idx = torch.empty((B * H * W,), dtype=dtype, device=dev)
             stats = torch.empty((4,), dtype=torch.int64, device=dev)
             ws = self._workspace.get(_native.workspace_bytes_cached(B * H * W, K, D), dev)

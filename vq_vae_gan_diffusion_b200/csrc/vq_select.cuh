@@ -529,7 +529,6 @@ vq_fallback_kernel(const FallbackParams p) {
                 if (p.stats != nullptr) {
                     if (cnt > 1) atomicAdd(p.stats + 0, 1ull);
                     atomicAdd(p.stats + 2, 1ull);
-                    atomicAdd(p.stats + 3, (unsigned long long)p.K);
                 }
             }
         }
