@@ -420,7 +420,7 @@ def main():
         roofline["hbm_peak_gbs"] = peaks["hbm_gbs"]
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:              # reported at N=1 only (tier contract)
         sample = 16384 if K >= 8192 else min(N, 65536)
         v, tbest, n, reps = time_cpu_port(wl, args.distribution, sample, budget_s=12.0)
         cpu_baseline = {"value": v, "unit": "latents/s", "cores": os.cpu_count(), "kind": "port",

@@ -23,6 +23,9 @@
 namespace vq {
 
 constexpr int kSelThreads = 256;
+#ifndef VQ_SEL_MIN_BLOCKS
+#define VQ_SEL_MIN_BLOCKS 4               // resident CTAs per SM the register allocation is tuned for
+#endif
 constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kMaxCands = 64;           // codes per row the exact stage evaluates (GEMM hands over <= 32 per group)
 constexpr int kFbThreads = 256;
@@ -95,7 +98,7 @@ __device__ __forceinline__ uint32_t dist_key(float d) {
 }
 
 template <bool kForward, int kLayout>
-__global__ void __launch_bounds__(kSelThreads, 4)
+__global__ void __launch_bounds__(kSelThreads, VQ_SEL_MIN_BLOCKS)
 vq_select_kernel(const SelectParams p) {
     __shared__ __align__(16) float tile[kSelRows * kD];       // 32 KiB, swizzled row-major (vq_common.cuh tile_off)
     __shared__ int clist[kSelWarps][4][kMaxCands];            // candidate codes of each row of each warp
