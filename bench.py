@@ -260,6 +260,10 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    if local_rank == 0:
+        _native.build()                                      # no-op when the in-tree library is up to date
+    if world > 1:
+        dist.barrier()
     _native.check(_native.lib().vq_device_check(), "vq_device_check")
 
     wl = WORKLOADS[args.workload]

@@ -26,6 +26,7 @@ def vq():
     if not torch.cuda.is_available():
         pytest.skip("no CUDA device")
     import vq_vae_gan_diffusion_b200 as m
+    m.build()                                                # no-op when lib/libvq_b200.so is up to date (it travels with the tree)
     assert os.path.exists(m._native.LIB_PATH), "libvq_b200.so must be built in-tree (no fallback)"
     m._native.check(m._native.lib().vq_device_check(), "vq_device_check")
     assert torch.backends.cuda.matmul.allow_tf32 is False

@@ -34,15 +34,30 @@ def _sources():
     return sorted(os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cu", ".cuh"))) + [HEADER_PATH]
 
 
+def _source_digest() -> str:
+    """Content hash of everything the library is built from (the tree is copied between machines, so file times say
+    nothing about whether lib/libvq_b200.so matches the sources)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in _sources():
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/vq_api.cu (which includes every kernel) into lib/libvq_b200.so.  Cross-compiles without a GPU."""
-    srcs = _sources()
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+    """Compile csrc/vq_api.cu (which includes every kernel) into lib/libvq_b200.so.  Cross-compiles without a GPU.
+    A no-op when the library was built from the current sources (content hash in lib/libvq_b200.so.src)."""
+    digest = _source_digest()
+    stamp = LIB_PATH + ".src"
+    if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB_PATH
     os.makedirs(_LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
-    cmd = [nvcc, *NVCC_FLAGS, "-ccbin", ccbin, "-o", LIB_PATH + ".tmp", os.path.join(_CSRC, "vq_api.cu")]
+    tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+    cmd = [nvcc, *NVCC_FLAGS, "-ccbin", ccbin, "-o", tmp, os.path.join(_CSRC, "vq_api.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
@@ -50,7 +65,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise VQNativeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    os.replace(LIB_PATH + ".tmp", LIB_PATH)
+    os.replace(tmp, LIB_PATH)
+    with open(stamp + ".tmp", "w") as f:
+        f.write(digest + "\n")
+    os.replace(stamp + ".tmp", stamp)
     return LIB_PATH
 
 
