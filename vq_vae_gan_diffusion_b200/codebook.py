@@ -32,7 +32,12 @@ _KERNEL_D = 256          # channel width the kernels are specialised for (latent
 
 
 def _stream_ptr(device) -> int:
-    return int(torch.cuda.current_stream(device).cuda_stream)
+    """Raw cudaStream_t of the current stream (the fast private accessor when this torch build has it)."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    try:
+        return int(torch._C._cuda_getCurrentRawStream(idx))
+    except AttributeError:                                   # pragma: no cover
+        return int(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _ptr(t) -> int:
@@ -93,8 +98,8 @@ class _VQFunction(torch.autograd.Function):
                 _native.check(rc, "vq_forward")
             if module.count_launches:
                 module._launches = int(_native.lib().vq_last_launch_count())
-        module.last_histogram = hist
-        module.last_stats = stats
+        object.__setattr__(module, "last_histogram", hist)   # (plain tensors: skip nn.Module.__setattr__'s bookkeeping)
+        object.__setattr__(module, "last_stats", stats)
         ctx.save_for_backward(zc, idx, weight)
         ctx.module = module
         ctx.shape = (B, D, H, W)
@@ -282,7 +287,7 @@ class CodeBook(nn.Module):
                 _native.check(rc, "vq_argmin")
             if self.count_launches:
                 self._launches = int(_native.lib().vq_last_launch_count())
-        self.last_stats = stats
+        object.__setattr__(self, "last_stats", stats)
         return idx
 
     def stats_dict(self):
