@@ -2,16 +2,16 @@
 //
 // Computes, for every latent row n, the approximate scores  s[n,k] = |e_k|^2 - 2 * fp16(z_n) . fp16(e_k)
 // (the k-dependent part of codebook.py:70-79) on the 5th-gen tensor cores and reduces them IN THE EPILOGUE to a
-// short list of candidate entries -- a 32-code chunk plus a bit mask of its "quads" (4 consecutive codes) whose
-// minimum is within margin[n] of the running row minimum -- so the N x K distance matrix never leaves the SM.
-// vq_select_kernel (vq_select.cuh) recomputes the distances of the surviving quads exactly in fp32 and takes the
-// first minimum.
+// short list of candidate entries -- a 32-code chunk plus a 32-bit mask of its codes whose score is within the
+// candidate threshold of the running row minimum (vq_common.cuh: candidate_threshold) -- so the N x K distance matrix
+// never leaves the SM.  vq_select_kernel (vq_select.cuh) recomputes the distances of the surviving codes exactly in
+// fp32 and takes the first minimum.
 //
 // CTA = 11 warps, persistent over row tiles (128 latents each).  In the production configuration (kShare) the CTAs run as
 // clusters of two that SHARE the codebook stream: the two CTAs work on different row tiles but the same code tiles, each
 // fetches half of every 32 KiB codebook stage and multicasts it into both rings (cp.async.bulk .multicast::cluster), which
 // halves the L2 -> SMEM operand traffic per SM -- the kernel runs against the 1 kW power cap, so bytes moved are clock
-// (measured: same cycles per tile, 3 % less time).  MMA issue, TMEM hand-off and epilogue stay local to the CTA; only the
+// (measured: same cycles per tile, 2.5 % less time when the kernel is timed alone, neutral inside a sustained loop).  MMA issue, TMEM hand-off and epilogue stay local to the CTA; only the
 // stage-release barrier collects a commit from both CTAs.  Two alternatives were built and measured at K = 16384 and
 // dropped: cta_group::2 pairs (one M = 256 MMA over both SMs, each CTA holding half of B: two cross-CTA hops land in the
 // TMEM buffer cycle, 1.70 ms vs 1.46 ms) and 128-code half tiles with four accumulator quarters (N = 128 MMAs re-read the
@@ -27,7 +27,7 @@
 //   warps 6..9  epilogue group 1: columns [128, 256)
 //               thread <-> TMEM lane <-> latent row; tcgen05.ld 32 columns at a time (prefetched one chunk ahead,
 //               like the |e|^2 values), one FFMA per element for the score, a 3-input-min tree per chunk whose
-//               4-wide partial minima are the quad minima, and a short slow path that pushes (chunk, quad mask)
+//               4-wide partial minima are reused, and a short slow path that pushes (chunk, code mask, chunk minimum)
 //               into a per-(row, group) ring in shared memory.  The accumulator buffer is released as soon as its
 //               last columns are in registers.  A buffer cycles MMA -> drain -> MMA, so the tensor pipe stays busy
 //               only while drain + hand-off latency <= one MMA tile time; splitting the columns over two warps per
