@@ -72,3 +72,40 @@ def test_install_registers_reference_module_path():
     from network.vqvae.submodule.codebook import CodeBook  # noqa: the reference's import line (vqvae.py:17)
     assert CodeBook is vq.CodeBook
     del sys.modules["network.vqvae.submodule.codebook"]
+
+
+def test_build_is_a_noop_when_sources_are_unchanged():
+    """The build stamp is a content hash of the sources (the tree is copied between machines, so file times are useless)."""
+    path = _native.build()
+    before = os.path.getmtime(path)
+    assert _native.build() == path and os.path.getmtime(path) == before
+    assert open(path + ".src").read().strip() == _native._source_digest()
+
+
+def test_nearest_search_host_side_validation():
+    from vq_vae_gan_diffusion_b200 import nearest
+    assert nearest._index_bits(torch.int64, 10 ** 6) == 64 and nearest._index_bits(torch.int32, 10 ** 6) == 32
+    assert nearest._index_bits(torch.int16, 32768) == 16 and nearest._index_bits(torch.uint16, 65536) == 16
+    with pytest.raises(ValueError):
+        nearest._index_bits(torch.int16, 32769)
+    with pytest.raises(ValueError):
+        nearest._index_bits(torch.uint16, 65537)
+    with pytest.raises(ValueError):
+        nearest._index_bits(torch.float32, 8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vq.CodeTable(torch.zeros(4, 96))                       # CPU table
+    with pytest.raises(ValueError):
+        vq.CodeTable(torch.zeros(4, 300))                      # wider than the kernels
+    L = _native.lib()
+    # row-major / narrow entry points validate before touching the device: unknown recipe, bad index width, D != 256
+    assert L.vq_argmin_rows(None, 0, 128, None, None, None, None, 16, 0, None, 64, None, None, 0, None) == -2
+    assert L.vq_argmin_narrow(None, 1, 1, 64, None, None, None, None, 16, None, 32, None, None, 0, None) == -2
+
+
+def test_narrow_latent_dim_is_accepted_and_wide_rejected():
+    cb = vq.CodeBook(8, 64)
+    assert cb.codebook.weight.shape == (8, 64)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        cb(torch.zeros(1, 64, 2, 2))
+    with pytest.raises(ValueError):
+        vq.CodeBook(8, 512)(torch.zeros(1, 512, 2, 2))

@@ -209,6 +209,8 @@ class CodeBook(nn.Module):
         self._derived_key = None
 
     def _check_input(self, z: torch.Tensor):
+        if self.latent_dim > _KERNEL_D:
+            raise ValueError(f"latent_dim {self.latent_dim} > {_KERNEL_D} is not supported by the sm_100a kernels")
         if not isinstance(z, torch.Tensor) or z.dim() != 4:
             raise ValueError(f"CodeBook expects a 4-D (B, C, H, W) tensor, got {tuple(getattr(z, 'shape', ()))}")
         if not z.is_cuda:
@@ -217,8 +219,7 @@ class CodeBook(nn.Module):
             raise RuntimeError(f"CodeBook expects float32 latents, got {z.dtype}")
         if z.shape[1] != self.latent_dim:
             raise ValueError(f"channel dimension {z.shape[1]} != latent_dim {self.latent_dim}")
-        if self.latent_dim > _KERNEL_D:
-            raise ValueError(f"latent_dim {self.latent_dim} > {_KERNEL_D} is not supported by the sm_100a kernels")
+
         w = self.codebook.weight
         if w.device != z.device:
             raise RuntimeError(f"codebook weight on {w.device}, input on {z.device}")
