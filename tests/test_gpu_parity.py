@@ -288,12 +288,18 @@ def test_degenerate_codebook_mass_fallback(vq, oracle):
     with torch.no_grad():
         cb.codebook.weight.copy_(torch.from_numpy(E))
         z_q, idx, loss = cb(torch.from_numpy(z).to(dev))
+        hist = cb.last_histogram.clone()
+        z_q2, idx2, loss2 = cb(torch.from_numpy(z).to(dev))
     st = cb.stats_dict()
-    ref = oracle.forward(z, E, want_zq=False)
+    ref = oracle.forward(z, E)
     assert np.array_equal(idx.cpu().numpy(), ref["idx"])
     assert set(np.unique(ref["idx"]).tolist()) <= {0, 100, 200}
     assert st["tie_rows"] == ref["tie_rows"] == B * H * W
     assert st["fallback_rows"] == B * H * W
+    assert np.array_equal(z_q.permute(0, 2, 3, 1).reshape(-1, 256).cpu().numpy(), ref["zq_nhwc"])
+    assert np.array_equal(hist.cpu().numpy(), ref["hist"])
+    assert abs(float(loss) - float(ref["loss"])) <= 1e-6 * abs(float(ref["loss"]))
+    assert torch.equal(idx, idx2) and torch.equal(z_q, z_q2) and float(loss) == float(loss2)   # reproducible
 
 
 def test_partial_fallback_split_scan(vq, oracle):
@@ -308,19 +314,24 @@ def test_partial_fallback_split_scan(vq, oracle):
     E[1000:1100] = v + 1e-4 * rng.standard_normal((100, 256)).astype(np.float32)   # ... and 100 near copies
     pick = rng.integers(2000, K, size=B * H * W)              # ordinary rows stay away from the cluster
     zf = E[pick] + 0.3 * rng.standard_normal((B * H * W, 256)).astype(np.float32)
-    hot = rng.choice(B * H * W, size=21, replace=False)      # 21 rows next to the cluster: 3 row groups, one ragged
+    hot = rng.choice(B * H * W, size=21, replace=False)      # 21 rows next to the cluster: 2 row groups, one ragged
     zf[hot] = v + 0.05 * rng.standard_normal((21, 256)).astype(np.float32)
     z = np.ascontiguousarray(zf.reshape(B, H, W, 256).transpose(0, 3, 1, 2))
     cb = vq.CodeBook(K, 256).to(dev)
     with torch.no_grad():
         cb.codebook.weight.copy_(torch.from_numpy(E))
         z_q, idx, loss = cb(torch.from_numpy(z).to(dev))
+        st = cb.stats_dict()
+        hist = cb.last_histogram.clone()
+        losses = [float(cb(torch.from_numpy(z).to(dev))[2]) for _ in range(3)]
         idx_tok = cb.encode_indices(torch.from_numpy(z).to(dev))
-    st = cb.stats_dict()
     ref = oracle.forward(z, E)
     assert np.array_equal(idx.cpu().numpy(), ref["idx"])
     assert np.array_equal(idx_tok.cpu().numpy(), ref["idx"])
     assert np.array_equal(z_q.permute(0, 2, 3, 1).reshape(-1, 256).cpu().numpy(), ref["zq_nhwc"])
+    assert np.array_equal(hist.cpu().numpy(), ref["hist"])
+    assert abs(float(loss) - float(ref["loss"])) <= 1e-6 * abs(float(ref["loss"]))
+    assert all(v == float(loss) for v in losses), (float(loss), losses)     # reproducible from call to call
     assert st["fallback_rows"] == 21, st
     assert st["tie_rows"] == ref["tie_rows"]
 

@@ -1,0 +1,18 @@
+#!/bin/bash
+# The sequence that produces what profiles/ holds (run on a B200 box through gpurun; TAG prefixes the output files):
+#   gpurun --timeout 600 -- 'bash tools/refresh_profiles.sh v'
+# Plain runs first (bench values are never taken under a profiler), then the ncu launch list and one `--set full`
+# capture of the seven kernels of one cfg4 step; condense afterwards with tools/ncu_summary.py.
+TAG=${1:-v}
+O=gpurun_out
+mkdir -p $O
+python bench.py > $O/${TAG}_bench_init.json 2> $O/${TAG}_bench_init.err
+python bench.py --distribution trained --no-cpu-baseline > $O/${TAG}_bench_trained.json 2>> $O/${TAG}_bench_init.err
+python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench_init.err
+python tools/gpu_microbench.py --rows > $O/${TAG}_micro.jsonl 2>> $O/${TAG}_bench_init.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:vq_ --launch-skip 28 --launch-count 7 -f -o $O/${TAG}_full \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_ncu2.log 2>&1
+ncu -i $O/${TAG}_full.ncu-rep --page raw --csv > $O/${TAG}_full_raw.csv 2>> $O/${TAG}_ncu2.log
+tail -c 600 $O/${TAG}_bench_init.json

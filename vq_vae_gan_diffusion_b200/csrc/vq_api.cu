@@ -380,7 +380,8 @@ static int forward_impl(bool training, bool rows, int recipe, const float* z, in
         if (rc != VQ_OK) return rc;
         // the kernel sizes its own work split from the worklist length so that one wave of resident CTAs covers it
         const unsigned fgrid = (unsigned)(vq::kFbCtasPerSm * dev->sms);
-        vq::vq_fallback_kernel<<<fgrid, vq::kFbThreads, 0, st>>>(fp);
+        if (recipe == vq::kRecipeDiffSq) vq::vq_fallback_kernel<true><<<fgrid, vq::kFbThreads, 0, st>>>(fp);
+        else                             vq::vq_fallback_kernel<false><<<fgrid, vq::kFbThreads, 0, st>>>(fp);
         VQ_LAUNCH_CHECK("vq_fallback_kernel");
     }
 

@@ -29,11 +29,15 @@ constexpr int kSelThreads = 256;
 constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kMaxCands = 64;           // codes per row the exact stage evaluates (GEMM hands over <= 32 per group)
 constexpr int kFbThreads = 256;
-constexpr int kFbGroup = 8;             // overflowed rows scanned together (they share every code-row load)
-constexpr int kFbMaxGroups = 512;       // row groups whose scan is split over code blocks (4096 rows)
+constexpr int kFbWarps = kFbThreads / 32;
+constexpr int kFbGroup = 16;            // overflowed rows scanned together (they share every code-row load)
+constexpr int kFbMaxGroups = 256;       // row groups whose scan is split over code blocks (4096 rows)
 constexpr int kFbMaxParts = 256;        // code blocks per group
-constexpr int kFbCtasPerSm = 3;         // resident CTAs per SM the kernel is tuned for (registers, 45 KiB of shared memory)
-constexpr int kFbPitch = 36;            // floats per staged code-row segment (32 + 4: 144-byte pitch, conflict-free)
+constexpr int kFbCtasPerSm = 3;         // resident CTAs per SM the kernel is tuned for (registers, 37 KiB of shared memory)
+constexpr int kFbOct = 8;               // codes per warp pass: lane <-> (code lane >> 2, canonical partial sum lane & 3)
+constexpr int kFbPitch = 68;            // floats per staged quarter code row / per (row, partial sum) run of the latents
+                                        // (64 + 4: 272-byte pitch, conflict-free for the 16-byte fills and the reads)
+constexpr int kFbZRow = 4 * kFbPitch;   // floats per de-interleaved latent row
 
 struct SelectParams {
     const float* z;            // (B, D, HW) fp32
@@ -370,130 +374,135 @@ __device__ __forceinline__ void merge_min(uint32_t& d, int& k, int& c, uint32_t 
     else if (d2 == d) { c += c2; k = min(k, k2); }
 }
 
-// Work item = (group of kFbGroup worklist entries, block of codes): one thread per code streams its code row once
-// with 128-bit loads and applies it to all rows of the group (held in shared memory), so the codebook traffic of the
-// fallback is 1/kFbGroup of a row-by-row scan.  The number of code blocks per group is chosen ON THE DEVICE from the
-// worklist length so that groups x blocks fills the resident CTAs about once: a handful of overflowed rows is spread
-// over the whole chip (one or two codes per thread), while a degenerate codebook (every row overflows) gets one CTA
-// per group scanning all codes with no merge step.  The last code block of a group to arrive merges the per-block
-// minima cooperatively.
+// Work item = (group of kFbGroup worklist entries, block of codes).  A warp takes 8 codes per pass, lane <-> (code,
+// canonical partial sum j): the lane accumulates the terms d == j (mod 4) of its code for ALL rows of the group (one
+// accumulator per row), exactly the split the select kernel's exact stage uses, so 16 rows share every code-row load
+// at 16 accumulator registers.  Code rows are fetched coalesced, 64 columns at a time (8 rows x 256 B per warp request
+// group, the next quarter in flight while the current one is used), staged in a per-warp buffer whose 272-byte pitch
+// makes both the 16-byte fills and the lanes' 4-byte reads conflict-free; the group's latent rows sit in shared memory
+// DE-INTERLEAVED by j, so that a lane reads four consecutive terms of its partial sum with one 16-byte load (4 FMAs per
+// load, broadcast to the 8 lanes of the same j).  After a pass the four partial sums of a (row, code) pair are
+// combined as (p0 + p1) + (p2 + p3), the pass minimum per row is taken over the warp with redux.sync on distance
+// keys, and lane r keeps row r's running result.  The number of code blocks per group is chosen ON THE DEVICE from
+// the worklist length so that groups x blocks fills the resident CTAs about once: a handful of overflowed rows is
+// spread over the whole chip, while a degenerate codebook (every row overflows) gets one CTA per group scanning all
+// codes with no merge step.  The last code block of a group to arrive merges the per-block minima (a warp per row).
+template <bool kDiffSq>
 __global__ void __launch_bounds__(kFbThreads, kFbCtasPerSm)
 vq_fallback_kernel(const FallbackParams p) {
-    __shared__ float4 zr4[kFbGroup][kD / 4];
-    __shared__ __align__(16) float stage[kFbThreads / 32][32 * kFbPitch];      // 36 KiB: per-warp [32 codes][32 d] transposer
-    __shared__ uint32_t sd[kFbGroup][kFbThreads / 32];
-    __shared__ int sk[kFbGroup][kFbThreads / 32], sn[kFbGroup][kFbThreads / 32];
-    __shared__ int64_t row_s[kFbGroup];
+    __shared__ __align__(16) float zt[kFbGroup * kFbZRow];                    // 17 KiB: zt[r][j][i] = z[row r][4 i + j]
+    __shared__ __align__(16) float stage[kFbWarps][kFbOct * kFbPitch];        // 17 KiB: per-warp [8 codes][64 d]
+    __shared__ float z2_s[kFbGroup];
+    __shared__ uint32_t sd[kFbGroup][kFbWarps];
+    __shared__ int sk[kFbGroup][kFbWarps], sn[kFbGroup][kFbWarps];
+    __shared__ int64_t row_s[kFbGroup], zoff_s[kFbGroup];
     __shared__ int is_final;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int count = __ldg(p.fb_count);
     if (count == 0) return;
-    const bool diffsq = p.recipe == kRecipeDiffSq;           // block-uniform
     const int groups = (count + kFbGroup - 1) / kFbGroup;
-    // code blocks per group: fill the grid once; a multiple of kFbThreads codes each; never more than kFbMaxParts
-    int parts = max(1, min(min(kFbMaxParts, (int)gridDim.x / groups), (p.K + kFbThreads - 1) / kFbThreads));
+    // code blocks per group: fill the grid once; a multiple of one CTA pass (64 codes) each; never more than kFbMaxParts
+    constexpr int kPass = kFbWarps * kFbOct;
+    int parts = max(1, min(min(kFbMaxParts, (int)gridDim.x / groups), (p.K + kPass - 1) / kPass));
     if (groups > kFbMaxGroups) parts = 1;
-    const int per_part = ((p.K + parts * kFbThreads - 1) / (parts * kFbThreads)) * kFbThreads;
+    const int per_part = ((p.K + parts * kPass - 1) / (parts * kPass)) * kPass;
     parts = (p.K + per_part - 1) / per_part;
     const bool split = parts > 1;
     const int64_t items = (int64_t)groups * parts;
+    const int c = lane >> 2, j = lane & 3;                    // compute role: code of the pass, canonical partial sum
+    const int lrow = lane >> 4, lcol = lane & 15;             // staging role: request i fetches code rows 2 i + lrow
+    float* const stg = &stage[warp][0];
     for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
         const int g = (int)(w / parts), part0 = (int)(w % parts);
         __syncthreads();
-        if (tid < kFbGroup) row_s[tid] = (g * kFbGroup + tid < count) ? (int64_t)__ldg(p.fb_rows + g * kFbGroup + tid) : -1;
-        __syncthreads();
-#pragma unroll
-        for (int r = 0; r < kFbGroup; r++) {
-            const int64_t n = row_s[r];
-            if (tid < kD) reinterpret_cast<float*>(zr4[r])[tid] = (n >= 0) ? __ldg(p.z + ((n / p.HW) * kD + tid) * p.HW + n % p.HW) : 0.0f;
+        if (tid < kFbGroup) {
+            const int64_t n = (g * kFbGroup + tid < count) ? (int64_t)__ldg(p.fb_rows + g * kFbGroup + tid) : -1;
+            row_s[tid] = n;
+            zoff_s[tid] = (n >= 0) ? (n / p.HW) * kD * p.HW + n % p.HW : -1;      // element (row n, d = 0) of the NCHW latents
+            z2_s[tid] = (n >= 0) ? __ldg(p.z2 + n) : 0.0f;
         }
         __syncthreads();
-        float z2[kFbGroup];
-        uint32_t best_d[kFbGroup];
-        int best_k[kFbGroup], n_at_min[kFbGroup];
 #pragma unroll
-        for (int r = 0; r < kFbGroup; r++) {
-            z2[r] = (row_s[r] >= 0) ? __ldg(p.z2 + row_s[r]) : 0.0f;
-            best_d[r] = 0xffffffffu; best_k[r] = 0x7fffffff; n_at_min[r] = 0;
+        for (int r = 0; r < kFbGroup; r++) {                  // thread <-> d; all rows' loads independent
+            const int64_t o = zoff_s[r];
+            zt[r * kFbZRow + (tid & 3) * kFbPitch + (tid >> 2)] = (o >= 0) ? __ldg(p.z + o + (int64_t)tid * p.HW) : 0.0f;
         }
-        const int k_hi = min(p.K, (part0 + 1) * per_part);
-        // A warp scans 32 consecutive codes at a time, one code per lane (ascending k per lane).  The code rows are
-        // fetched COALESCED -- per 128-byte column block, 8 lanes x 16 bytes per code row, 4 rows per request -- and
-        // transposed through a padded per-warp staging buffer, so that every lane then reads its own code's 32 values
-        // with 16-byte shared-memory loads (row pitch 144 B: conflict-free both ways).  Latency is covered by the other resident warps (3 CTAs per SM).
-        float* stg = &stage[warp][0];
-        const int lc = lane >> 3, ls = lane & 7;
-        for (int kb = part0 * per_part + warp * 32; kb < k_hi; kb += kFbThreads) {
-            const int k = kb + lane;
-            float acc[kFbGroup][4];
+        __syncthreads();
+        uint32_t best_d = 0xffffffffu;                        // lane r < kFbGroup: this warp's running result of row r
+        int best_k = 0x7fffffff, best_c = 0;
+        const int k_lo = part0 * per_part, k_hi = min(p.K, k_lo + per_part);
+        float4 pre[4];
+        auto fetch = [&](int kb, int q) {
 #pragma unroll
-            for (int r = 0; r < kFbGroup; r++) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0f;
+            for (int i = 0; i < 4; i++) {
+                const int kk = kb + 2 * i + lrow;
+                pre[i] = (kk < k_hi) ? __ldg(reinterpret_cast<const float4*>(p.E + (int64_t)kk * kD + 64 * q) + lcol)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
+        int kb = k_lo + warp * kFbOct;
+        if (kb < k_hi) fetch(kb, 0);
+        for (; kb < k_hi; kb += kPass) {
+            float acc[kFbGroup];
+#pragma unroll
+            for (int r = 0; r < kFbGroup; r++) acc[r] = 0.0f;
 #pragma unroll 1
-            for (int db = 0; db < kD / 32; db++) {
-                float4 pre[8];
+            for (int q = 0; q < 4; q++) {
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    const int c = 4 * i + lc;
-                    pre[i] = (kb + c < k_hi) ? __ldg(reinterpret_cast<const float4*>(p.E + (int64_t)(kb + c) * kD) + 8 * db + ls)
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; i++) *reinterpret_cast<float4*>(stg + (4 * i + lc) * kFbPitch + 4 * ls) = pre[i];
+                for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(stg + (2 * i + lrow) * kFbPitch + 4 * lcol) = pre[i];
                 __syncwarp();
+                if (q < 3) fetch(kb, q + 1);                  // next quarter (or the next pass's first) in flight
+                else if (kb + kPass < k_hi) fetch(kb + kPass, 0);
+                const float* zq = zt + j * kFbPitch + 16 * q;
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float4 e = *reinterpret_cast<const float4*>(stg + lane * kFbPitch + 4 * j);
+                for (int m = 0; m < 4; m++) {
+                    float e[4];
+#pragma unroll
+                    for (int t = 0; t < 4; t++) e[t] = stg[c * kFbPitch + 16 * m + 4 * t + j];
 #pragma unroll
                     for (int r = 0; r < kFbGroup; r++) {
-                        const float4 zv = zr4[r][8 * db + j];
-                        if (diffsq) {
-                            const float dx = __fsub_rn(zv.x, e.x), dy = __fsub_rn(zv.y, e.y);
-                            const float dz = __fsub_rn(zv.z, e.z), dw = __fsub_rn(zv.w, e.w);
-                            acc[r][0] = __fadd_rn(acc[r][0], __fmul_rn(dx, dx));
-                            acc[r][1] = __fadd_rn(acc[r][1], __fmul_rn(dy, dy));
-                            acc[r][2] = __fadd_rn(acc[r][2], __fmul_rn(dz, dz));
-                            acc[r][3] = __fadd_rn(acc[r][3], __fmul_rn(dw, dw));
+                        const float4 zv = *reinterpret_cast<const float4*>(zq + r * kFbZRow + 4 * m);
+                        if (kDiffSq) {
+                            const float d0 = __fsub_rn(zv.x, e[0]), d1 = __fsub_rn(zv.y, e[1]);
+                            const float d2 = __fsub_rn(zv.z, e[2]), d3 = __fsub_rn(zv.w, e[3]);
+                            acc[r] = __fadd_rn(acc[r], __fmul_rn(d0, d0));
+                            acc[r] = __fadd_rn(acc[r], __fmul_rn(d1, d1));
+                            acc[r] = __fadd_rn(acc[r], __fmul_rn(d2, d2));
+                            acc[r] = __fadd_rn(acc[r], __fmul_rn(d3, d3));
                         } else {
-                            acc[r][0] = __fmaf_rn(zv.x, e.x, acc[r][0]);
-                            acc[r][1] = __fmaf_rn(zv.y, e.y, acc[r][1]);
-                            acc[r][2] = __fmaf_rn(zv.z, e.z, acc[r][2]);
-                            acc[r][3] = __fmaf_rn(zv.w, e.w, acc[r][3]);
+                            acc[r] = __fmaf_rn(zv.x, e[0], acc[r]);
+                            acc[r] = __fmaf_rn(zv.y, e[1], acc[r]);
+                            acc[r] = __fmaf_rn(zv.z, e[2], acc[r]);
+                            acc[r] = __fmaf_rn(zv.w, e[3], acc[r]);
                         }
                     }
                 }
                 __syncwarp();
             }
-            if (k < k_hi) {
-                const float e2k = __ldg(p.e2 + k);
-#pragma unroll
-                for (int r = 0; r < kFbGroup; r++) {
-                    const float dot = __fadd_rn(__fadd_rn(acc[r][0], acc[r][1]), __fadd_rn(acc[r][2], acc[r][3]));
-                    merge_min(best_d[r], best_k[r], n_at_min[r], dist_key(diffsq ? dot : ref_distance(z2[r], e2k, dot)), k, 1);
-                }
-            }
-        }
-        // block-level merge of the per-thread minima: warp shuffles, then thread r finishes row r
-        auto block_merge = [&]() {
+            // this pass's minimum per row over the warp's 8 codes (first index on ties, multiplicity)
+            const int k = kb + c;
+            const bool lead = (j == 0) && (k < k_hi);
+            const float e2k = (lead && !kDiffSq) ? __ldg(p.e2 + k) : 0.0f;
 #pragma unroll
             for (int r = 0; r < kFbGroup; r++) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const uint32_t d2 = __shfl_xor_sync(0xffffffffu, best_d[r], o);
-                    const int k2 = __shfl_xor_sync(0xffffffffu, best_k[r], o);
-                    const int c2 = __shfl_xor_sync(0xffffffffu, n_at_min[r], o);
-                    merge_min(best_d[r], best_k[r], n_at_min[r], d2, k2, c2);
-                }
-                if (lane == 0) { sd[r][warp] = best_d[r]; sk[r][warp] = best_k[r]; sn[r][warp] = n_at_min[r]; }
+                const float dot = combine4(acc[r]);           // (p0 + p1) + (p2 + p3) on all four lanes
+                const uint32_t u = lead ? dist_key(kDiffSq ? dot : ref_distance(z2_s[r], e2k, dot)) : 0xffffffffu;
+                const uint32_t um = __reduce_min_sync(0xffffffffu, u);
+                const bool at = lead && (u == um);
+                const int km = (int)__reduce_min_sync(0xffffffffu, at ? (uint32_t)k : 0x7fffffffu);
+                const int cn = __popc(__ballot_sync(0xffffffffu, at));
+                if (lane == r) merge_min(best_d, best_k, best_c, um, km, cn);
             }
-            __syncthreads();
-            if (tid < kFbGroup) {
-                uint32_t d = sd[tid][0];
-                int k = sk[tid][0], cnt = sn[tid][0];
-                for (int v = 1; v < kFbThreads / 32; v++) merge_min(d, k, cnt, sd[tid][v], sk[tid][v], sn[tid][v]);
-                sd[tid][0] = d; sk[tid][0] = k; sn[tid][0] = cnt;
-            }
-        };
-        block_merge();
+        }
+        // block-level merge of the per-warp results: thread r finishes row r
+        if (lane < kFbGroup) { sd[lane][warp] = best_d; sk[lane][warp] = best_k; sn[lane][warp] = best_c; }
+        __syncthreads();
+        if (tid < kFbGroup) {
+            uint32_t d = sd[tid][0];
+            int k = sk[tid][0], cnt = sn[tid][0];
+            for (int v = 1; v < kFbWarps; v++) merge_min(d, k, cnt, sd[tid][v], sk[tid][v], sn[tid][v]);
+            sd[tid][0] = d; sk[tid][0] = k; sn[tid][0] = cnt;
+        }
         if (split) {
             if (tid < kFbGroup && row_s[tid] >= 0)
                 p.part[((int64_t)g * kFbGroup + tid) * parts + part0] =
@@ -507,25 +516,31 @@ vq_fallback_kernel(const FallbackParams p) {
             __syncthreads();
             if (!is_final) continue;
             __threadfence();
-            // the last block to arrive merges the per-block results of the group, all threads taking part
-#pragma unroll
-            for (int r = 0; r < kFbGroup; r++) {
-                best_d[r] = 0xffffffffu; best_k[r] = 0x7fffffff; n_at_min[r] = 0;
-                if (row_s[r] < 0) continue;                      // block-uniform
-                for (int q = tid; q < parts; q += kFbThreads) {
+            // the last block to arrive merges the per-block results of the group: a warp per row, lanes over the blocks
+            for (int r = warp; r < kFbGroup; r += kFbWarps) {
+                if (row_s[r] < 0) continue;                      // warp-uniform
+                uint32_t d = 0xffffffffu;
+                int k = 0x7fffffff, cnt = 0;
+                for (int q = lane; q < parts; q += 32) {
                     const float4 v = __ldcg(p.part + ((int64_t)g * kFbGroup + r) * parts + q);
-                    merge_min(best_d[r], best_k[r], n_at_min[r], __float_as_uint(v.x), __float_as_int(v.y), __float_as_int(v.z));
+                    merge_min(d, k, cnt, __float_as_uint(v.x), __float_as_int(v.y), __float_as_int(v.z));
                 }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const uint32_t d2 = __shfl_xor_sync(0xffffffffu, d, o);
+                    const int k2 = __shfl_xor_sync(0xffffffffu, k, o);
+                    const int c2 = __shfl_xor_sync(0xffffffffu, cnt, o);
+                    merge_min(d, k, cnt, d2, k2, c2);
+                }
+                if (lane == 0) { sd[r][0] = d; sk[r][0] = k; sn[r][0] = cnt; }
             }
-            __syncthreads();
-            block_merge();
         }
         __syncthreads();
         if (tid < kFbGroup && row_s[tid] >= 0) {
             const int64_t n = row_s[tid];
             int k = sk[tid][0];
             const int cnt = sn[tid][0];
-            // a row can be listed twice (once per epilogue group): the first finisher publishes and counts it
+            // publish the winner as a one-code candidate entry (count -2 = "decided"): the select kernel finishes the row
             if (atomicExch(p.out_cnt + 2 * n, -2) != -2) {
                 if (k == 0x7fffffff) k = 0;                      // (K >= 1: cannot happen)
                 reinterpret_cast<uint2*>(p.out_q)[n * kOutCap] = make_uint2((uint32_t)(k >> 5), 1u << (k & 31));
