@@ -6,6 +6,8 @@
 TAG=${1:-v}
 O=gpurun_out
 mkdir -p $O
+timeout 400 python -m pytest tests -m gpu -x -q > $O/${TAG}_tests.log 2>&1 || { tail -20 $O/${TAG}_tests.log; echo 'GPU tests failed: not profiling'; exit 1; }
+tail -1 $O/${TAG}_tests.log
 python bench.py > $O/${TAG}_bench_init.json 2> $O/${TAG}_bench_init.err
 python bench.py --distribution trained --no-cpu-baseline > $O/${TAG}_bench_trained.json 2>> $O/${TAG}_bench_init.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/${TAG}_bench_reference.json 2>> $O/${TAG}_bench_init.err
@@ -15,4 +17,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:vq_ --launch-skip 28 --launch-count 7 -f -o $O/${TAG}_full \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > $O/${TAG}_ncu2.log 2>&1
 ncu -i $O/${TAG}_full.ncu-rep --page raw --csv > $O/${TAG}_full_raw.csv 2>> $O/${TAG}_ncu2.log
-tail -c 600 $O/${TAG}_bench_init.json
+python tools/fallback_bench.py > $O/${TAG}_fallback.jsonl 2>> $O/${TAG}_bench_init.err
+[ -f vq_vae_gan_diffusion_b200/lib/libvq_b200_head.so ] && VQ_B200_LIB=$PWD/vq_vae_gan_diffusion_b200/lib/libvq_b200_head.so \
+    python tools/fallback_bench.py >> $O/${TAG}_fallback.jsonl 2>> $O/${TAG}_bench_init.err
+tail -c 600 $O/${TAG}_bench_init.json; cat $O/${TAG}_fallback.jsonl

@@ -28,16 +28,17 @@ constexpr int kSelThreads = 256;
 #endif
 constexpr int kSelWarps = kSelThreads / 32;
 constexpr int kMaxCands = 64;           // codes per row the exact stage evaluates (GEMM hands over <= 32 per group)
-constexpr int kFbThreads = 256;
+constexpr int kFbThreads = 128;
 constexpr int kFbWarps = kFbThreads / 32;
-constexpr int kFbGroup = 16;            // overflowed rows scanned together (they share every code-row load)
-constexpr int kFbMaxGroups = 256;       // row groups whose scan is split over code blocks (4096 rows)
+constexpr int kFbGroup = 8;             // overflowed rows scanned together (they share every code-row load)
+constexpr int kFbMaxGroups = 512;       // row groups whose scan is split over code blocks (4096 rows)
 constexpr int kFbMaxParts = 256;        // code blocks per group
-constexpr int kFbCtasPerSm = 3;         // resident CTAs per SM the kernel is tuned for (registers, 37 KiB of shared memory)
-constexpr int kFbOct = 8;               // codes per warp pass: lane <-> (code lane >> 2, canonical partial sum lane & 3)
-constexpr int kFbPitch = 68;            // floats per staged quarter code row / per (row, partial sum) run of the latents
-                                        // (64 + 4: 272-byte pitch, conflict-free for the 16-byte fills and the reads)
-constexpr int kFbZRow = 4 * kFbPitch;   // floats per de-interleaved latent row
+constexpr int kFbCtasPerSm = 4;         // resident CTAs per SM the kernel is tuned for (128 registers, 27 KiB of shared memory)
+constexpr int kFbCodes = 4;             // codes per lane and pass: a lane owns a 4 codes x 8 rows register tile of ONE
+                                        // canonical partial sum (32 accumulators), a warp pass covers 32 codes
+constexpr int kFbEPitch = 36;           // floats per staged 32-column code-row segment (32 + 4: conflict-free both ways)
+constexpr int kFbZPitch = 68;           // floats per (row, partial sum) run of the de-interleaved latents (64 + 4)
+constexpr int kFbZRow = 4 * kFbZPitch;  // floats per de-interleaved latent row
 
 struct SelectParams {
     const float* z;            // (B, D, HW) fp32
@@ -374,24 +375,27 @@ __device__ __forceinline__ void merge_min(uint32_t& d, int& k, int& c, uint32_t 
     else if (d2 == d) { c += c2; k = min(k, k2); }
 }
 
-// Work item = (group of kFbGroup worklist entries, block of codes).  A warp takes 8 codes per pass, lane <-> (code,
-// canonical partial sum j): the lane accumulates the terms d == j (mod 4) of its code for ALL rows of the group (one
-// accumulator per row), exactly the split the select kernel's exact stage uses, so 16 rows share every code-row load
-// at 16 accumulator registers.  Code rows are fetched coalesced, 64 columns at a time (8 rows x 256 B per warp request
-// group, the next quarter in flight while the current one is used), staged in a per-warp buffer whose 272-byte pitch
-// makes both the 16-byte fills and the lanes' 4-byte reads conflict-free; the group's latent rows sit in shared memory
-// DE-INTERLEAVED by j, so that a lane reads four consecutive terms of its partial sum with one 16-byte load (4 FMAs per
-// load, broadcast to the 8 lanes of the same j).  After a pass the four partial sums of a (row, code) pair are
-// combined as (p0 + p1) + (p2 + p3), the pass minimum per row is taken over the warp with redux.sync on distance
-// keys, and lane r keeps row r's running result.  The number of code blocks per group is chosen ON THE DEVICE from
-// the worklist length so that groups x blocks fills the resident CTAs about once: a handful of overflowed rows is
-// spread over the whole chip, while a degenerate codebook (every row overflows) gets one CTA per group scanning all
-// codes with no merge step.  The last code block of a group to arrive merges the per-block minima (a warp per row).
+// Work item = (group of kFbGroup worklist entries, block of codes).  The scan is bound by shared-memory -> register
+// bandwidth (128 B per cycle and SM), so it is register-tiled: lane <-> (code block cb = lane >> 2, canonical partial
+// sum j = lane & 3) owns the terms d == j (mod 4) of FOUR codes (kb + cb + 8 t) for all EIGHT rows of the group -- 32
+// accumulators; per 16 columns it reads its codes' values with 4-byte loads (16 of them) and each row's four terms with
+// one 16-byte load (8 of them) for 128 FMAs, about a third of the shared-memory traffic per FMA of a one-code-per-lane
+// scheme (two of those were built first; ncu: l1tex 49-55 % busy, short-scoreboard stalls on top).  A warp
+// pass covers 32 codes: their rows are fetched coalesced, 32 columns at a time (8 lanes x 16 bytes per row, the next segment in flight
+// while the current one is used), into a per-warp buffer whose 144-byte pitch makes both the 16-byte fills and the
+// 4-byte reads conflict-free; the group's latent rows sit in shared memory DE-INTERLEAVED by j, which is what turns
+// four consecutive terms of a partial sum into one 16-byte load (broadcast to the 8 lanes of the same j).  After a
+// pass the partial sums of every (row, code) pair are combined as (p0 + p1) + (p2 + p3), each lane reduces its four
+// codes, the warp reduces with redux.sync on distance keys, and lane r keeps row r's running result.  The number of
+// code blocks per group is chosen ON THE DEVICE from the worklist length so that groups x blocks fills the resident
+// CTAs about once: a handful of overflowed rows is spread over the whole chip, while a degenerate codebook (every row
+// overflows) gets one CTA per group scanning all codes with no merge step.  The last code block of a group to arrive
+// merges the per-block minima (a warp per row).
 template <bool kDiffSq>
 __global__ void __launch_bounds__(kFbThreads, kFbCtasPerSm)
 vq_fallback_kernel(const FallbackParams p) {
-    __shared__ __align__(16) float zt[kFbGroup * kFbZRow];                    // 17 KiB: zt[r][j][i] = z[row r][4 i + j]
-    __shared__ __align__(16) float stage[kFbWarps][kFbOct * kFbPitch];        // 17 KiB: per-warp [8 codes][64 d]
+    __shared__ __align__(16) float zt[kFbGroup * kFbZRow];                    // 8.5 KiB: zt[r][j][i] = z[row r][4 i + j]
+    __shared__ __align__(16) float stage[kFbWarps][32 * kFbEPitch];           // 18 KiB: per-warp [32 codes][32 d]
     __shared__ float z2_s[kFbGroup];
     __shared__ uint32_t sd[kFbGroup][kFbWarps];
     __shared__ int sk[kFbGroup][kFbWarps], sn[kFbGroup][kFbWarps];
@@ -401,16 +405,16 @@ vq_fallback_kernel(const FallbackParams p) {
     const int count = __ldg(p.fb_count);
     if (count == 0) return;
     const int groups = (count + kFbGroup - 1) / kFbGroup;
-    // code blocks per group: fill the grid once; a multiple of one CTA pass (64 codes) each; never more than kFbMaxParts
-    constexpr int kPass = kFbWarps * kFbOct;
+    // code blocks per group: fill the grid once; a multiple of one CTA pass (128 codes) each; never more than kFbMaxParts
+    constexpr int kPass = kFbWarps * 32;
     int parts = max(1, min(min(kFbMaxParts, (int)gridDim.x / groups), (p.K + kPass - 1) / kPass));
     if (groups > kFbMaxGroups) parts = 1;
     const int per_part = ((p.K + parts * kPass - 1) / (parts * kPass)) * kPass;
     parts = (p.K + per_part - 1) / per_part;
     const bool split = parts > 1;
     const int64_t items = (int64_t)groups * parts;
-    const int c = lane >> 2, j = lane & 3;                    // compute role: code of the pass, canonical partial sum
-    const int lrow = lane >> 4, lcol = lane & 15;             // staging role: request i fetches code rows 2 i + lrow
+    const int cb = lane >> 2, j = lane & 3;                   // compute role: code block, canonical partial sum
+    const int lc = lane >> 3, ls = lane & 7;                  // staging role: request i fetches code rows 4 i + lc
     float* const stg = &stage[warp][0];
     for (int64_t w = blockIdx.x; w < items; w += gridDim.x) {
         const int g = (int)(w / parts), part0 = (int)(w % parts);
@@ -423,74 +427,96 @@ vq_fallback_kernel(const FallbackParams p) {
         }
         __syncthreads();
 #pragma unroll
-        for (int r = 0; r < kFbGroup; r++) {                  // thread <-> d; all rows' loads independent
+        for (int r = 0; r < kFbGroup; r++) {                  // thread <-> d, d + 128; all loads independent
             const int64_t o = zoff_s[r];
-            zt[r * kFbZRow + (tid & 3) * kFbPitch + (tid >> 2)] = (o >= 0) ? __ldg(p.z + o + (int64_t)tid * p.HW) : 0.0f;
+#pragma unroll
+            for (int h = 0; h < kD / kFbThreads; h++) {
+                const int d = tid + kFbThreads * h;
+                zt[r * kFbZRow + (d & 3) * kFbZPitch + (d >> 2)] = (o >= 0) ? __ldg(p.z + o + (int64_t)d * p.HW) : 0.0f;
+            }
         }
         __syncthreads();
         uint32_t best_d = 0xffffffffu;                        // lane r < kFbGroup: this warp's running result of row r
         int best_k = 0x7fffffff, best_c = 0;
         const int k_lo = part0 * per_part, k_hi = min(p.K, k_lo + per_part);
-        float4 pre[4];
-        auto fetch = [&](int kb, int q) {
+        float4 pre[8];
+        auto fetch = [&](int kb, int db) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const int kk = kb + 2 * i + lrow;
-                pre[i] = (kk < k_hi) ? __ldg(reinterpret_cast<const float4*>(p.E + (int64_t)kk * kD + 64 * q) + lcol)
+            for (int i = 0; i < 8; i++) {
+                const int kk = kb + 4 * i + lc;
+                pre[i] = (kk < k_hi) ? __ldg(reinterpret_cast<const float4*>(p.E + (int64_t)kk * kD + 32 * db) + ls)
                                      : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         };
-        int kb = k_lo + warp * kFbOct;
+        int kb = k_lo + warp * 32;
         if (kb < k_hi) fetch(kb, 0);
         for (; kb < k_hi; kb += kPass) {
-            float acc[kFbGroup];
+            float acc[kFbCodes][kFbGroup];
 #pragma unroll
-            for (int r = 0; r < kFbGroup; r++) acc[r] = 0.0f;
+            for (int t = 0; t < kFbCodes; t++)
+#pragma unroll
+                for (int r = 0; r < kFbGroup; r++) acc[t][r] = 0.0f;
 #pragma unroll 1
-            for (int q = 0; q < 4; q++) {
+            for (int db = 0; db < kD / 32; db++) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) *reinterpret_cast<float4*>(stg + (2 * i + lrow) * kFbPitch + 4 * lcol) = pre[i];
+                for (int i = 0; i < 8; i++) *reinterpret_cast<float4*>(stg + (4 * i + lc) * kFbEPitch + 4 * ls) = pre[i];
                 __syncwarp();
-                if (q < 3) fetch(kb, q + 1);                  // next quarter (or the next pass's first) in flight
+                if (db < kD / 32 - 1) fetch(kb, db + 1);      // next segment (or the next pass's first) in flight
                 else if (kb + kPass < k_hi) fetch(kb + kPass, 0);
-                const float* zq = zt + j * kFbPitch + 16 * q;
+                const float* zq = zt + j * kFbZPitch + 8 * db;
+                const float* eq = stg + cb * kFbEPitch + j;
 #pragma unroll
-                for (int m = 0; m < 4; m++) {
-                    float e[4];
+                for (int h = 0; h < 2; h++) {
+                    float e[kFbCodes][4];
 #pragma unroll
-                    for (int t = 0; t < 4; t++) e[t] = stg[c * kFbPitch + 16 * m + 4 * t + j];
+                    for (int t = 0; t < kFbCodes; t++)
+#pragma unroll
+                        for (int u = 0; u < 4; u++) e[t][u] = eq[8 * t * kFbEPitch + 4 * (4 * h + u)];
 #pragma unroll
                     for (int r = 0; r < kFbGroup; r++) {
-                        const float4 zv = *reinterpret_cast<const float4*>(zq + r * kFbZRow + 4 * m);
-                        if (kDiffSq) {
-                            const float d0 = __fsub_rn(zv.x, e[0]), d1 = __fsub_rn(zv.y, e[1]);
-                            const float d2 = __fsub_rn(zv.z, e[2]), d3 = __fsub_rn(zv.w, e[3]);
-                            acc[r] = __fadd_rn(acc[r], __fmul_rn(d0, d0));
-                            acc[r] = __fadd_rn(acc[r], __fmul_rn(d1, d1));
-                            acc[r] = __fadd_rn(acc[r], __fmul_rn(d2, d2));
-                            acc[r] = __fadd_rn(acc[r], __fmul_rn(d3, d3));
-                        } else {
-                            acc[r] = __fmaf_rn(zv.x, e[0], acc[r]);
-                            acc[r] = __fmaf_rn(zv.y, e[1], acc[r]);
-                            acc[r] = __fmaf_rn(zv.z, e[2], acc[r]);
-                            acc[r] = __fmaf_rn(zv.w, e[3], acc[r]);
+                        const float4 zv = *reinterpret_cast<const float4*>(zq + r * kFbZRow + 4 * h);
+#pragma unroll
+                        for (int t = 0; t < kFbCodes; t++) {
+                            if (kDiffSq) {
+                                const float d0 = __fsub_rn(zv.x, e[t][0]), d1 = __fsub_rn(zv.y, e[t][1]);
+                                const float d2 = __fsub_rn(zv.z, e[t][2]), d3 = __fsub_rn(zv.w, e[t][3]);
+                                acc[t][r] = __fadd_rn(acc[t][r], __fmul_rn(d0, d0));
+                                acc[t][r] = __fadd_rn(acc[t][r], __fmul_rn(d1, d1));
+                                acc[t][r] = __fadd_rn(acc[t][r], __fmul_rn(d2, d2));
+                                acc[t][r] = __fadd_rn(acc[t][r], __fmul_rn(d3, d3));
+                            } else {
+                                acc[t][r] = __fmaf_rn(zv.x, e[t][0], acc[t][r]);
+                                acc[t][r] = __fmaf_rn(zv.y, e[t][1], acc[t][r]);
+                                acc[t][r] = __fmaf_rn(zv.z, e[t][2], acc[t][r]);
+                                acc[t][r] = __fmaf_rn(zv.w, e[t][3], acc[t][r]);
+                            }
                         }
                     }
                 }
                 __syncwarp();
             }
-            // this pass's minimum per row over the warp's 8 codes (first index on ties, multiplicity)
-            const int k = kb + c;
-            const bool lead = (j == 0) && (k < k_hi);
-            const float e2k = (lead && !kDiffSq) ? __ldg(p.e2 + k) : 0.0f;
+            // this pass's minimum per row: over the lane's four codes (ascending k), then over the warp
+            float e2k[kFbCodes];
+#pragma unroll
+            for (int t = 0; t < kFbCodes; t++) {
+                const int k = kb + cb + 8 * t;
+                e2k[t] = (!kDiffSq && k < k_hi) ? __ldg(p.e2 + k) : 0.0f;
+            }
 #pragma unroll
             for (int r = 0; r < kFbGroup; r++) {
-                const float dot = combine4(acc[r]);           // (p0 + p1) + (p2 + p3) on all four lanes
-                const uint32_t u = lead ? dist_key(kDiffSq ? dot : ref_distance(z2_s[r], e2k, dot)) : 0xffffffffu;
-                const uint32_t um = __reduce_min_sync(0xffffffffu, u);
-                const bool at = lead && (u == um);
-                const int km = (int)__reduce_min_sync(0xffffffffu, at ? (uint32_t)k : 0x7fffffffu);
-                const int cn = __popc(__ballot_sync(0xffffffffu, at));
+                uint32_t u_loc = 0xffffffffu;
+                int k_loc = 0x7fffffff, c_loc = 0;
+#pragma unroll
+                for (int t = 0; t < kFbCodes; t++) {
+                    const float dot = combine4(acc[t][r]);    // (p0 + p1) + (p2 + p3) on all four lanes
+                    const int k = kb + cb + 8 * t;
+                    if (j == 0 && k < k_hi)
+                        merge_min(u_loc, k_loc, c_loc, dist_key(kDiffSq ? dot : ref_distance(z2_s[r], e2k[t], dot)), k, 1);
+                }
+                const uint32_t um = __reduce_min_sync(0xffffffffu, u_loc);
+                const bool at = (c_loc > 0) && (u_loc == um);
+                const int km = (int)__reduce_min_sync(0xffffffffu, at ? (uint32_t)k_loc : 0x7fffffffu);
+                const int cn = (int)__reduce_add_sync(0xffffffffu, at ? (uint32_t)c_loc : 0u);
                 if (lane == r) merge_min(best_d, best_k, best_c, um, km, cn);
             }
         }
