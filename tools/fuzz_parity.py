@@ -3,7 +3,11 @@ across code-tile boundaries), random value distributions (well separated, near t
 scaled-down magnitudes), forward + backward + tokeniser + row-major search, every result checked against the CPU oracle
 (indices / histogram / z_q bit-exact, loss 1e-6, gradients 1e-5).
 
-    python tools/fuzz_parity.py [--cases 40] [--seed 0]
+    python tools/fuzz_parity.py [--cases 40] [--seed 0] [--kinds trained,init,dup,big,tiny,cluster]
+
+"cluster" plants a run of identical / nearly identical codes and a few latents next to it, so that those rows overflow
+their candidate lists and take the exact full-scan fallback (split over code blocks, ragged row groups, K off the pass
+boundaries).
 """
 from __future__ import annotations
 
@@ -26,6 +30,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=40)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--kinds", default="trained,init,dup,big,tiny,cluster")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     dev = torch.device("cuda:0")
@@ -39,7 +44,7 @@ def main():
             H, W = int(rng.integers(1, 12)), int(rng.integers(1, 12))
         B = int(rng.integers(1, max(2, 6000 // (H * W))))
         K = int(rng.choice([1, 3, 31, 256, 257, 500, 1024, 1025, 3000, 4097]))
-        kind = rng.choice(["trained", "init", "dup", "big", "tiny"])
+        kind = rng.choice(args.kinds.split(","))
         N = B * H * W
         if kind == "init":
             E = rng.uniform(-1.0 / K, 1.0 / K, size=(K, 256)).astype(np.float32)
@@ -49,6 +54,13 @@ def main():
             if kind == "dup" and K >= 3:
                 E[K // 2:] = E[: K - K // 2]
             zf = E[rng.integers(0, K, N)] + np.float32(rng.choice([0.1, 0.5, 1.5])) * rng.standard_normal((N, 256)).astype(np.float32)
+            if kind == "cluster" and K >= 200:
+                c = int(rng.integers(40, min(K // 2, 400)))
+                a = int(rng.integers(0, K - c))
+                v = rng.standard_normal(256).astype(np.float32)
+                E[a:a + c] = v + np.float32(rng.choice([0.0, 1e-4])) * rng.standard_normal((c, 256)).astype(np.float32)
+                hot = rng.choice(N, size=min(N, int(rng.integers(1, 70))), replace=False)
+                zf[hot] = v + np.float32(0.05) * rng.standard_normal((len(hot), 256)).astype(np.float32)
             if kind == "big":
                 E *= np.float32(300.0); zf *= np.float32(300.0)
             if kind == "tiny":
