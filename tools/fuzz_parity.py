@@ -55,10 +55,10 @@ def main():
                 E[K // 2:] = E[: K - K // 2]
             zf = E[rng.integers(0, K, N)] + np.float32(rng.choice([0.1, 0.5, 1.5])) * rng.standard_normal((N, 256)).astype(np.float32)
             if kind == "cluster" and K >= 200:
-                c = int(rng.integers(40, min(K // 2, 400)))
-                a = int(rng.integers(0, K - c))
+                csize = int(rng.integers(40, min(K // 2, 400)))
+                a = int(rng.integers(0, K - csize))
                 v = rng.standard_normal(256).astype(np.float32)
-                E[a:a + c] = v + np.float32(rng.choice([0.0, 1e-4])) * rng.standard_normal((c, 256)).astype(np.float32)
+                E[a:a + csize] = v + np.float32(rng.choice([0.0, 1e-4])) * rng.standard_normal((csize, 256)).astype(np.float32)
                 hot = rng.choice(N, size=min(N, int(rng.integers(1, 70))), replace=False)
                 zf[hot] = v + np.float32(0.05) * rng.standard_normal((len(hot), 256)).astype(np.float32)
             if kind == "big":
