@@ -152,6 +152,25 @@ int vq_backward(const float* gout, const int64_t* gout_strides_host, float g_los
 int vq_embed_nchw(const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K,
                   float* out_nchw, vq_stream_t stream);
 
+/*
+ * Token-stream formats after the tokeniser.
+ *
+ * vq_index_to_log_onehot replaces index_to_log_onehot(x, num_classes)
+ * (network/vq_diffusion/vq_diffusion.py:29-35, network/vqDiffusion/submodule/diffusion_vq_official.py:53-60):
+ *   out (B, num_classes, L) fp32 = log(clamp(one_hot(idx (B, L) int64), min = clamp_min)), class axis second;
+ *   the reference's clamp_min is 1e-30.  Indices outside [0, num_classes) leave their column at log(clamp_min)
+ *   (F.one_hot raises for them: the Python mirror checks before calling).
+ *
+ * vq_mask_replace replaces the arithmetic of VQTransformer.forward's input corruption
+ * (network/vqTransformer/vqTransformer.py:117-141): out (B, L + 1) int64 with out[:, 0] = sos_token and
+ *   out[:, 1 + l] = m * indices + (1 - m) * random_indices,  m = (int64) round(mask)   (mask: the fp32 Bernoulli draw).
+ *   The random draws themselves stay with the caller (torch's generator), so the stream is the reference's.
+ */
+int vq_index_to_log_onehot(const int64_t* idx, int64_t B, int64_t L, int num_classes, float clamp_min, float* out,
+                           vq_stream_t stream);
+int vq_mask_replace(const int64_t* indices, const float* mask, const int64_t* random_indices, int64_t sos_token,
+                    int64_t B, int64_t L, int64_t* out, vq_stream_t stream);
+
 /* Number of kernel launches the last call on this thread enqueued (for bench.py's gpu_launches). */
 int vq_last_launch_count(void);
 

@@ -223,3 +223,28 @@ def torch_cpu_step(z, E, g_out=None, beta: float = 0.25, indices_only: bool = Fa
         return z_q, idx, loss, None, None
     (loss + (z_q * g_out).sum()).backward()
     return z_q.detach(), idx, loss.detach(), zin.grad, W.grad
+
+
+# ----------------------------------------------------------------------------------------------
+# Token-stream formats after the tokeniser; pinned by tests/golden/tok_*.npz
+# (tests/golden/make_golden_tokens.py runs the reference's own functions / lines).
+# ----------------------------------------------------------------------------------------------
+
+def index_to_log_onehot_np(x: np.ndarray, num_classes: int) -> np.ndarray:
+    """network/vq_diffusion/vq_diffusion.py:29-35 (== diffusion_vq_official.py:53-60): x (B, ...) int64 ->
+    log(clamp(one_hot(x), min=1e-30)) as (B, num_classes, ...) fp32, the class axis moved to position 1."""
+    x = np.asarray(x, dtype=np.int64)
+    if x.min(initial=0) < 0 or x.max(initial=0) >= num_classes:
+        raise RuntimeError("Class values must be in [0, num_classes)")                   # F.one_hot raises
+    onehot = (x[..., None] == np.arange(num_classes, dtype=np.int64)).astype(np.float32)  # F.one_hot(...).float()  :31/:56
+    order = (0, x.ndim) + tuple(range(1, x.ndim))                                         # permute_order  :32/:57
+    return np.log(np.maximum(onehot.transpose(order), np.float32(1e-30)))                 # log(clamp(min=1e-30))  :34/:59
+
+
+def blend_with_sos_np(indices: np.ndarray, mask: np.ndarray, random_indices: np.ndarray, sos_token: int) -> np.ndarray:
+    """network/vqTransformer/vqTransformer.py:117-118, 124, 138-141: mask is the fp32 Bernoulli draw (:121-123), random_indices the
+    randint_like draw (:127-129).  Returns cat(sos, mask.round().long() * indices + (1 - mask.round().long()) * random)."""
+    m = np.rint(np.asarray(mask, dtype=np.float32)).astype(np.int64)                      # .round().to(int64)  :124
+    new = m * np.asarray(indices, np.int64) + (1 - m) * np.asarray(random_indices, np.int64)   # :138
+    sos = np.full((new.shape[0], 1), sos_token, dtype=np.int64)                            # :117-118
+    return np.concatenate([sos, new], axis=1)                                              # :141

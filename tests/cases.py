@@ -118,3 +118,25 @@ def make_diffsq_inputs(spec: dict):
         E = rng.standard_normal((K, D), dtype=np.float32)
         x = E[rng.integers(0, K, size=B * L)] + np.float32(spec["noise"]) * rng.standard_normal((B * L, D), dtype=np.float32)
     return np.ascontiguousarray(x.reshape(B, L, D), dtype=np.float32), E
+
+
+# Token-stream formats after the tokeniser.  index_to_log_onehot: the vector path (L % 4 == 0), the
+# scalar path, trailing dims beyond one (the VQ-Diffusion tokens are (B, L); the function is rank-generic), the class
+# count off the 32-class tile, the [MASK] class (num_classes = K + 1) unused.
+TOKEN_ONEHOT_CASES = {
+    "tok_onehot_vec":    dict(shape=(3, 64), num_classes=45, seed=401),
+    "tok_onehot_scalar": dict(shape=(2, 37), num_classes=33, seed=402),
+    "tok_onehot_2d":     dict(shape=(2, 6, 10), num_classes=17, seed=403),
+    "tok_onehot_mask":   dict(shape=(2, 256), num_classes=129, seed=404, high=128),       # class 128 = [MASK], never set
+}
+
+# VQTransformer.forward's input corruption (vqTransformer.py:117-141): pkeep 0.5 is the reference's default.
+TOKEN_BLEND_CASES = {
+    "tok_blend_small": dict(shape=(4, 256), num_classes=1024, pkeep=0.5, sos_token=0, seed=411),
+    "tok_blend_odd":   dict(shape=(3, 77), num_classes=513, pkeep=0.9, sos_token=512, seed=412),
+}
+
+
+def make_token_indices(spec: dict) -> np.ndarray:
+    rng = np.random.default_rng(spec["seed"])
+    return rng.integers(0, spec.get("high", spec["num_classes"]), size=spec["shape"], dtype=np.int64)

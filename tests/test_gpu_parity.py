@@ -680,3 +680,94 @@ def test_narrow_latent_dim_runs_zero_padded(D, K, vq, oracle):
         assert np.array_equal(cb.encode_indices(zt.detach()).cpu().numpy(), ref["idx"])
     with pytest.raises(ValueError):
         vq.CodeBook(16, 512).to(dev)(torch.zeros(1, 512, 2, 2, device=dev))
+
+
+# ------------------------------------------------------------------ token-stream formats
+from cases import TOKEN_BLEND_CASES, TOKEN_ONEHOT_CASES, make_token_indices  # noqa: E402
+
+ULP_AT_69 = 2.0 ** -17          # float32 spacing at |log(1e-30)| = 69.08
+
+
+def reference_log_onehot(x, num_classes):
+    """network/vq_diffusion/vq_diffusion.py:29-35, the reference's own lines (any device)."""
+    x_onehot = torch.nn.functional.one_hot(x, num_classes)
+    permute_order = (0, -1) + tuple(range(1, len(x.size())))
+    x_onehot = x_onehot.permute(permute_order)
+    return torch.log(x_onehot.float().clamp(min=1e-30))
+
+
+@pytest.mark.parametrize("name", list(TOKEN_ONEHOT_CASES))
+def test_index_to_log_onehot(name, vq):
+    """vq_index_to_log_onehot against the reference's lines on the same GPU (bit-exact: same logf), against the CPU
+    oracle / golden output of the reference (0 exactly; log(1e-30) within one float32 ulp -- device logf vs host libm)."""
+    from oracle.vq_oracle import index_to_log_onehot_np
+    dev = torch.device("cuda:0")
+    spec = TOKEN_ONEHOT_CASES[name]
+    x_np = make_token_indices(spec)
+    x = torch.from_numpy(x_np).to(dev)
+    out = vq.index_to_log_onehot(x, spec["num_classes"])
+    exp = reference_log_onehot(x, spec["num_classes"])
+    assert out.dtype == torch.float32 and out.shape == exp.shape and out.is_contiguous()
+    assert torch.equal(out, exp)
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))["out"]
+    orc = index_to_log_onehot_np(x_np, spec["num_classes"])
+    got = out.cpu().numpy()
+    assert np.array_equal(orc, gold)
+    assert np.array_equal(got == 0.0, gold == 0.0)                       # the one-hot pattern itself: exact
+    assert float(np.abs(got - gold).max()) <= ULP_AT_69
+    assert torch.equal(out.argmax(1), x)                                 # log_onehot_to_index (vq_diffusion.py:37-38) inverts it
+
+
+def test_index_to_log_onehot_sizes_and_errors(vq):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(5)
+    # the VQ-Diffusion shape: 1024 tokens, K + 1 classes; a non-contiguous view; an unaligned-length batch
+    for shape, C in (((8, 1024), 1025), ((5, 33), 7), ((1, 4), 1)):
+        x = torch.randint(0, C, shape, device=dev, generator=g)
+        assert torch.equal(vq.index_to_log_onehot(x, C), reference_log_onehot(x, C))
+    xt = torch.randint(0, 40, (16, 12), device=dev, generator=g).t()     # (12, 16) view with strides (1, 12)
+    assert torch.equal(vq.index_to_log_onehot(xt, 40), reference_log_onehot(xt, 40))
+    assert vq.index_to_log_onehot(torch.zeros((0, 8), dtype=torch.int64, device=dev), 5).shape == (0, 5, 8)
+    with pytest.raises(RuntimeError, match="smaller than num_classes"):
+        vq.index_to_log_onehot(torch.tensor([[0, 5]], device=dev), 5)
+    with pytest.raises(RuntimeError, match="non-negative"):
+        vq.index_to_log_onehot(torch.tensor([[0, -1]], device=dev), 5)
+    with pytest.raises(RuntimeError, match="LongTensor"):
+        vq.index_to_log_onehot(torch.zeros((2, 2), dtype=torch.int32, device=dev), 5)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vq.index_to_log_onehot(torch.zeros((2, 2), dtype=torch.int64), 5)
+
+
+@pytest.mark.parametrize("name", list(TOKEN_BLEND_CASES))
+def test_blend_with_sos_golden(name, vq):
+    """vq_mask_replace on the reference's stored draws == the reference's new_indices (vqTransformer.py:117-141)."""
+    from oracle.vq_oracle import blend_with_sos_np
+    dev = torch.device("cuda:0")
+    spec = TOKEN_BLEND_CASES[name]
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    idx_np = make_token_indices(spec)
+    out = vq.blend_with_sos(torch.from_numpy(idx_np).to(dev), torch.from_numpy(gold["mask"]).to(dev),
+                            torch.from_numpy(gold["random_indices"]).to(dev), spec["sos_token"])
+    assert out.dtype == torch.int64 and out.shape == (idx_np.shape[0], idx_np.shape[1] + 1)
+    assert np.array_equal(out.cpu().numpy(), gold["new_indices"])
+    assert np.array_equal(out.cpu().numpy(), blend_with_sos_np(idx_np, gold["mask"], gold["random_indices"], spec["sos_token"]))
+
+
+def test_mask_and_replace_consumes_the_generator_like_the_reference(vq):
+    """Same seed -> same corrupted tokens as the reference's lines run on the same device (the draws stay in torch)."""
+    dev = torch.device("cuda:0")
+    indices = torch.randint(0, 1024, (6, 256), device=dev)
+    pkeep, vocab, sos = 0.5, 1024, 0
+    torch.manual_seed(77)
+    got = vq.mask_and_replace(indices, pkeep, vocab, sos)
+    after_ours = torch.rand(4, device=dev)
+    torch.manual_seed(77)
+    sos_tokens = (torch.ones(indices.shape[0], 1) * sos).long().to(dev)                       # vqTransformer.py:117-118
+    mask = torch.bernoulli(pkeep * torch.ones(indices.shape, device=indices.device))          # :121-123
+    mask = mask.round().to(dtype=torch.int64)                                                 # :124
+    random_indices = torch.randint_like(indices, high=vocab)                                  # :127-129
+    exp = torch.cat((sos_tokens, mask * indices + (1 - mask) * random_indices), dim=1)        # :138-141
+    after_ref = torch.rand(4, device=dev)
+    assert torch.equal(got, exp)
+    assert torch.equal(after_ours, after_ref)                                                 # generator left in the same state
+    assert 0.3 < float((got[:, 1:] == indices).double().mean()) < 0.7

@@ -264,3 +264,29 @@ def test_diffsq_known_answers(oracle):
     xn = x.copy()
     xn[1, 0] = np.nan
     assert oracle.nearest_diffsq(xn, E)["idx"].tolist() == [0, 0, 3, 3]   # all distances NaN -> first code
+
+
+# ------------------------------------------------------------------ token-stream formats
+
+def test_token_onehot_oracle_matches_reference():
+    """oracle index_to_log_onehot_np == the reference's index_to_log_onehot (both copies), bit for bit."""
+    from cases import TOKEN_ONEHOT_CASES, make_token_indices
+    from oracle.vq_oracle import index_to_log_onehot_np
+    for name, spec in TOKEN_ONEHOT_CASES.items():
+        gold = load(name)["out"]
+        got = index_to_log_onehot_np(make_token_indices(spec), spec["num_classes"])
+        assert got.dtype == np.float32 and got.shape == gold.shape, name
+        assert np.array_equal(got, gold), name
+    with pytest.raises(RuntimeError):
+        index_to_log_onehot_np(np.array([[0, 5]]), 5)
+
+
+def test_token_blend_oracle_matches_reference():
+    """oracle blend_with_sos_np == vqTransformer.py:117-141 evaluated on the stored draws."""
+    from cases import TOKEN_BLEND_CASES, make_token_indices
+    from oracle.vq_oracle import blend_with_sos_np
+    for name, spec in TOKEN_BLEND_CASES.items():
+        gold = load(name)
+        got = blend_with_sos_np(make_token_indices(spec), gold["mask"], gold["random_indices"], spec["sos_token"])
+        assert got.dtype == np.int64 and np.array_equal(got, gold["new_indices"]), name
+        assert (got[:, 0] == spec["sos_token"]).all()

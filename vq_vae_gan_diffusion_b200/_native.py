@@ -95,6 +95,8 @@ _SIGNATURES = {
     "vq_forward": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vq_backward": (_int, [_vp, ctypes.POINTER(_i64), _f32, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _f32, _i64, _vp, _vp, _vp]),
     "vq_embed_nchw": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _vp]),
+    "vq_index_to_log_onehot": (_int, [_vp, _i64, _i64, _int, _f32, _vp, _vp]),
+    "vq_mask_replace": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "vq_profile_enable": (_int, [_int]),
     "vq_profile_collect": (_int, [ctypes.POINTER(_f32), _int, ctypes.POINTER(_int)]),
     "vq_debug_timeline": (_int, [_vp, _int]),

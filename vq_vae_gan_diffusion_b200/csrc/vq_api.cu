@@ -17,6 +17,7 @@
 #include "vq_common.cuh"
 #include "vq_prep.cuh"
 #include "vq_select.cuh"
+#include "vq_tokens.cuh"
 
 #define VQ_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -517,5 +518,44 @@ VQ_EXPORT int vq_embed_nchw(const int64_t* idx, const float* E, int64_t B, int64
     else
         vq::vq_embed_nchw_kernel<false><<<grid, vq::kBwdThreads, 0, st>>>(idx, E, N, HW, K, out);
     VQ_LAUNCH_CHECK("vq_embed_nchw_kernel");
+    return VQ_OK;
+}
+
+VQ_EXPORT int vq_index_to_log_onehot(const int64_t* idx, int64_t B, int64_t L, int num_classes, float clamp_min, float* out,
+                                     vq_stream_t stream) {
+    g_launches = 0;
+    if (B < 0 || L < 0 || num_classes < 1) return fail(VQ_E_INVALID, "bad shape B=%lld L=%lld num_classes=%d", (long long)B, (long long)L, num_classes);
+    if (B == 0 || L == 0) return VQ_OK;
+    if (!idx || !out) return fail(VQ_E_INVALID, "null pointer");
+    DevInfo* dev;
+    int rc = device_info(&dev);
+    if (rc != VQ_OK) return rc;
+    const bool vec = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int64_t threads = vec ? B * (L / 4) : B * L;
+    const int64_t gx = (threads + vq::kTokThreads - 1) / vq::kTokThreads;
+    const int64_t gy = (num_classes + vq::kTokClassTile - 1) / vq::kTokClassTile;
+    if (gx > 0x7fffffffLL || gy > 65535) return fail(VQ_E_UNSUPPORTED, "one-hot grid %lld x %lld too large", (long long)gx, (long long)gy);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const dim3 grid((unsigned)gx, (unsigned)gy);
+    if (vec) vq::vq_log_onehot_kernel<true><<<grid, vq::kTokThreads, 0, st>>>(idx, B, L, num_classes, clamp_min, out);
+    else     vq::vq_log_onehot_kernel<false><<<grid, vq::kTokThreads, 0, st>>>(idx, B, L, num_classes, clamp_min, out);
+    VQ_LAUNCH_CHECK("vq_log_onehot_kernel");
+    return VQ_OK;
+}
+
+VQ_EXPORT int vq_mask_replace(const int64_t* indices, const float* mask, const int64_t* random_indices, int64_t sos_token,
+                              int64_t B, int64_t L, int64_t* out, vq_stream_t stream) {
+    g_launches = 0;
+    if (B < 0 || L < 0) return fail(VQ_E_INVALID, "bad shape B=%lld L=%lld", (long long)B, (long long)L);
+    if (B == 0) return VQ_OK;
+    if (!out || (L > 0 && (!indices || !mask || !random_indices))) return fail(VQ_E_INVALID, "null pointer");
+    DevInfo* dev;
+    int rc = device_info(&dev);
+    if (rc != VQ_OK) return rc;
+    const int64_t gx = (B * (L + 1) + vq::kTokThreads - 1) / vq::kTokThreads;
+    if (gx > 0x7fffffffLL) return fail(VQ_E_UNSUPPORTED, "token grid %lld too large", (long long)gx);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    vq::vq_mask_replace_kernel<<<(unsigned)gx, vq::kTokThreads, 0, st>>>(indices, mask, random_indices, sos_token, B, L, out);
+    VQ_LAUNCH_CHECK("vq_mask_replace_kernel");
     return VQ_OK;
 }
