@@ -46,6 +46,24 @@ def test_host_side_validation_without_gpu():
     assert L.vq_forward(None, 4, 4, 256, None, None, None, None, 16, 0.25, None, None, None, None, None, None, 0, None) == -1
 
 
+def test_token_entry_points_validate_without_gpu():
+    L = _native.lib()
+    assert L.vq_index_to_log_onehot(None, -1, 4, 8, 1e-30, None, None) == -1      # VQ_E_INVALID: negative shape
+    assert L.vq_index_to_log_onehot(None, 2, 4, 0, 1e-30, None, None) == -1       # num_classes < 1
+    assert b"num_classes" in L.vq_last_error()
+    assert L.vq_index_to_log_onehot(None, 0, 4, 8, 1e-30, None, None) == 0        # empty batch: nothing to launch
+    assert L.vq_index_to_log_onehot(None, 2, 4, 8, 1e-30, None, None) == -1       # null pointers
+    assert L.vq_mask_replace(None, None, None, 0, -1, 4, None, None) == -1
+    assert L.vq_mask_replace(None, None, None, 0, 0, 4, None, None) == 0
+    assert L.vq_mask_replace(None, None, None, 0, 2, 4, None, None) == -1
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vq.index_to_log_onehot(torch.zeros((2, 3), dtype=torch.int64), 4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vq.mask_and_replace(torch.zeros((2, 3), dtype=torch.int64), 0.5, 16, 0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vq.blend_with_sos(torch.zeros((2, 3), dtype=torch.int64), torch.ones(2, 3), torch.zeros((2, 3), dtype=torch.int64), 0)
+
+
 def test_module_has_no_cpu_path():
     cb = vq.CodeBook(32, 256)
     assert list(cb.state_dict().keys()) == ["codebook.weight"]
