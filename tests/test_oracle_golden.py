@@ -290,3 +290,27 @@ def test_token_blend_oracle_matches_reference():
         got = blend_with_sos_np(make_token_indices(spec), gold["mask"], gold["random_indices"], spec["sos_token"])
         assert got.dtype == np.int64 and np.array_equal(got, gold["new_indices"]), name
         assert (got[:, 0] == spec["sos_token"]).all()
+
+
+def test_token_oracles_against_torch_cpu_ops():
+    """Random shapes: the numpy restatements against the reference's op sequence evaluated with torch on CPU."""
+    import torch
+    from oracle.vq_oracle import blend_with_sos_np, index_to_log_onehot_np
+    rng = np.random.default_rng(9)
+    for _ in range(12):
+        nd = int(rng.integers(1, 4))
+        shape = tuple(int(v) for v in rng.integers(1, 9, size=nd))
+        C = int(rng.integers(1, 40))
+        x = rng.integers(0, C, size=shape, dtype=np.int64)
+        xt = torch.from_numpy(x)
+        onehot = torch.nn.functional.one_hot(xt, C).permute((0, -1) + tuple(range(1, xt.dim())))      # vq_diffusion.py:31-33
+        exp = torch.log(onehot.float().clamp(min=1e-30)).numpy()                                       # :34
+        assert np.array_equal(index_to_log_onehot_np(x, C), exp)
+    for _ in range(6):
+        B, L, V = int(rng.integers(1, 6)), int(rng.integers(1, 50)), int(rng.integers(2, 2000))
+        idx = torch.from_numpy(rng.integers(0, V, size=(B, L), dtype=np.int64))
+        mask_f = torch.bernoulli(0.5 * torch.ones(B, L))
+        rnd = torch.randint_like(idx, high=V)
+        m = mask_f.round().to(dtype=torch.int64)
+        exp = torch.cat(((torch.ones(B, 1) * 7).long(), m * idx + (1 - m) * rnd), dim=1)              # vqTransformer.py:117-141
+        assert np.array_equal(blend_with_sos_np(idx.numpy(), mask_f.numpy(), rnd.numpy(), 7), exp.numpy())
