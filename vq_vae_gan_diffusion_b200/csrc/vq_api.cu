@@ -140,7 +140,7 @@ struct Workspace {
     uint32_t* out_q;        // (N, kOutCap) candidate entries (chunk << 8 | quad mask)
     double* loss_partial;   // (ceil(N/32))
     unsigned int* blocks_done;   // (1) + padding; zeroed by vq_forward
-    int32_t* fb_rows;            // (2N) rows needing the exact full scan (a row may be listed once per group)
+    int32_t* fb_rows;            // (2N) rows needing the exact full scan (the GEMM lists each row once)
     int32_t* fb_count;           // (1)
     float4* fb_part;             // (kFbMaxGroups * kFbGroup, kFbMaxParts)
     unsigned int* fb_arrive;     // (kFbMaxGroups)
