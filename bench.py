@@ -17,9 +17,11 @@ buffers (H2D of z and g_out -- double buffered on a copy stream -- and D2H of lo
 against the measured bf16 tensor peak, `cpu_baseline` = the torch-CPU port of the reference (same ATen ops) timed on this box's
 host cores on a bounded row sample.
 
---impl reference: the reference arm.  The reference is pure Python/PyTorch and cannot travel to the GPU box, so this
-arm times the oracle port (oracle/vq_oracle.py: torch_cpu_step, the same ATen op sequence as codebook.py, on all
-host threads) on a bounded sample of the same workload.
+--impl reference: the reference arm.  Times the UNMODIFIED reference class (network/vqvae/submodule/codebook.py, staged
+byte for byte under git-ignored baseline/_ref/ by tools/stage_reference.py -- the reference is pure Python, there is
+nothing to pip-install) on the box's host cores, all threads (torchrun exports OMP_NUM_THREADS=1: overridden), on a bounded
+row sample of the same workload (`kind: "reference"`; the torch-CPU port of the oracle, `kind: "port"`, only if the staged
+tree is missing).
 """
 from __future__ import annotations
 
@@ -127,7 +129,7 @@ class ClockSampler:
                 continue
             try:
                 mx = float(parts[1])
-                if t0 - 0.05 <= ts <= t1 + 0.15:
+                if t0 <= ts <= t1:
                     mhz.append(float(parts[0]))
                     for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
                         if v.lower().startswith("active"):
@@ -136,6 +138,31 @@ class ClockSampler:
                 continue
         return {"sm_mhz": statistics.median(mhz) if mhz else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
                 "samples": len(mhz)}
+
+
+def bind_host_memory_to_gpu_node(local_rank: int):
+    """Prefer the NUMA node of this rank's GPU for the memory this process allocates from now on (set_mempolicy
+    MPOL_PREFERRED through the raw syscall: libnuma is not in the image), and report what was done.  Best effort."""
+    import ctypes
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+    except Exception as e:                                   # pragma: no cover
+        return {"node": None, "bound": False, "why": f"no numa_node for the GPU ({type(e).__name__})"}
+    if node < 0:
+        return {"node": node, "bound": False, "why": "single-node host"}
+    try:
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238            # x86_64
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))
+        return {"node": node, "bound": rc == 0, "why": None if rc == 0 else f"set_mempolicy errno {ctypes.get_errno()}"}
+    except Exception as e:                                   # pragma: no cover
+        return {"node": node, "bound": False, "why": type(e).__name__}
 
 
 def make_latents(torch, dev, B, H, W, K, distribution, seed):
@@ -154,41 +181,99 @@ def make_latents(torch, dev, B, H, W, K, distribution, seed):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_step(z_np, E_np, g_np, tokenizer):
-    """One fwd(+bwd) of the torch-CPU port of the reference (oracle/vq_oracle.py: torch_cpu_step): the same ATen op
-    sequence the reference issues, on all host threads."""
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm is meant to use every host core."""
     import torch
-    from oracle.vq_oracle import torch_cpu_step
-    z = torch.from_numpy(z_np)
-    E = torch.from_numpy(E_np)
-    g = None if tokenizer else torch.from_numpy(g_np).view(z.shape[0], 1, 1, -1).permute(0, 3, 1, 2)
-    return torch_cpu_step(z, E, g, BETA, indices_only=tokenizer)[1]
+    n = os.cpu_count() or 1
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    os.environ.pop("OMP_NUM_THREADS", None)
+    torch.set_num_threads(n)
+    return torch.get_num_threads()
 
 
-def time_cpu_port(wl, distribution, sample_rows, budget_s, reps_min=1):
-    """numpy/BLAS port of the reference on a bounded row sample of the workload -> latents/s."""
-    import numpy as np
-    K = wl["K"]
-    rng = np.random.default_rng(1234)
-    n = min(sample_rows, wl["B"] * wl["H"] * wl["W"])
-    if distribution == "init":
-        E = rng.uniform(-1.0 / K, 1.0 / K, size=(K, D)).astype(np.float32)
-        zf = rng.standard_normal((n, D), dtype=np.float32)
-    else:
-        E = rng.standard_normal((K, D), dtype=np.float32)
-        zf = E[rng.integers(0, K, size=n)] + np.float32(0.3) * rng.standard_normal((n, D), dtype=np.float32)
-    z = np.ascontiguousarray(zf.reshape(n, 1, 1, D).transpose(0, 3, 1, 2))
-    g = rng.standard_normal((n, D), dtype=np.float32)
-    tok = bool(wl.get("tokenizer"))
-    cpu_port_step(z[:256], E, g[:256], tok)                 # warm-up (BLAS thread pool, page faults)
+def load_reference_class():
+    """The unmodified reference CodeBook from the staged tree (baseline/_ref) or, in the build container, /root/reference."""
+    import importlib.util
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from stage_reference import staged_root
+    root = staged_root()
+    if root is None:
+        return None
+    spec = importlib.util.spec_from_file_location("_reference_codebook_unmodified",
+                                                  os.path.join(root, "network", "vqvae", "submodule", "codebook.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.CodeBook
+
+
+class CpuArm:
+    """fwd(+bwd) of the reference's CPU path on a bounded sample of the workload (rows are independent)."""
+
+    def __init__(self, wl, distribution, sample_rows):
+        import numpy as np
+        import torch
+        self.torch = torch
+        self.threads = use_all_host_threads()
+        K, H, W = wl["K"], wl["H"], wl["W"]
+        self.tok = bool(wl.get("tokenizer"))
+        n_total = wl["B"] * H * W
+        items = max(1, min(sample_rows, n_total) // (H * W))
+        self.n = items * H * W
+        self.n_total = n_total
+        rng = np.random.default_rng(1234)
+        if distribution == "init":
+            E = rng.uniform(-1.0 / K, 1.0 / K, size=(K, D)).astype(np.float32)
+            zf = rng.standard_normal((self.n, D), dtype=np.float32)
+        else:
+            E = rng.standard_normal((K, D), dtype=np.float32)
+            zf = E[rng.integers(0, K, size=self.n)] + np.float32(0.3) * rng.standard_normal((self.n, D), dtype=np.float32)
+        self.z = torch.from_numpy(np.ascontiguousarray(zf.reshape(items, H, W, D).transpose(0, 3, 1, 2)))
+        self.g = torch.from_numpy(rng.standard_normal((items, H, W, D), dtype=np.float32)).permute(0, 3, 1, 2)
+        self.E = torch.from_numpy(E)
+        cls = load_reference_class()
+        self.kind = "reference" if cls is not None else "port"
+        if cls is not None:
+            self.module = cls(num_codebook_vectors=K, latent_dim=D)
+            with torch.no_grad():
+                self.module.codebook.weight.copy_(self.E)
+
+    def step(self):
+        torch = self.torch
+        if self.kind == "port":
+            from oracle.vq_oracle import torch_cpu_step
+            return torch_cpu_step(self.z, self.E, None if self.tok else self.g, BETA, indices_only=self.tok)[1]
+        if self.tok:                                         # what VQTransformer.encode_to_z runs: the full forward under no_grad
+            with torch.no_grad():
+                return self.module(self.z)[1]
+        self.module.codebook.weight.grad = None
+        z = self.z.clone().requires_grad_(True)
+        z_q, idx, loss = self.module(z)                      # codebook.py:47-111
+        (loss + (z_q * self.g).sum()).backward()
+        return idx
+
+    def describe(self):
+        what = ("the unmodified reference class network/vqvae/submodule/codebook.py::CodeBook (staged in baseline/_ref)"
+                if self.kind == "reference" else "torch-CPU port of codebook.py (same ATen ops; staged reference tree missing)")
+        return (f"{self.n} of {self.n_total} latents per step (rows are independent), {what}, "
+                f"fwd{'' if self.tok else '+bwd'}, {self.threads} threads")
+
+
+def time_cpu_arm(arm, budget_s, reps_min=1, reps_max=20):
+    arm.step()                                               # warm-up (thread pool, page faults)
     times = []
     t_start = time.perf_counter()
-    while len(times) < reps_min or (time.perf_counter() - t_start < budget_s and len(times) < 20):
+    while len(times) < reps_min or (time.perf_counter() - t_start < budget_s and len(times) < reps_max):
         t0 = time.perf_counter()
-        cpu_port_step(z, E, g, tok)
+        arm.step()
         times.append(time.perf_counter() - t0)
-    best = min(times)
-    return n / best, best, n, len(times)
+    return times
+
+
+def cpu_sample_rows(wl):
+    return 16384 if wl["K"] >= 8192 else 65536
 
 
 def run_reference_arm(args):
@@ -196,27 +281,25 @@ def run_reference_arm(args):
     if rank != 0:
         return 0
     wl = WORKLOADS[args.workload]
-    cores = os.cpu_count() or 1
-    sample = 16384 if wl["K"] >= 8192 else 65536
-    n_total = wl["B"] * wl["H"] * wl["W"]
-    sample = min(sample, n_total)
-    # warm-up passes then K timed steps, each a bounded sample
+    arm = CpuArm(wl, args.distribution, cpu_sample_rows(wl))
     for _ in range(max(args.warmup, 1)):
-        time_cpu_port(wl, args.distribution, min(sample, 2048), 0.0)
+        arm.step()
     per_step = []
     for _ in range(args.steps):
-        v, t, n, _ = time_cpu_port(wl, args.distribution, sample, 0.0)
-        per_step.append(t)
+        t0 = time.perf_counter()
+        arm.step()
+        per_step.append(time.perf_counter() - t0)
     ms = 1e3 * sum(per_step) / len(per_step)
-    value = sample / (ms / 1e3)
+    value = arm.n / (ms / 1e3)
     line = {
-        "impl": "reference", "metric": "vq_latents_per_sec_fwd_bwd" if not wl.get("tokenizer") else "vq_latents_per_sec_tokenize",
+        "impl": "reference", "metric": "vq_latents_per_sec_fwd_bwd" if not arm.tok else "vq_latents_per_sec_tokenize",
         "value": value, "unit": "latents/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": args.workload + ": " + wl["desc"], "K": wl["K"], "D": D,
-                                        "distribution": args.distribution, "sample_rows_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": "latents/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} of {n_total} latents per step (rows are independent), torch-CPU port of codebook.py (same ATen ops)"},
+                                        "distribution": args.distribution, "sample_rows_per_step": arm.n,
+                                        "note": "a rate: each step is a bounded row sample of the workload (rows are independent), "
+                                                "timed on rank 0's host cores only, whatever --gpus says"},
+        "cpu_baseline": {"value": value, "unit": "latents/s", "cores": arm.threads, "kind": arm.kind, "sample": arm.describe()},
         "e2e": {"value": value, "unit": "latents/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -235,6 +318,9 @@ def main():
     ap.add_argument("--distribution", default="init", choices=["init", "trained"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--soak-seconds", type=float, default=2.0,
+                    help="after the timed region, keep stepping for about this long and report the distance-GEMM kernel's "
+                         "fraction of peak once clocks have settled under the power cap (roofline.frac_sustained_run); 0 = off")
     ap.add_argument("--strong", action="store_true",
                     help="strong scaling: the workload's batch is the GLOBAL batch, split evenly over the ranks (default: weak, "
                          "the batch is per GPU)")
@@ -332,9 +418,31 @@ def main():
     clocks = sampler.summary(t_wall0, t_wall1) if rank == 0 else None
     stats = cb.stats_dict()
 
+    # ---- soak: the same step back to back for a few seconds; the kernel time of the LAST steps is what a long training
+    #      run sees once the SM clock has settled under the 1 kW cap (reported next to the burst figure, not instead of it)
+    soak = None
+    if args.soak_seconds > 0 and world == 1 and not tok:
+        n_soak = max(int(args.soak_seconds * 1e3 / ms_step), 400)
+        for _ in range(n_soak - 300):
+            step(z_req, g_out)
+        _native.profile_enable(True)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(300):
+            step(z_req, g_out)
+        s1.record()
+        torch.cuda.synchronize()
+        soak_gemm = _native.profile_collect()
+        _native.profile_enable(False)
+        soak = {"steps": n_soak, "ms_per_step_last_300": s0.elapsed_time(s1) / 300,
+                "gemm_ms_last_300": sum(soak_gemm) / max(len(soak_gemm), 1)}
+
     # ---- end to end: host buffers in, loss + indices out, copies inside the timed region
     e2e = None
     if not args.no_e2e:
+        # pinned host buffers on the NUMA node this GPU hangs off (best effort): with eight ranks pinning 537 MB each on
+        # one node, the far socket's GPUs would pull their inputs across the inter-socket link
+        numa = bind_host_memory_to_gpu_node(local_rank)
         z_host = z.cpu().pin_memory()
         # upstream gradient in channels-last memory (the layout of z_q, which is what flows back from post_quant_conv)
         g_host = None if tok else g_out.permute(0, 2, 3, 1).contiguous().cpu().pin_memory()
@@ -393,7 +501,7 @@ def main():
         h2d = z_host.numel() * 4 + (0 if tok else g_host.numel() * 4)
         d2h = N * 8 + (0 if tok else 4)
         e2e = {"value": N * world / (ms_e2e / 1e3), "unit": "latents/s", "ms_per_step": ms_e2e,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "host_numa": numa}
 
     if rank != 0:
         if world > 1:
@@ -422,14 +530,19 @@ def main():
         bytes_per_latent = 1032 if tok else 5136
         roofline["step_hbm_gbs_algorithmic"] = N * bytes_per_latent / (ms_step / 1e3) / 1e9
         roofline["hbm_peak_gbs"] = peaks["hbm_gbs"]
+        if soak is not None and soak["gemm_ms_last_300"] > 0:
+            ach_s = flops / (soak["gemm_ms_last_300"] / 1e3) / 1e12
+            roofline["frac_sustained_run"] = ach_s / peaks["bf16_tflops"]
+            roofline["sustained_run"] = dict(soak, achieved=ach_s, frac_of_sustained_peak=ach_s / peaks["bf16_tflops_sustained"]
+                                             if peaks["bf16_tflops_sustained"] else None,
+                                             latents_per_s=N / (soak["ms_per_step_last_300"] / 1e3))
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:              # reported at N=1 only (tier contract)
-        sample = 16384 if K >= 8192 else min(N, 65536)
-        v, tbest, n, reps = time_cpu_port(wl, args.distribution, sample, budget_s=12.0)
-        cpu_baseline = {"value": v, "unit": "latents/s", "cores": os.cpu_count(), "kind": "port",
-                        "sample": f"best of {reps} passes over {n} of {N} latents (rows independent; torch-CPU port "
-                                  f"of codebook.py fwd{'' if tok else '+bwd'}), {tbest*1e3:.0f} ms per pass"}
+        arm = CpuArm(wl, args.distribution, cpu_sample_rows(wl))
+        times = time_cpu_arm(arm, budget_s=12.0)
+        cpu_baseline = {"value": arm.n / min(times), "unit": "latents/s", "cores": arm.threads, "kind": arm.kind,
+                        "sample": f"best of {len(times)} passes, {min(times)*1e3:.0f} ms per pass: " + arm.describe()}
 
     line = {
         "metric": "vq_latents_per_sec_fwd_bwd" if not tok else "vq_latents_per_sec_tokenize",

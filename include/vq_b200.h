@@ -145,6 +145,24 @@ int vq_backward(const float* gout, const int64_t* gout_strides_host, float g_los
                 float* grad_z_nchw, float* grad_E, vq_stream_t stream);
 
 /*
+ * vq_backward with two extras (new in this build; the reference trains on one device with autograd's own kernels):
+ *   grad_E_scale   factor applied to the codebook gradient only -- 1/W when W data-parallel ranks SUM their
+ *                  gradients, so that the sum is the gradient of the mean loss over the global batch while grad_z and
+ *                  the returned loss stay the local-mean quantities DDP expects (see dist.py);
+ *   deterministic  non-zero: the scatter-add of grad_E (embedding_dense_backward in the reference, whose CUDA kernel
+ *                  is itself order-dependent) runs in 64-bit fixed point -- integer addition is associative, so the
+ *                  result is bit-reproducible from run to run whatever order the atomics land in; needs `workspace`
+ *                  of vq_backward_workspace_bytes(K, D) bytes (256-byte aligned).  0: red.global.add.v4.f32, no
+ *                  workspace needed (may be NULL).
+ */
+int vq_backward_workspace_bytes(int K, int D, size_t* out_host);
+int vq_backward_ex(const float* gout, const int64_t* gout_strides_host, float g_loss, const float* g_loss_dev,
+                   const float* z_nchw, const int64_t* idx, const float* E,
+                   int64_t B, int64_t HW, int D, int K, float beta, int64_t n_global,
+                   float grad_E_scale, int deterministic, float* grad_z_nchw, float* grad_E,
+                   void* workspace, size_t workspace_bytes, vq_stream_t stream);
+
+/*
  * Index -> embedding lookup in NCHW layout (the decode side: codebook(indices).reshape(B,h,w,D).permute(0,3,1,2),
  * worker/vqganVqvaeWorker.py:459, network/vqTransformer/vqTransformer.py:98).
  *   out_nchw (B, D, HW) fp32
@@ -168,6 +186,9 @@ int vq_embed_nchw(const int64_t* idx, const float* E, int64_t B, int64_t HW, int
  */
 int vq_index_to_log_onehot(const int64_t* idx, int64_t B, int64_t L, int num_classes, float clamp_min, float* out,
                            vq_stream_t stream);
+/* vq_log_onehot_to_index replaces log_onehot_to_index(log_x) = log_x.argmax(1) (network/vq_diffusion/vq_diffusion.py:37-38):
+ *   log_x (B, num_classes, L) fp32 contiguous -> out (B, L) int64, first maximum, a NaN counts as the maximum (torch.argmax). */
+int vq_log_onehot_to_index(const float* log_x, int64_t B, int64_t L, int num_classes, int64_t* out, vq_stream_t stream);
 int vq_mask_replace(const int64_t* indices, const float* mask, const int64_t* random_indices, int64_t sos_token,
                     int64_t B, int64_t L, int64_t* out, vq_stream_t stream);
 

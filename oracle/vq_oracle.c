@@ -85,29 +85,20 @@ VQO_API void vq_oracle_row_norms(const float* X, int64_t R, int D, float* out) {
     for (int64_t r = 0; r < R; r++) out[r] = vqo_dot(X + r * D, 1, X + r * D, 1, D);
 }
 
-/*
- * Full forward.  z_nchw is contiguous (B, D, HW).  Any output pointer may be NULL.
- *   zq_nhwc  (N, D)   straight-through value fl(z + fl(e - z))
- *   idx      (N)      int64 argmin, first minimum
- *   loss     (1)      fp32
- *   hist     (K)      int64 bincount(idx)
- *   dist_min (N)      fp32 minimal distance (diagnostic)
- *   tie_rows (1)      rows whose minimal fp32 distance is attained by >= 2 codes
- */
-VQO_API int vq_oracle_forward(const float* z_nchw, int64_t B, int64_t HW, int D,
-                              const float* E, int K, float beta,
-                              float* zq_nhwc, int64_t* idx, float* loss, int64_t* hist,
-                              float* dist_min, uint64_t* tie_rows) {
-    if (B < 0 || HW < 0 || D <= 0 || K <= 0) return -1;
-    const int64_t N = B * HW;
-    float* e2 = (float*)malloc(sizeof(float) * (size_t)K);
-    int64_t* idx_local = idx ? idx : (int64_t*)malloc(sizeof(int64_t) * (size_t)(N > 0 ? N : 1));
-    if (!e2 || !idx_local) return -2;
-    vq_oracle_row_norms(E, K, D, e2);
+/* torch.argmin bookkeeping for one more distance (codebook.py:82): NaN counts as smaller than every number, the FIRST
+ * minimal element wins; n_best counts the codes attaining the minimum (NaN == NaN for this purpose) */
+static inline void vqo_argmin_step(int64_t k, float dist, float* best, int64_t* best_k, int* n_best) {
+    if (k == 0) { *best = dist; *best_k = k; *n_best = 1; }
+    else if (isnan(*best)) { if (isnan(dist)) (*n_best)++; }
+    else if (isnan(dist) || dist < *best) { *best = dist; *best_k = k; *n_best = 1; }
+    else if (dist == *best) (*n_best)++;
+}
 
+/* scalar argmin stage: the definition */
+static void vqo_argmin_scalar(const float* z_nchw, int64_t N, int64_t HW, int D, const float* E, const float* e2, int K,
+                              int64_t* idx, float* dist_min, uint64_t* tie_rows) {
     uint64_t ties = 0;
-    double sq_sum = 0.0;
-#pragma omp parallel for schedule(dynamic, 16) reduction(+ : ties, sq_sum)
+#pragma omp parallel for schedule(dynamic, 16) reduction(+ : ties)
     for (int64_t n = 0; n < N; n++) {
         const int64_t b = n / HW, hw = n % HW;
         const float* zr = z_nchw + b * (int64_t)D * HW + hw; /* element stride HW */
@@ -117,18 +108,128 @@ VQO_API int vq_oracle_forward(const float* z_nchw, int64_t B, int64_t HW, int D,
         int n_best = 0;
         for (int k = 0; k < K; k++) {
             const float dot = vqo_dot(zr, HW, E + (int64_t)k * D, 1, D);
-            const float dist = vqo_dist(z2, e2[k], dot);
-            /* torch.argmin semantics (codebook.py:82): NaN counts as smaller than every number, the FIRST minimal
-             * element wins; n_best counts the codes attaining the minimum (NaN == NaN for this purpose) */
-            if (k == 0) { best = dist; best_k = k; n_best = 1; }
-            else if (isnan(best)) { if (isnan(dist)) n_best++; }
-            else if (isnan(dist) || dist < best) { best = dist; best_k = k; n_best = 1; }
-            else if (dist == best) n_best++;
+            vqo_argmin_step(k, vqo_dist(z2, e2[k], dot), &best, &best_k, &n_best);
         }
-        idx_local[n] = best_k;
+        idx[n] = best_k;
         if (dist_min) dist_min[n] = best;
         if (n_best > 1) ties++;
-        const float* e = E + best_k * D;
+    }
+    *tie_rows = ties;
+}
+
+/*
+ * Vectorised argmin stage (AVX2 + FMA, 16 codes per step): the SAME arithmetic per (row, code) pair as the scalar stage
+ * -- every SIMD lane runs vqo_dot's four fma chains over d == j (mod 4) in ascending d, then (p0 + p1) + (p2 + p3), then
+ * vqo_dist -- with the codes of a block spread over the lanes, so the results are bit-identical (tests/test_oracle_golden.py
+ * checks that on every case).  It exists so that the GPU tests can put ALL rows of the benchmarked configs
+ * (262 144 latents x 16 384 codes) through the oracle in seconds.  D must be a multiple of 4 (else the caller uses the
+ * scalar stage); the K % 16 remainder codes go through the scalar code.
+ */
+#if defined(__x86_64__)
+#include <immintrin.h>
+__attribute__((target("avx2,fma")))
+static void vqo_argmin_avx2(const float* z_nchw, int64_t N, int64_t HW, int D, const float* E, const float* e2, int K,
+                            int64_t* idx, float* dist_min, uint64_t* tie_rows) {
+    const int kb_n = K / 16;                                  /* full blocks of 16 codes */
+    /* Et[kb][d][16]: block-transposed codebook, so that one row value meets 16 codes per fma pair */
+    float* Et = (float*)aligned_alloc(64, sizeof(float) * (size_t)(kb_n > 0 ? kb_n : 1) * (size_t)D * 16);
+    if (!Et) { vqo_argmin_scalar(z_nchw, N, HW, D, E, e2, K, idx, dist_min, tie_rows); return; }
+#pragma omp parallel for schedule(static)
+    for (int kb = 0; kb < kb_n; kb++)
+        for (int d = 0; d < D; d++)
+            for (int l = 0; l < 16; l++) Et[((size_t)kb * D + d) * 16 + l] = E[(size_t)(kb * 16 + l) * D + d];
+    uint64_t ties = 0;
+#pragma omp parallel reduction(+ : ties)
+    {
+        float* zrow = (float*)aligned_alloc(64, sizeof(float) * (size_t)((D + 15) / 16 * 16));
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t n = 0; n < N; n++) {
+            const int64_t b = n / HW, hw = n % HW;
+            const float* zr = z_nchw + b * (int64_t)D * HW + hw;
+            for (int d = 0; d < D; d++) zrow[d] = zr[(int64_t)d * HW];
+            const float z2 = vqo_dot(zrow, 1, zrow, 1, D);
+            const __m256 z2v = _mm256_set1_ps(z2), two = _mm256_set1_ps(2.0f);
+            float best = INFINITY;
+            int64_t best_k = 0;
+            int n_best = 0;
+            for (int kb = 0; kb < kb_n; kb++) {
+                const float* et = Et + (size_t)kb * D * 16;
+                __m256 a0 = _mm256_setzero_ps(), a1 = a0, a2 = a0, a3 = a0, b0 = a0, b1 = a0, b2 = a0, b3 = a0;
+                for (int d = 0; d < D; d += 4) {
+                    const __m256 x0 = _mm256_set1_ps(zrow[d]), x1 = _mm256_set1_ps(zrow[d + 1]);
+                    const __m256 x2 = _mm256_set1_ps(zrow[d + 2]), x3 = _mm256_set1_ps(zrow[d + 3]);
+                    a0 = _mm256_fmadd_ps(x0, _mm256_load_ps(et + (d + 0) * 16), a0);
+                    b0 = _mm256_fmadd_ps(x0, _mm256_load_ps(et + (d + 0) * 16 + 8), b0);
+                    a1 = _mm256_fmadd_ps(x1, _mm256_load_ps(et + (d + 1) * 16), a1);
+                    b1 = _mm256_fmadd_ps(x1, _mm256_load_ps(et + (d + 1) * 16 + 8), b1);
+                    a2 = _mm256_fmadd_ps(x2, _mm256_load_ps(et + (d + 2) * 16), a2);
+                    b2 = _mm256_fmadd_ps(x2, _mm256_load_ps(et + (d + 2) * 16 + 8), b2);
+                    a3 = _mm256_fmadd_ps(x3, _mm256_load_ps(et + (d + 3) * 16), a3);
+                    b3 = _mm256_fmadd_ps(x3, _mm256_load_ps(et + (d + 3) * 16 + 8), b3);
+                }
+                /* (p0 + p1) + (p2 + p3);  fl(fl(z2 + e2) - fl(2 dot)) */
+                const __m256 dota = _mm256_add_ps(_mm256_add_ps(a0, a1), _mm256_add_ps(a2, a3));
+                const __m256 dotb = _mm256_add_ps(_mm256_add_ps(b0, b1), _mm256_add_ps(b2, b3));
+                float dist[16] __attribute__((aligned(32)));
+                _mm256_store_ps(dist, _mm256_sub_ps(_mm256_add_ps(z2v, _mm256_loadu_ps(e2 + kb * 16)), _mm256_mul_ps(two, dota)));
+                _mm256_store_ps(dist + 8, _mm256_sub_ps(_mm256_add_ps(z2v, _mm256_loadu_ps(e2 + kb * 16 + 8)), _mm256_mul_ps(two, dotb)));
+                for (int l = 0; l < 16; l++) vqo_argmin_step((int64_t)kb * 16 + l, dist[l], &best, &best_k, &n_best);
+            }
+            for (int k = kb_n * 16; k < K; k++) {
+                const float dot = vqo_dot(zrow, 1, E + (int64_t)k * D, 1, D);
+                vqo_argmin_step(k, vqo_dist(z2, e2[k], dot), &best, &best_k, &n_best);
+            }
+            idx[n] = best_k;
+            if (dist_min) dist_min[n] = best;
+            if (n_best > 1) ties++;
+        }
+        free(zrow);
+    }
+    free(Et);
+    *tie_rows = ties;
+}
+static int vqo_have_avx2(void) { return __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma"); }
+#else
+static int vqo_have_avx2(void) { return 0; }
+#endif
+
+/* 1 when vq_oracle_forward(..., fast = 1) really runs the vectorised stage on this host */
+VQO_API int vq_oracle_has_fast_path(void) { return vqo_have_avx2(); }
+
+/*
+ * Full forward.  z_nchw is contiguous (B, D, HW).  Any output pointer may be NULL.
+ *   zq_nhwc  (N, D)   straight-through value fl(z + fl(e - z))
+ *   idx      (N)      int64 argmin, first minimum
+ *   loss     (1)      fp32
+ *   hist     (K)      int64 bincount(idx)
+ *   dist_min (N)      fp32 minimal distance (diagnostic)
+ *   tie_rows (1)      rows whose minimal fp32 distance is attained by >= 2 codes
+ *   fast              0: scalar argmin stage (the definition); 1: the vectorised stage when the host has AVX2 + FMA
+ */
+VQO_API int vq_oracle_forward(const float* z_nchw, int64_t B, int64_t HW, int D,
+                              const float* E, int K, float beta,
+                              float* zq_nhwc, int64_t* idx, float* loss, int64_t* hist,
+                              float* dist_min, uint64_t* tie_rows, int fast) {
+    if (B < 0 || HW < 0 || D <= 0 || K <= 0) return -1;
+    const int64_t N = B * HW;
+    float* e2 = (float*)malloc(sizeof(float) * (size_t)K);
+    int64_t* idx_local = idx ? idx : (int64_t*)malloc(sizeof(int64_t) * (size_t)(N > 0 ? N : 1));
+    if (!e2 || !idx_local) return -2;
+    vq_oracle_row_norms(E, K, D, e2);
+
+    uint64_t ties = 0;
+#if defined(__x86_64__)
+    if (fast && D % 4 == 0 && vqo_have_avx2()) vqo_argmin_avx2(z_nchw, N, HW, D, E, e2, K, idx_local, dist_min, &ties);
+    else
+#endif
+        vqo_argmin_scalar(z_nchw, N, HW, D, E, e2, K, idx_local, dist_min, &ties);
+
+    double sq_sum = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : sq_sum)
+    for (int64_t n = 0; n < N; n++) {
+        const int64_t b = n / HW, hw = n % HW;
+        const float* zr = z_nchw + b * (int64_t)D * HW + hw;
+        const float* e = E + idx_local[n] * D;
         for (int d = 0; d < D; d++) {
             const float zv = zr[(int64_t)d * HW];
             volatile float diff = e[d] - zv;               /* fl(e - z) */

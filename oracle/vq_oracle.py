@@ -54,8 +54,9 @@ class COracle:
         L.vq_oracle_row_norms.argtypes = [_f32p, ctypes.c_int64, ctypes.c_int, _f32p]
         L.vq_oracle_row_norms.restype = None
         L.vq_oracle_forward.argtypes = [_f32p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _f32p, ctypes.c_int,
-                                        ctypes.c_float, _f32p, _i64p, _f32p, _i64p, _f32p, _u64p]
+                                        ctypes.c_float, _f32p, _i64p, _f32p, _i64p, _f32p, _u64p, ctypes.c_int]
         L.vq_oracle_forward.restype = ctypes.c_int
+        L.vq_oracle_has_fast_path.restype = ctypes.c_int
         L.vq_oracle_pair_dist.argtypes = [_f32p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, _f32p, _i64p, _i64p,
                                           ctypes.c_int64, _f32p]
         L.vq_oracle_pair_dist.restype = None
@@ -76,8 +77,15 @@ class COracle:
         self.lib.vq_oracle_row_norms(_p(X, _f32p), X.shape[0], X.shape[1], _p(out, _f32p))
         return out
 
-    def forward(self, z: np.ndarray, E: np.ndarray, beta: float = 0.25, want_zq: bool = True):
-        """z: (B, D, H, W) fp32, E: (K, D) fp32 -> dict(zq_nhwc (N,D), idx, loss, hist, dist_min, tie_rows)."""
+    @property
+    def has_fast_path(self) -> bool:
+        return bool(self.lib.vq_oracle_has_fast_path())
+
+    def forward(self, z: np.ndarray, E: np.ndarray, beta: float = 0.25, want_zq: bool = True, fast: bool = False):
+        """z: (B, D, H, W) fp32, E: (K, D) fp32 -> dict(zq_nhwc (N,D), idx, loss, hist, dist_min, tie_rows).
+
+        ``fast`` runs the argmin stage vectorised over codes (AVX2 + FMA, same arithmetic per pair, bit-identical
+        results -- tests/test_oracle_golden.py); used for the full-size GPU parity tests."""
         z = np.ascontiguousarray(z, dtype=np.float32)
         E = np.ascontiguousarray(E, dtype=np.float32)
         B, D = z.shape[0], z.shape[1]
@@ -92,7 +100,8 @@ class COracle:
         dmin = np.empty(N, np.float32)
         ties = ctypes.c_uint64(0)
         rc = self.lib.vq_oracle_forward(_p(z, _f32p), B, HW, D, _p(E, _f32p), K, beta, _p(zq, _f32p), _p(idx, _i64p),
-                                        _p(loss, _f32p), _p(hist, _i64p), _p(dmin, _f32p), ctypes.byref(ties))
+                                        _p(loss, _f32p), _p(hist, _i64p), _p(dmin, _f32p), ctypes.byref(ties),
+                                        1 if fast else 0)
         if rc != 0:
             raise RuntimeError(f"vq_oracle_forward rc={rc}")
         return dict(zq_nhwc=zq, idx=idx, loss=np.float32(loss[0]), hist=hist, dist_min=dmin, tie_rows=int(ties.value))
@@ -239,6 +248,12 @@ def index_to_log_onehot_np(x: np.ndarray, num_classes: int) -> np.ndarray:
     onehot = (x[..., None] == np.arange(num_classes, dtype=np.int64)).astype(np.float32)  # F.one_hot(...).float()  :31/:56
     order = (0, x.ndim) + tuple(range(1, x.ndim))                                         # permute_order  :32/:57
     return np.log(np.maximum(onehot.transpose(order), np.float32(1e-30)))                 # log(clamp(min=1e-30))  :34/:59
+
+
+def log_onehot_to_index_np(log_x: np.ndarray) -> np.ndarray:
+    """network/vq_diffusion/vq_diffusion.py:37-38: log_x.argmax(1) -- first maximal class, a NaN counts as the maximum
+    (torch.argmax and numpy.argmax agree on both rules)."""
+    return np.argmax(np.asarray(log_x, dtype=np.float32), axis=1).astype(np.int64)
 
 
 def blend_with_sos_np(indices: np.ndarray, mask: np.ndarray, random_indices: np.ndarray, sos_token: int) -> np.ndarray:

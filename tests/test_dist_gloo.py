@@ -1,7 +1,9 @@
 """World-size-2 CPU (gloo) tests of the data-parallel path: batch-sharded latents, replicated codebook, ONE exchange
-step (SUM all-reduce of grad_E and of [hist | loss | 1]).  The compute on each rank is the CPU oracle (the CUDA
-module has no CPU path); what is under test is the host logic of vq_vae_gan_diffusion_b200/dist.py and the
-n_global convention of the backward: summed shard gradients == single-device gradient on the concatenated batch.
+step (a SUM all-reduce of the flat buffer [grad_E / W | hist | loss | 1]).  The compute on each rank is the CPU oracle
+(the CUDA module has no CPU path); what is under test is the host logic of vq_vae_gan_diffusion_b200/dist.py and its
+gradient convention: local-mean loss and grad_z per rank (what DDP-averaged upstream layers expect), codebook gradient
+averaged over ranks == single-device gradient on the concatenated batch -- stand-alone (DataParallelVQ) and inside a
+DistributedDataParallel-wrapped model.  The same checks run on the CUDA kernels in tests/test_gpu_dist.py.
 """
 import os
 import sys
@@ -32,8 +34,8 @@ class OracleCodeBook(torch.nn.Module):
         with torch.no_grad():
             self.codebook.weight.copy_(torch.from_numpy(E))
         self.beta = beta
-        self.grad_world_size = 1
-        self.grad_hook = None
+        self.grad_scale = 1.0
+        self.grad_alloc = None
         self.last_histogram = None
 
     def forward(self, z):
@@ -55,18 +57,21 @@ class OracleCodeBook(torch.nn.Module):
             @staticmethod
             def backward(ctx, g_zq, _gi, g_loss):
                 z, w = ctx.saved_tensors
-                n_global = ctx.idx.size * mod.grad_world_size
                 g = None if g_zq is None else np.ascontiguousarray(g_zq.numpy())
-                gz, gE = mod.oracle.backward(g, float(g_loss), z.detach().numpy(), ctx.idx, w.detach().numpy(), mod.beta,
-                                             n_global=n_global)
-                return torch.from_numpy(gz), torch.from_numpy(gE)
+                gz, gE = mod.oracle.backward(g, float(g_loss), z.detach().numpy(), ctx.idx, w.detach().numpy(), mod.beta)
+                gE_t = torch.from_numpy(gE) * mod.grad_scale          # vq_backward_ex's grad_E_scale
+                if mod.grad_alloc is not None:                        # ... written where the wrapper wants it
+                    out = mod.grad_alloc(gE_t.shape[0], gE_t.shape[1], gE_t.device)
+                    out.copy_(gE_t)
+                    gE_t = out
+                return torch.from_numpy(gz), gE_t
 
         return Fn.apply(z, self.codebook.weight)
 
 
 def _worker(rank, world, init_file, out_file):
     from cases import CASES, make_inputs
-    from vq_vae_gan_diffusion_b200.dist import DataParallelVQ, allreduce_codebook, pack_stats, unpack_stats
+    from vq_vae_gan_diffusion_b200.dist import DataParallelVQ
     from oracle.vq_oracle import COracle
     dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
     try:
@@ -77,16 +82,7 @@ def _worker(rank, world, init_file, out_file):
         sl = slice(rank * (B // world), (rank + 1) * (B // world))
         orc = COracle()
 
-        # --- 1. the raw protocol: local oracle results -> one exchange -> global results
-        loc = orc.forward(z[sl], E, 0.25)
-        n_total = B * spec["H"] * spec["W"]
-        gz_loc, gE_loc = orc.backward(np.transpose(g[sl], (0, 3, 1, 2)), 1.0, z[sl], loc["idx"], E, 0.25, n_global=n_total)
-        gE_t = torch.from_numpy(gE_loc.copy())
-        stats = pack_stats(torch.from_numpy(loc["hist"]), torch.tensor(float(loc["loss"])))
-        allreduce_codebook(gE_t, stats)
-        hist_g, loss_g = unpack_stats(stats)
-
-        # --- 2. the wrapper: hooks, async all-reduce, wait()
+        # --- 1. the stand-alone wrapper: hook, ONE async all-reduce, wait()
         cb = OracleCodeBook(E)
         dp = DataParallelVQ(cb)
         zt = torch.from_numpy(z[sl].copy()).requires_grad_(True)
@@ -94,15 +90,65 @@ def _worker(rank, world, init_file, out_file):
         gt = torch.from_numpy(np.ascontiguousarray(np.transpose(g[sl], (0, 3, 1, 2))))
         torch.autograd.backward([z_q, loss], [gt, torch.tensor(1.0)])
         dp.wait()
+        gE_wrap = cb.codebook.weight.grad.numpy().copy()
+        hist_wrap, loss_wrap = dp.global_histogram.numpy(), float(dp.global_loss)
+
+        # gradient accumulation, DDP style: micro-steps under no_sync() accumulate LOCAL gradients, the last one exchanges
+        # the accumulated .grad (which is not aliased to the flat buffer then: the wrapper exchanges a packed copy)
+        cb.codebook.weight.grad = None
+        with dp.no_sync():
+            z_q, _, loss2 = dp(zt)
+            torch.autograd.backward([z_q, loss2], [gt, torch.tensor(1.0)])
+        z_q, _, loss2 = dp(zt)
+        torch.autograd.backward([z_q, loss2], [gt, torch.tensor(1.0)])
+        dp.wait()
+        gE_accum = cb.codebook.weight.grad.numpy().copy()
+
+        # evaluation step (no backward): histogram / loss still become global on demand
+        with torch.no_grad():
+            dp(zt)
+        hist_eval, loss_eval = dp.global_histogram.numpy(), float(dp.global_loss)
+
+        # --- 2. inside DistributedDataParallel, with a small encoder in front: nothing special is needed
+        torch.manual_seed(7)
+        D = spec["D"]
+        enc = torch.nn.Conv2d(D, D, 1)
+        cb2 = OracleCodeBook(E)
+
+        class Net(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.enc, self.cb = enc, cb2
+
+            def forward(self, x):
+                return self.cb(self.enc(x))
+
+        net = Net()
+        ddp = torch.nn.parallel.DistributedDataParallel(net)
+        xq, _, l2 = ddp(torch.from_numpy(z[sl].copy()))
+        (l2 + (xq * gt).sum()).backward()
+        ddp_gw = enc.weight.grad.numpy().copy()
+        ddp_gE = cb2.codebook.weight.grad.numpy().copy()
 
         if rank == 0:
             full = orc.forward(z, E, 0.25)
             gz_full, gE_full = orc.backward(np.transpose(g, (0, 3, 1, 2)), 1.0, z, full["idx"], E, 0.25)
-            np.savez(out_file, gE_proto=gE_t.numpy(), hist_proto=hist_g.numpy(), loss_proto=float(loss_g),
-                     gE_wrap=cb.codebook.weight.grad.numpy(), hist_wrap=dp.global_histogram.numpy(),
-                     loss_wrap=float(dp.global_loss), gz_wrap=zt.grad.numpy(),
-                     gE_full=gE_full, hist_full=full["hist"], loss_full=float(full["loss"]), gz_full=gz_full[sl],
-                     idx_ok=np.array_equal(idx.numpy(), full["idx"][: idx.numel()]))
+            loc = orc.forward(z[sl], E, 0.25)
+            gz_loc, _ = orc.backward(np.transpose(g[sl], (0, 3, 1, 2)), 1.0, z[sl], loc["idx"], E, 0.25)
+            # single-device run of the same net on the concatenated batch: objective = global-mean loss + (1/W) sum(z_q g),
+            # i.e. the average of the per-rank objectives
+            torch.manual_seed(7)
+            enc1 = torch.nn.Conv2d(D, D, 1)
+            cb1 = OracleCodeBook(E)
+            q1, _, l1 = cb1(enc1(torch.from_numpy(z.copy())))
+            g_all = torch.from_numpy(np.ascontiguousarray(np.transpose(g, (0, 3, 1, 2))))
+            (l1 + (q1 * g_all).sum() / world).backward()
+            np.savez(out_file, gE_wrap=gE_wrap, hist_wrap=hist_wrap, loss_wrap=loss_wrap, gz_wrap=zt.grad.numpy() / 3,
+                     gE_accum=gE_accum, hist_eval=hist_eval, loss_eval=loss_eval,
+                     gE_full=gE_full, hist_full=full["hist"], loss_full=float(full["loss"]), gz_loc=gz_loc,
+                     loss_local=float(loss.detach()), loss_loc_ref=float(loc["loss"]),
+                     idx_ok=np.array_equal(idx.numpy(), full["idx"][: idx.numel()]),
+                     ddp_gw=ddp_gw, ddp_gE=ddp_gE, one_gw=enc1.weight.grad.numpy(), one_gE=cb1.codebook.weight.grad.numpy())
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -115,18 +161,25 @@ def test_two_rank_gloo_exchange():
         out_file = os.path.join(td, "out.npz")
         mp.spawn(_worker, args=(2, init_file, out_file), nprocs=2, join=True)
         r = np.load(out_file)
-    for tag in ("proto", "wrap"):
-        assert_close(r[f"gE_{tag}"], r["gE_full"], f"summed shard grad_E ({tag})")
+    # stand-alone wrapper: averaged shard gradients == single-device gradient on the concatenated batch
+    assert_close(r["gE_wrap"], r["gE_full"], "averaged shard grad_E")
+    assert_close(r["gE_accum"], 2 * r["gE_full"], "grad_E after a second accumulated micro-step")
+    for tag in ("wrap", "eval"):
         assert np.array_equal(r[f"hist_{tag}"], r["hist_full"])
         # equal shard sizes: the mean of the per-rank losses is the global loss
         assert abs(float(r[f"loss_{tag}"]) - float(r["loss_full"])) <= 1e-6 * abs(float(r["loss_full"]))
-    assert_close(r["gz_wrap"], r["gz_full"], "rank-0 grad_z slice")
+    # each rank's loss and grad_z are the LOCAL-mean quantities (three backward passes were accumulated into zt.grad)
+    assert abs(float(r["loss_local"]) - float(r["loss_loc_ref"])) <= 1e-6 * abs(float(r["loss_loc_ref"]))
+    assert_close(r["gz_wrap"], r["gz_loc"], "rank-0 grad_z (local mean)")
     assert bool(r["idx_ok"])
+    # inside DDP: encoder and codebook gradients equal the single-device ones
+    assert_close(r["ddp_gw"], r["one_gw"], "DDP encoder weight gradient", rtol=2e-5)
+    assert_close(r["ddp_gE"], r["one_gE"], "DDP codebook gradient", rtol=2e-5)
 
 
 def test_pack_unpack_exact_counts():
-    from vq_vae_gan_diffusion_b200.dist import pack_stats, unpack_stats
-    hist = torch.tensor([0, 1, 2 ** 40 + 3, 7], dtype=torch.int64)
-    buf = pack_stats(hist, torch.tensor(0.5)) + pack_stats(hist, torch.tensor(1.5))
-    h, l = unpack_stats(buf)
-    assert torch.equal(h, 2 * hist) and abs(float(l) - 1.0) < 1e-7
+    from vq_vae_gan_diffusion_b200.dist import pack_hist, unpack_hist
+    hist = torch.tensor([0, 1, 2 ** 39 + 3, 7, 65535, 65536, 2 ** 24 + 1], dtype=torch.int64)
+    buf = torch.zeros(2 * hist.numel())
+    pack_hist(hist, buf)
+    assert torch.equal(unpack_hist(buf * 3), 3 * hist)       # what a 3-rank SUM of equal histograms delivers

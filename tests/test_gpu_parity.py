@@ -771,3 +771,25 @@ def test_mask_and_replace_consumes_the_generator_like_the_reference(vq):
     assert torch.equal(got, exp)
     assert torch.equal(after_ours, after_ref)                                                 # generator left in the same state
     assert 0.3 < float((got[:, 1:] == indices).double().mean()) < 0.7
+
+
+def test_log_onehot_to_index(vq):
+    """log_onehot_to_index(log_x) = log_x.argmax(1) (vq_diffusion.py:37-38) against the oracle and torch.argmax on the GPU:
+    round trip with index_to_log_onehot, vector and scalar paths, ties (first maximum), NaN (counts as the maximum), -inf rows."""
+    from oracle.vq_oracle import log_onehot_to_index_np
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(8)
+    for shape, C in (((4, 64), 45), ((3, 37), 33), ((2, 6, 10), 17), ((2, 1024), 1025)):
+        x = torch.randint(0, C, shape, device=dev, generator=g)
+        assert torch.equal(vq.log_onehot_to_index(vq.index_to_log_onehot(x, C)), x)
+        v = torch.randn((shape[0], C) + tuple(shape[1:]), device=dev, generator=g)
+        v[0, 3] = v[0, 1]                                   # ties along the class axis: first wins
+        v[-1, C // 2].view(-1)[0] = float("nan")
+        v[-1, C - 1].view(-1)[0] = float("nan")             # first NaN wins
+        v[0, :].view(C, -1)[:, -1] = float("-inf")
+        got = vq.log_onehot_to_index(v)
+        assert got.dtype == torch.int64 and got.shape == (shape[0],) + tuple(shape[1:])
+        assert torch.equal(got, v.argmax(1))
+        assert np.array_equal(got.cpu().numpy(), log_onehot_to_index_np(v.cpu().numpy()))
+    with pytest.raises(RuntimeError):
+        vq.log_onehot_to_index(torch.zeros(2, 3))

@@ -314,3 +314,51 @@ def test_token_oracles_against_torch_cpu_ops():
         m = mask_f.round().to(dtype=torch.int64)
         exp = torch.cat(((torch.ones(B, 1) * 7).long(), m * idx + (1 - m) * rnd), dim=1)              # vqTransformer.py:117-141
         assert np.array_equal(blend_with_sos_np(idx.numpy(), mask_f.numpy(), rnd.numpy(), 7), exp.numpy())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The vectorised argmin stage of the oracle (used by the full-size GPU parity tests) against its scalar definition.
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", list(CASES))
+def test_fast_oracle_stage_is_bit_identical_to_the_scalar_one(name, oracle):
+    if not oracle.has_fast_path:
+        pytest.skip("host has no AVX2 + FMA: forward(fast=True) runs the scalar stage")
+    z, E, _ = make_inputs(CASES[name])
+    a, b = oracle.forward(z, E), oracle.forward(z, E, fast=True)
+    for key in ("idx", "hist", "zq_nhwc", "dist_min"):
+        assert np.array_equal(a[key], b[key], equal_nan=key == "dist_min"), key
+    assert a["tie_rows"] == b["tie_rows"]
+    assert a["loss"] == b["loss"] or (np.isnan(a["loss"]) and np.isnan(b["loss"]))
+
+
+def test_fast_oracle_stage_nan_inf_and_ragged_k(oracle):
+    if not oracle.has_fast_path:
+        pytest.skip("host has no AVX2 + FMA")
+    rng = np.random.default_rng(5)
+    for K in (1, 15, 16, 17, 33, 250):
+        E = rng.standard_normal((K, 256), dtype=np.float32)
+        z = rng.standard_normal((3, 256, 2, 5), dtype=np.float32)
+        z[0, 3, 1, 1] = np.nan
+        z[1, :, 0, 2] = np.inf
+        z[2, 7, 1, 4] = -np.inf
+        if K > 20:
+            E[K // 2, 5] = np.nan
+            E[3, 9] = np.inf
+        a, b = oracle.forward(z, E), oracle.forward(z, E, fast=True)
+        assert np.array_equal(a["idx"], b["idx"]) and a["tie_rows"] == b["tie_rows"], K
+        assert np.array_equal(a["dist_min"], b["dist_min"], equal_nan=True), K
+
+
+def test_log_onehot_to_index_oracle_matches_torch_argmax():
+    """log_onehot_to_index = log_x.argmax(1) (vq_diffusion.py:37-38): round trip through index_to_log_onehot, ties, NaN."""
+    import torch
+    from oracle.vq_oracle import index_to_log_onehot_np, log_onehot_to_index_np
+    rng = np.random.default_rng(3)
+    x = rng.integers(0, 17, size=(3, 5, 4), dtype=np.int64)
+    assert np.array_equal(log_onehot_to_index_np(index_to_log_onehot_np(x, 17)), x)
+    v = rng.standard_normal((4, 9, 6)).astype(np.float32)
+    v[0, 3, 1] = v[0, 5, 1] = 7.0                       # tie: first wins
+    v[1, 4, 2] = np.nan
+    v[1, 6, 2] = np.nan                                 # first NaN wins
+    v[2, :, 0] = -np.inf
+    assert np.array_equal(log_onehot_to_index_np(v), torch.from_numpy(v).argmax(1).numpy())

@@ -94,8 +94,12 @@ _SIGNATURES = {
     "vq_argmin_rows": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _int, _vp, _int, _vp, _vp, _sz, _vp]),
     "vq_forward": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vq_backward": (_int, [_vp, ctypes.POINTER(_i64), _f32, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _f32, _i64, _vp, _vp, _vp]),
+    "vq_backward_workspace_bytes": (_int, [_int, _int, ctypes.POINTER(_sz)]),
+    "vq_backward_ex": (_int, [_vp, ctypes.POINTER(_i64), _f32, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _f32, _i64, _f32, _int,
+                              _vp, _vp, _vp, _sz, _vp]),
     "vq_embed_nchw": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _vp]),
     "vq_index_to_log_onehot": (_int, [_vp, _i64, _i64, _int, _f32, _vp, _vp]),
+    "vq_log_onehot_to_index": (_int, [_vp, _i64, _i64, _int, _vp, _vp]),
     "vq_mask_replace": (_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "vq_profile_enable": (_int, [_int]),
     "vq_profile_collect": (_int, [ctypes.POINTER(_f32), _int, ctypes.POINTER(_int)]),
@@ -155,6 +159,17 @@ def workspace_bytes(N: int, K: int, D: int) -> int:
 
 
 _ws_cache = {}
+_bws_cache = {}
+
+
+def backward_workspace_bytes_cached(K: int, D: int) -> int:
+    """Scratch the deterministic backward needs (vq_backward_workspace_bytes)."""
+    v = _bws_cache.get((K, D))
+    if v is None:
+        out = _sz(0)
+        check(lib().vq_backward_workspace_bytes(int(K), int(D), ctypes.byref(out)), "vq_backward_workspace_bytes")
+        v = _bws_cache[(K, D)] = int(out.value)
+    return v
 
 
 def workspace_bytes_cached(N: int, K: int, D: int) -> int:

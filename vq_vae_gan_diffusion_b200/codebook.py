@@ -63,15 +63,28 @@ class _on_device:
 
 
 class _Workspace:
-    """Grow-only scratch buffer, one per (module, device)."""
+    """Grow-only scratch buffers, one per (module, device, CUDA stream): the workspace holds the call's control words and
+    candidate lists, so two streams running the same module concurrently must not share one."""
 
     def __init__(self):
-        self.buf = None
+        self.bufs = {}
 
-    def get(self, nbytes: int, device) -> torch.Tensor:
-        if self.buf is None or self.buf.device != device or self.buf.numel() < nbytes:
-            self.buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        return self.buf
+    def get(self, nbytes: int, device, stream: int = 0) -> torch.Tensor:
+        key = (device, stream)
+        buf = self.bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            if len(self.bufs) > 8:                           # streams come and go: do not hoard scratch memory
+                self.bufs.clear()
+            buf = self.bufs[key] = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        return buf
+
+
+def _kernel_weight(weight: torch.Tensor) -> torch.Tensor:
+    """The (K, D) fp32 matrix the kernels read: they use 16-byte loads on dense rows, so a non-contiguous weight or one
+    at a storage offset that is not 16-byte aligned (a slice of a flat parameter buffer) is copied first."""
+    if weight.is_contiguous() and weight.data_ptr() % 16 == 0:
+        return weight
+    return weight.detach().clone(memory_format=torch.contiguous_format)
 
 
 class _VQFunction(torch.autograd.Function):
@@ -83,17 +96,19 @@ class _VQFunction(torch.autograd.Function):
         K = weight.shape[0]
         dev = z.device
         zc = z.contiguous()                                  # NCHW; the kernels read it in place
+        weight = _kernel_weight(weight)
         with _on_device(dev):
-            E_h, e2, cb = module._derived(weight, force=refresh)
+            st = _stream_ptr(dev)
+            E_h, e2, cb = module._derived(weight, force=refresh, stream=st)
             zq = torch.empty((B, H, W, D), dtype=torch.float32, device=dev)
             idx = torch.empty((B * H * W,), dtype=torch.int64, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             hist = torch.empty((K,), dtype=torch.int64, device=dev)
             stats = torch.empty((4,), dtype=torch.int64, device=dev)
-            ws = module._workspace.get(_native.workspace_bytes_cached(B * H * W, K, D), dev)
+            ws = module._workspace.get(_native.workspace_bytes_cached(B * H * W, K, D), dev, st)
             rc = _native.lib().vq_forward(_ptr(zc), B, H * W, D, _ptr(weight), _ptr(E_h), _ptr(e2), _ptr(cb), K,
                                           float(module.beta), _ptr(zq), _ptr(idx), _ptr(loss), _ptr(hist),
-                                          _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr(dev))
+                                          _ptr(stats), _ptr(ws), ws.numel(), st)
             if rc != 0:
                 _native.check(rc, "vq_forward")
             if module.count_launches:
@@ -130,18 +145,26 @@ class _VQFunction(torch.autograd.Function):
         if g_loss is not None:
             g_loss_t = g_loss.to(device=dev, dtype=torch.float32).contiguous()
         with _on_device(dev):
+            st = _stream_ptr(dev)
             grad_z = torch.empty((B, D, H, W), dtype=torch.float32, device=dev) if need_z else None
-            grad_E = torch.empty((K, D), dtype=torch.float32, device=dev) if need_w else None
-            n_global = B * H * W * int(module.grad_world_size)
-            rc = _native.lib().vq_backward(_ptr(g_zq), strides, 0.0, _ptr(g_loss_t), _ptr(zc), _ptr(idx), _ptr(weight),
-                                           B, H * W, D, K, float(module.beta), n_global, _ptr(grad_z), _ptr(grad_E),
-                                           _stream_ptr(dev))
+            grad_E = None
+            if need_w:
+                # a data-parallel wrapper may hand out the head of its flat exchange buffer (dist.py): the scatter-add
+                # then lands where the all-reduce reads, with no packing copy
+                grad_E = module.grad_alloc(K, D, dev) if module.grad_alloc is not None else \
+                    torch.empty((K, D), dtype=torch.float32, device=dev)
+            det = bool(module.deterministic) and need_w
+            ws = None
+            if det:
+                ws = module._workspace_bwd.get(_native.backward_workspace_bytes_cached(K, D), dev, st)
+            rc = _native.lib().vq_backward_ex(_ptr(g_zq), strides, 0.0, _ptr(g_loss_t), _ptr(zc), _ptr(idx), _ptr(weight),
+                                              B, H * W, D, K, float(module.beta), B * H * W, float(module.grad_scale),
+                                              1 if det else 0, _ptr(grad_z), _ptr(grad_E), _ptr(ws),
+                                              0 if ws is None else ws.numel(), st)
             if rc != 0:
-                _native.check(rc, "vq_backward")
+                _native.check(rc, "vq_backward_ex")
             if module.count_launches:
                 module._launches_bwd = int(_native.lib().vq_last_launch_count())
-        if grad_E is not None and module.grad_hook is not None:
-            grad_E = module.grad_hook(grad_E)
         return grad_z, grad_E, None, None
 
 
@@ -169,18 +192,25 @@ class CodeBook(nn.Module):
         self._e2 = None
         self._cb = None
         self._derived_key = None
+        self._derived_by_stream = {}
         self._workspace = _Workspace()
+        self._workspace_bwd = _Workspace()
         self._launches = 0
         self._launches_bwd = 0
         self.count_launches = False      # bench.py: record how many kernels each call enqueued
-        # data-parallel plumbing (see dist.py): loss mean runs over N_local * grad_world_size latents
-        self.grad_world_size = 1
-        self.grad_hook = None
+        # deterministic=True: the codebook-gradient scatter-add runs in 64-bit fixed point (vq_backward_ex), bit-reproducible
+        # from run to run; default is the faster red.global.add.v4.f32 (order of the float additions varies)
+        self.deterministic = False
+        # data-parallel plumbing (see dist.py).  The backward always returns the gradient of THIS rank's mean loss for z
+        # (what DDP-averaged upstream layers expect); grad_scale (1 / world size) applies to the codebook gradient only,
+        # so that the SUM over ranks is the gradient of the global-batch mean.  grad_alloc lets the wrapper place grad_E.
+        self.grad_scale = 1.0
+        self.grad_alloc = None
         self.last_histogram = None
         self.last_stats = None
 
     # ------------------------------------------------------------------ derived codebook state
-    def _derived(self, weight: torch.Tensor, force: bool = False):
+    def _derived(self, weight: torch.Tensor, force: bool = False, stream: int = 0):
         """fp16 operand image + |e|^2 + scalars of the current weight.
 
         While the codebook is being trained (grad mode on, weight requires grad) they are rebuilt on every call -- the
@@ -190,23 +220,31 @@ class CodeBook(nn.Module):
         ``load_state_dict()``, ``.to(device)`` all change one of them).  In-place edits through ``weight.data`` bypass
         the version counter: call :meth:`refresh_codebook` after those."""
         key = (weight.data_ptr(), weight._version, weight.device, tuple(weight.shape))
-        if force or key != self._derived_key:
+        # one set of derived buffers per CUDA stream: they are written and read in stream order, so a second stream using
+        # the module concurrently gets its own (and rebuilds it) instead of racing on a shared one
+        ent = self._derived_by_stream.get(stream)
+        if force or ent is None or ent[3] != key:
             K, D = weight.shape
             dev = weight.device
             k_pad = _native.padded_codes(K)
-            if self._E_h is None or self._E_h.device != dev or self._E_h.shape[0] != k_pad:
-                self._E_h = torch.empty((k_pad, D), dtype=torch.float16, device=dev)
-                self._e2 = torch.empty((k_pad,), dtype=torch.float32, device=dev)
-                self._cb = torch.empty((4,), dtype=torch.float32, device=dev)
-            rc = _native.lib().vq_prepare_codebook(_ptr(weight), K, D, _ptr(self._E_h), _ptr(self._e2), _ptr(self._cb),
-                                                   _stream_ptr(dev))
+            if ent is None or ent[0].device != dev or ent[0].shape[0] != k_pad:
+                if len(self._derived_by_stream) > 8:
+                    self._derived_by_stream.clear()
+                ent = [torch.empty((k_pad, D), dtype=torch.float16, device=dev),
+                       torch.empty((k_pad,), dtype=torch.float32, device=dev),
+                       torch.empty((4,), dtype=torch.float32, device=dev), None]
+                self._derived_by_stream[stream] = ent
+            rc = _native.lib().vq_prepare_codebook(_ptr(weight), K, D, _ptr(ent[0]), _ptr(ent[1]), _ptr(ent[2]), stream or _stream_ptr(dev))
             _native.check(rc, "vq_prepare_codebook")
-            self._derived_key = key
-        return self._E_h, self._e2, self._cb
+            ent[3] = key
+            self._E_h, self._e2, self._cb, self._derived_key = ent[0], ent[1], ent[2], key
+        return ent[0], ent[1], ent[2]
 
     def refresh_codebook(self) -> None:
         """Drop the cached derived state (needed only after in-place edits through ``weight.data``)."""
         self._derived_key = None
+        for ent in self._derived_by_stream.values():
+            ent[3] = None
 
     def _check_input(self, z: torch.Tensor):
         if self.latent_dim > _KERNEL_D:
@@ -273,17 +311,19 @@ class CodeBook(nn.Module):
         K = weight.shape[0]
         dev = z.device
         zc = z.contiguous()
+        weight = _kernel_weight(weight)
         with _on_device(dev):
-            E_h, e2, cb = self._derived(weight, force=force)
+            st = _stream_ptr(dev)
+            E_h, e2, cb = self._derived(weight, force=force, stream=st)
             idx = torch.empty((B * H * W,), dtype=dtype, device=dev)
             stats = torch.empty((4,), dtype=torch.int64, device=dev)
-            ws = self._workspace.get(_native.workspace_bytes_cached(B * H * W, K, D), dev)
+            ws = self._workspace.get(_native.workspace_bytes_cached(B * H * W, K, D), dev, st)
             if bits == 64:
                 rc = _native.lib().vq_argmin(_ptr(zc), B, H * W, D, _ptr(weight), _ptr(E_h), _ptr(e2), _ptr(cb), K,
-                                             _ptr(idx), _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr(dev))
+                                             _ptr(idx), _ptr(stats), _ptr(ws), ws.numel(), st)
             else:
                 rc = _native.lib().vq_argmin_narrow(_ptr(zc), B, H * W, D, _ptr(weight), _ptr(E_h), _ptr(e2), _ptr(cb), K,
-                                                    _ptr(idx), bits, _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr(dev))
+                                                    _ptr(idx), bits, _ptr(stats), _ptr(ws), ws.numel(), st)
             if rc != 0:
                 _native.check(rc, "vq_argmin")
             if self.count_launches:
@@ -302,7 +342,10 @@ class CodeBook(nn.Module):
         state = self.__dict__.copy()
         for k in _DERIVED_ATTRS:
             state[k] = None
+        state["_derived_by_stream"] = {}
         state["_workspace"] = _Workspace()
+        state["_workspace_bwd"] = _Workspace()
+        state["grad_alloc"] = None
         state["last_histogram"] = None
         state["last_stats"] = None
         return state

@@ -68,9 +68,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (and surfaces as a CUDA error) instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (and surfaces as a CUDA error) instead of hanging the GPU.  The bound is ~20 s of SM
+// cycles -- two orders of magnitude above the longest legitimate wait (a whole cfg4 GEMM is 1.5 ms), long enough to ride
+// out compute preemption, MPS time slicing or a debugger stop without turning them into a sticky error; build with
+// -DVQ_MBAR_TIMEOUT_CYCLES=... for a tighter bound while debugging a protocol change.
 #ifndef VQ_MBAR_TIMEOUT_CYCLES
-#define VQ_MBAR_TIMEOUT_CYCLES (4000000000ll)
+#define VQ_MBAR_TIMEOUT_CYCLES (40000000000ll)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;

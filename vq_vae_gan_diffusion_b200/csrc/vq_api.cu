@@ -452,15 +452,17 @@ VQ_EXPORT int vq_debug_scores(const float* z_nchw, int64_t B, int64_t HW, int D,
     return run_gemm(z_nchw, N, HW, false, VQ_RECIPE_EXPANDED, E_h, e_norm2, cb_scalars, K, w, scores, nullptr, nullptr, reinterpret_cast<cudaStream_t>(stream));
 }
 
-VQ_EXPORT int vq_backward(const float* gout, const int64_t* gout_strides, float g_loss, const float* g_loss_dev,
-                          const float* z_nchw,
-                          const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K, float beta,
-                          int64_t n_global, float* grad_z, float* grad_E, vq_stream_t stream) {
+static int backward_impl(const float* gout, const int64_t* gout_strides, float g_loss, const float* g_loss_dev,
+                         const float* z_nchw, const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K, float beta,
+                         int64_t n_global, float grad_E_scale, bool deterministic, float* grad_z, float* grad_E,
+                         void* ws, size_t ws_bytes, vq_stream_t stream) {
     g_launches = 0;
     int rc = check_common(z_nchw, B, HW, D, K);
     if (rc != VQ_OK) return rc;
     const int64_t N = B * HW;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if ((reinterpret_cast<uintptr_t>(grad_E) & 15) != 0 || (reinterpret_cast<uintptr_t>(E) & 15) != 0)
+        return fail(VQ_E_INVALID, "E and grad_E must be 16-byte aligned");
     if (grad_E) VQ_CUDA(cudaMemsetAsync(grad_E, 0, (size_t)K * D * sizeof(float), st));
     if (N == 0 || (!grad_z && !grad_E)) return VQ_OK;
     if (!idx || !E) return fail(VQ_E_INVALID, "null idx/E pointer");
@@ -481,23 +483,78 @@ VQ_EXPORT int vq_backward(const float* gout, const int64_t* gout_strides, float 
     bp.g_loss_dev = g_loss_dev;
     bp.inv_nd = 1.0 / ((double)n_global * (double)D);
     bp.beta = beta;
+    bp.e_scale = grad_E_scale;
     bp.grad_z = grad_z; bp.grad_E = grad_E;
+    bp.acc_fx = nullptr; bp.fx_shift = nullptr;
     const unsigned grid = (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows);
+    const bool det = deterministic && grad_E != nullptr;
+    if (det) {
+        // workspace: [acc (K, D) int64 | maxbits | shift]
+        const size_t need = (size_t)K * D * sizeof(long long) + 256;
+        if (ws == nullptr || (reinterpret_cast<uintptr_t>(ws) & 255) != 0)
+            return fail(VQ_E_INVALID, "deterministic backward needs a 256-byte aligned workspace");
+        if (ws_bytes < need) return fail(VQ_E_WORKSPACE, "workspace too small: %zu < %zu bytes", ws_bytes, need);
+        bp.acc_fx = static_cast<long long*>(ws);
+        unsigned int* maxbits = reinterpret_cast<unsigned int*>(static_cast<char*>(ws) + (size_t)K * D * sizeof(long long));
+        int* shift = reinterpret_cast<int*>(maxbits + 1);
+        bp.fx_shift = shift;
+        VQ_CUDA(cudaMemsetAsync(ws, 0, need, st));
+        vq::vq_backward_maxdiff_kernel<<<grid, vq::kBwdThreads, 0, st>>>(z_nchw, idx, E, N, HW, K, maxbits);
+        VQ_LAUNCH_CHECK("vq_backward_maxdiff_kernel");
+        vq::vq_backward_fxshift_kernel<<<1, 1, 0, st>>>(maxbits, shift);
+        VQ_LAUNCH_CHECK("vq_backward_fxshift_kernel");
+    }
     // channels-last upstream gradient (d contiguous; the layout of the z_q we returned) is read lanes-over-d, an
     // hw-contiguous one like z; 16-byte tile accesses need hw-contiguous, 16-byte aligned 32-latent tiles
     const bool cl = gout != nullptr && bp.gs_d == 1 && !(bp.gs_hw == 1 && HW > 1) && bp.gs_b % 4 == 0 && bp.gs_hw % 4 == 0 &&
                     (reinterpret_cast<uintptr_t>(gout) & 15) == 0;
     const bool vec = (HW % vq::kSelRows == 0) && ((reinterpret_cast<uintptr_t>(z_nchw) & 15) == 0) &&
                      (grad_z == nullptr || (reinterpret_cast<uintptr_t>(grad_z) & 15) == 0);
+#define VQ_BWD_LAUNCH(V, C)                                                                          \
+    do {                                                                                             \
+        if (det) vq::vq_backward_kernel<V, C, true><<<grid, vq::kBwdThreads, 0, st>>>(bp);            \
+        else     vq::vq_backward_kernel<V, C, false><<<grid, vq::kBwdThreads, 0, st>>>(bp);           \
+    } while (0)
     if (vec) {
-        if (cl) vq::vq_backward_kernel<true, true><<<grid, vq::kBwdThreads, 0, st>>>(bp);
-        else    vq::vq_backward_kernel<true, false><<<grid, vq::kBwdThreads, 0, st>>>(bp);
+        if (cl) VQ_BWD_LAUNCH(true, true);
+        else    VQ_BWD_LAUNCH(true, false);
     } else {
-        if (cl) vq::vq_backward_kernel<false, true><<<grid, vq::kBwdThreads, 0, st>>>(bp);
-        else    vq::vq_backward_kernel<false, false><<<grid, vq::kBwdThreads, 0, st>>>(bp);
+        if (cl) VQ_BWD_LAUNCH(false, true);
+        else    VQ_BWD_LAUNCH(false, false);
     }
+#undef VQ_BWD_LAUNCH
     VQ_LAUNCH_CHECK("vq_backward_kernel");
+    if (det) {
+        const int64_t n_elems = (int64_t)K * D;
+        const unsigned fgrid = (unsigned)((n_elems + 256 * 8 - 1) / (256 * 8));
+        vq::vq_backward_fxfinish_kernel<<<fgrid, 256, 0, st>>>(bp.acc_fx, bp.fx_shift, n_elems, g_loss, g_loss_dev, bp.inv_nd, beta,
+                                                              grad_E_scale, grad_E);
+        VQ_LAUNCH_CHECK("vq_backward_fxfinish_kernel");
+    }
     return VQ_OK;
+}
+
+VQ_EXPORT int vq_backward(const float* gout, const int64_t* gout_strides, float g_loss, const float* g_loss_dev,
+                          const float* z_nchw,
+                          const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K, float beta,
+                          int64_t n_global, float* grad_z, float* grad_E, vq_stream_t stream) {
+    return backward_impl(gout, gout_strides, g_loss, g_loss_dev, z_nchw, idx, E, B, HW, D, K, beta, n_global, 1.0f, false, grad_z,
+                         grad_E, nullptr, 0, stream);
+}
+
+VQ_EXPORT int vq_backward_workspace_bytes(int K, int D, size_t* out) {
+    if (out == nullptr) return fail(VQ_E_INVALID, "null out pointer");
+    if (K < 1 || D < 1) return fail(VQ_E_INVALID, "bad shape K=%d D=%d", K, D);
+    *out = (size_t)K * D * sizeof(long long) + 256;
+    return VQ_OK;
+}
+
+VQ_EXPORT int vq_backward_ex(const float* gout, const int64_t* gout_strides, float g_loss, const float* g_loss_dev,
+                             const float* z_nchw, const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K,
+                             float beta, int64_t n_global, float grad_E_scale, int deterministic, float* grad_z, float* grad_E,
+                             void* workspace, size_t workspace_bytes, vq_stream_t stream) {
+    return backward_impl(gout, gout_strides, g_loss, g_loss_dev, z_nchw, idx, E, B, HW, D, K, beta, n_global, grad_E_scale,
+                         deterministic != 0, grad_z, grad_E, workspace, workspace_bytes, stream);
 }
 
 VQ_EXPORT int vq_embed_nchw(const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K, float* out,
@@ -540,6 +597,25 @@ VQ_EXPORT int vq_index_to_log_onehot(const int64_t* idx, int64_t B, int64_t L, i
     if (vec) vq::vq_log_onehot_kernel<true><<<grid, vq::kTokThreads, 0, st>>>(idx, B, L, num_classes, clamp_min, out);
     else     vq::vq_log_onehot_kernel<false><<<grid, vq::kTokThreads, 0, st>>>(idx, B, L, num_classes, clamp_min, out);
     VQ_LAUNCH_CHECK("vq_log_onehot_kernel");
+    return VQ_OK;
+}
+
+VQ_EXPORT int vq_log_onehot_to_index(const float* log_x, int64_t B, int64_t L, int num_classes, int64_t* out, vq_stream_t stream) {
+    g_launches = 0;
+    if (B < 0 || L < 0 || num_classes < 1) return fail(VQ_E_INVALID, "bad shape B=%lld L=%lld num_classes=%d", (long long)B, (long long)L, num_classes);
+    if (B == 0 || L == 0) return VQ_OK;
+    if (!log_x || !out) return fail(VQ_E_INVALID, "null pointer");
+    DevInfo* dev;
+    int rc = device_info(&dev);
+    if (rc != VQ_OK) return rc;
+    const bool vec = (L % 4 == 0) && ((reinterpret_cast<uintptr_t>(log_x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const int64_t threads = vec ? B * (L / 4) : B * L;
+    const int64_t gx = (threads + vq::kTokThreads - 1) / vq::kTokThreads;
+    if (gx > 0x7fffffffLL) return fail(VQ_E_UNSUPPORTED, "argmax grid %lld too large", (long long)gx);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (vec) vq::vq_argmax_classes_kernel<true><<<(unsigned)gx, vq::kTokThreads, 0, st>>>(log_x, B, L, num_classes, out);
+    else     vq::vq_argmax_classes_kernel<false><<<(unsigned)gx, vq::kTokThreads, 0, st>>>(log_x, B, L, num_classes, out);
+    VQ_LAUNCH_CHECK("vq_argmax_classes_kernel");
     return VQ_OK;
 }
 

@@ -33,17 +33,31 @@ struct BackwardParams {
     const float* g_loss_dev;  // ... or, when non-null, a device scalar holding it (no host sync in autograd)
     double inv_nd;            // 1 / (n_global * D)
     float beta;
+    float e_scale;            // extra factor on the codebook gradient (1 / world size when the ranks' gradients are summed)
     float* grad_z;            // (B, D, HW) or null
     float* grad_E;            // (K, D) or null, zeroed before launch
+    // deterministic mode (kDet): the scatter-add runs in 64-bit fixed point -- integer addition is associative, so the
+    // result does not depend on the order in which the atomics land -- into acc_fx, scaled by 2^fx_shift[0]
+    long long* acc_fx;        // (K, D) zeroed before launch
+    const int* fx_shift;      // (1) device scalar written by vq_backward_maxdiff_kernel
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+__device__ __forceinline__ void red_add_s64(long long* addr, long long v) {
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
+}
+
+// Fixed-point scale of the deterministic scatter-add: |z - e| < 2^ex for every element (ex from the pre-pass below), so
+// with shift = 38 - ex a term is below 2^38 in magnitude and up to 2^24 of them (more latents than the API accepts per
+// code) stay inside 63 bits; the quantum 2^-shift is 2^-38 of the largest difference, far below fp32 resolution.
+constexpr int kFxTopBit = 38;
+
 // kVec: HW % 32 == 0 and 16-byte aligned z / grad_z (the 32 latents of a tile are 32 consecutive hw positions of one
-// batch item).  kGoutCL: g_out is channels-last (gs_d == 1) with 16-byte aligned rows.
-template <bool kVec, bool kGoutCL>
+// batch item).  kGoutCL: g_out is channels-last (gs_d == 1) with 16-byte aligned rows.  kDet: deterministic scatter-add.
+template <bool kVec, bool kGoutCL, bool kDet = false>
 __global__ void __launch_bounds__(kBwdThreads, VQ_BWD_MIN_BLOCKS)
 vq_backward_kernel(const BackwardParams p) {
     __shared__ __align__(16) float tile[kSelRows * kD];       // 32 KiB: z, then grad (kGoutCL) or diff
@@ -107,7 +121,8 @@ vq_backward_kernel(const BackwardParams p) {
 
     // 2. row form: diff = z - e, scatter-add into the codebook gradient, grad (or diff) back into the tile
     {
-        const float ce = -(p.beta * coef);
+        const float ce = -(p.beta * coef) * p.e_scale;
+        const float fx_mul = kDet ? pow2f(__ldg(p.fx_shift)) : 0.0f;     // exact power of two
         float4 ev[4][2];
         int kk[4];
 #pragma unroll
@@ -124,7 +139,8 @@ vq_backward_kernel(const BackwardParams p) {
             const bool live = (n0 + r < p.N) && kk[rr] >= 0;
             float4* zrow4 = reinterpret_cast<float4*>(tile + r * kD);
             const int g = tile_swz(r);
-            float* ge = (p.grad_E != nullptr && live) ? p.grad_E + (int64_t)kk[rr] * kD : nullptr;
+            float* ge = (!kDet && p.grad_E != nullptr && live) ? p.grad_E + (int64_t)kk[rr] * kD : nullptr;
+            long long* gx = (kDet && p.acc_fx != nullptr && live) ? p.acc_fx + (int64_t)kk[rr] * kD : nullptr;
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const int q = lane + 32 * h;
@@ -136,6 +152,13 @@ vq_backward_kernel(const BackwardParams p) {
                     diff.z = __fsub_rn(zv.z, e.z); diff.w = __fsub_rn(zv.w, e.w);
                 }
                 if (ge != nullptr) red_add_v4(ge + 4 * q, ce * diff.x, ce * diff.y, ce * diff.z, ce * diff.w);
+                if (kDet && gx != nullptr) {
+                    // diff * 2^shift is exact in fp32 (a power-of-two scaling) and below 2^38: the conversion is exact too
+                    red_add_s64(gx + 4 * q + 0, __float2ll_rn(diff.x * fx_mul));
+                    red_add_s64(gx + 4 * q + 1, __float2ll_rn(diff.y * fx_mul));
+                    red_add_s64(gx + 4 * q + 2, __float2ll_rn(diff.z * fx_mul));
+                    red_add_s64(gx + 4 * q + 3, __float2ll_rn(diff.w * fx_mul));
+                }
                 if (kGoutCL) {
                     float4 o;
                     const float4 gg = has_g ? gv[rr][h] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -202,6 +225,54 @@ vq_backward_kernel(const BackwardParams p) {
             }
         }
     }
+}
+
+// ---- deterministic mode helpers -------------------------------------------------------------------------------------
+// Pre-pass: max |z - e| over all latents -> the fixed-point shift.  maxbits must be zero on entry (non-negative floats
+// order like their bit patterns; a NaN / Inf difference has the largest pattern and makes the shift 0 -- the sums are
+// garbage then, exactly like the NaN gradient of the float path).  One CTA = 32 latents, lanes over latents.
+__global__ void __launch_bounds__(kBwdThreads)
+vq_backward_maxdiff_kernel(const float* __restrict__ z, const int64_t* __restrict__ idx, const float* __restrict__ E,
+                           int64_t N, int64_t HW, int K, unsigned int* __restrict__ maxbits) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n = (int64_t)blockIdx.x * kSelRows + lane;
+    float mx = 0.0f;
+    if (n < N) {
+        const int64_t kk = __ldg(idx + n);
+        if (kk >= 0 && kk < K) {
+            const float* src = z + ((n / HW) * kD) * HW + n % HW;
+            const float* e = E + kk * kD;
+#pragma unroll 8
+            for (int i = 0; i < kD / 8; i++) {
+                const int d = warp + 8 * i;
+                float v = fabsf(__fsub_rn(__ldg(src + (int64_t)d * HW), __ldg(e + d)));
+                if (!(v == v)) v = INFINITY;                 // (fmaxf would drop a NaN)
+                mx = fmaxf(mx, v);
+            }
+        }
+    }
+    unsigned int b = __float_as_uint(mx);
+    b = __reduce_max_sync(0xffffffffu, b);
+    if (lane == 0 && b != 0u) atomicMax(maxbits, b);
+}
+
+// shift = kFxTopBit - ex with |maxdiff| < 2^ex (single thread)
+__global__ void vq_backward_fxshift_kernel(const unsigned int* __restrict__ maxbits, int* __restrict__ shift) {
+    const float mx = __uint_as_float(*maxbits);
+    int ex = exponent_of(mx);
+    *shift = max(-100, min(100, kFxTopBit - ex));
+}
+
+// grad_E[k][d] = fl( acc * 2^-shift * ce ), ce = -(beta * coef) * e_scale evaluated exactly like the float path
+__global__ void __launch_bounds__(256)
+vq_backward_fxfinish_kernel(const long long* __restrict__ acc, const int* __restrict__ shift, int64_t n_elems,
+                            float g_loss, const float* __restrict__ g_loss_dev, double inv_nd, float beta, float e_scale,
+                            float* __restrict__ grad_E) {
+    const float coef = (float)(2.0 * (double)(g_loss_dev != nullptr ? __ldg(g_loss_dev) : g_loss) * inv_nd);
+    const float ce = -(beta * coef) * e_scale;
+    const double unit = (double)ce * (double)pow2f(-__ldg(shift));
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * 256)
+        grad_E[i] = (float)((double)acc[i] * unit);
 }
 
 // out[b, d, hw] = E[idx[b*HW + hw]][d]  (decode side: worker/vqganVqvaeWorker.py:459, vqTransformer.py:98)

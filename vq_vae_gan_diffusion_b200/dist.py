@@ -1,61 +1,61 @@
 """Data-parallel plumbing for the VQ hot path (new in this build; the reference is single-device).
 
-Latents shard by batch across ranks (one process per GPU), the codebook is replicated.  Per training step exactly
-one exchange happens, a SUM all-reduce (NCCL over NVLink on GPUs, gloo in the CPU tests) of
+Latents shard by batch across ranks (one process per GPU), the codebook is replicated.  Convention -- the one
+``DistributedDataParallel`` uses for every other layer, so a CodeBook works the same inside or outside a DDP-wrapped model:
 
-    grad_E   (K, D) fp32     codebook gradient          -- launched from inside backward
-    hist     (K)    int64    usage histogram             -- launched right after forward, overlaps backward
-    loss     (1)    fp32     sum of the per-rank losses  -- idem
+* every rank's forward returns the mean loss over ITS latents, and its backward returns the gradient of that local mean for
+  ``z`` (upstream layers wrapped in DDP get their gradients AVERAGED over ranks, which turns local-mean gradients into
+  global-mean gradients);
+* the codebook gradient of the global-batch mean is the AVERAGE of the per-rank codebook gradients (equal shard sizes).
 
-Everything else is local.  With ``n_global = sum of shard sizes`` passed to the backward, the SUM of the per-rank
-codebook gradients equals the single-device gradient on the concatenated batch, and the per-rank ``grad_z`` already
-is the corresponding slice of the global-batch gradient; no 1/W rescale is needed.
+Two ways to get that average:
 
-The gradient all-reduce is launched from a post-accumulate-grad hook on the codebook weight, i.e. as soon as the
-scatter-add kernel has been enqueued; NCCL runs it on its own stream, so the rest of the backward pass (quant_conv,
-encoder) overlaps it.  ``wait()`` joins it before the optimizer step (stream-ordered, the host does not block).
+1. The CodeBook sits inside a DDP-wrapped module (the usual case: ``DDP(VQVAE(...))``): nothing to do, DDP's bucket
+   all-reduce averages ``codebook.weight.grad`` like any other parameter.  Do NOT also wrap it in :class:`DataParallelVQ`.
+2. Stand-alone (bench.py, or a codebook kept out of DDP with ``_ddp_params_and_buffers_to_ignore``):
+   :class:`DataParallelVQ` issues exactly ONE collective per training step, a SUM all-reduce (NCCL over NVLink on GPUs,
+   gloo in the CPU tests) of one flat fp32 buffer
+
+       [ grad_E (K*D) | hist low 16 bits (K) | hist high bits (K) | loss | 1 ]
+
+   launched from a post-accumulate-grad hook on the codebook weight, i.e. as soon as the scatter-add kernel has been
+   enqueued; NCCL runs it on its own stream, so the rest of the backward pass (quant_conv, encoder) overlaps it.  The
+   backward writes ``grad_E`` pre-scaled by 1/W straight into the head of that buffer (``vq_backward_ex``'s
+   ``grad_E_scale``; no packing copy, no rescale pass), so the SUM is the average.  Histogram counts travel as two exact
+   fp32 words (low 16 bits and the rest: sums stay below 2^24 for up to 256 ranks and 2^40 latents per code).
+   ``wait()`` joins the collective before the optimizer step (stream-ordered, the host does not block).
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
 
-__all__ = ["pack_stats", "unpack_stats", "allreduce_codebook", "DataParallelVQ"]
+__all__ = ["DataParallelVQ", "pack_hist", "unpack_hist"]
 
 
-def pack_stats(hist: torch.Tensor, loss: torch.Tensor) -> torch.Tensor:
-    """[hist (K) | loss | 1] as float64 (counts up to 2^53 stay exact under SUM): one buffer, one collective."""
+def pack_hist(hist: torch.Tensor, out: torch.Tensor) -> None:
+    """int64 counts (K) -> out (2K) fp32: [count & 0xffff | count >> 16], each exactly representable and exactly summable."""
     K = hist.numel()
-    buf = torch.empty(K + 2, dtype=torch.float64, device=hist.device)
-    buf[:K] = hist
-    buf[K] = loss.detach()
-    buf[K + 1] = 1.0
-    return buf
+    out[:K] = (hist & 0xFFFF).to(torch.float32)
+    out[K:2 * K] = (hist >> 16).to(torch.float32)
 
 
-def unpack_stats(buf: torch.Tensor):
-    """-> (global histogram int64 (K), mean of the per-rank losses fp32 0-dim)."""
-    K = buf.numel() - 2
-    return buf[:K].round().to(torch.int64), (buf[K] / buf[K + 1]).to(torch.float32)
-
-
-def allreduce_codebook(grad_E: torch.Tensor, stats_buf: torch.Tensor, group=None, async_op: bool = False):
-    """The one exchange step: SUM over ranks, in place.  Returns the work handles when async."""
-    w1 = dist.all_reduce(grad_E, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
-    w2 = dist.all_reduce(stats_buf, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
-    return (w1, w2) if async_op else None
+def unpack_hist(buf: torch.Tensor) -> torch.Tensor:
+    """(2K) fp32 sums -> int64 counts (K)."""
+    K = buf.numel() // 2
+    return buf[:K].round().to(torch.int64) + (buf[K:2 * K].round().to(torch.int64) << 16)
 
 
 class DataParallelVQ(torch.nn.Module):
-    """Wraps a CodeBook for batch-sharded training.
+    """Wraps a stand-alone CodeBook for batch-sharded training (see the module docstring for when NOT to use it).
 
         dp = DataParallelVQ(codebook)             # after dist.init_process_group
-        z_q, idx, loss = dp(z_local)              # local forward; histogram / loss all-reduce starts
-        (loss + downstream(z_q)).backward()       # grad_E all-reduce starts inside backward, overlapped
-        dp.wait()                                 # before optimizer.step(): weight.grad is the global gradient
+        z_q, idx, loss = dp(z_local)              # local forward
+        (loss + downstream(z_q)).backward()       # the ONE all-reduce starts inside backward, overlapped with what follows
+        dp.wait()                                 # before optimizer.step(): weight.grad is the global-batch gradient
         dp.global_histogram, dp.global_loss
 
-    Shards must have equal size (the loss reported is the mean of the per-rank losses).
+    Shards must have equal size (the global loss / gradient are means of the per-rank ones).
     """
 
     def __init__(self, codebook, group=None):
@@ -63,45 +63,98 @@ class DataParallelVQ(torch.nn.Module):
         self.codebook_module = codebook
         self.group = group
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
-        codebook.grad_world_size = self.world_size
-        self._pending = []
-        self._hist = None
-        self._loss_sum = None
+        codebook.grad_scale = 1.0 / self.world_size
+        codebook.grad_alloc = self._alloc_grad
+        self._flat = None            # the step's exchange buffer
+        self._work = None
+        self._reduced = None         # (flat buffer, K, D) of the last completed exchange
+        self._local = None           # (hist, loss) of the last forward, not yet exchanged
         self.sync_grads = True
         self._hook = codebook.codebook.weight.register_post_accumulate_grad_hook(self._on_grad_ready)
 
+    # ---- flat exchange buffer: [grad_E (K*D) | hist lo (K) | hist hi (K) | loss | 1]
+    def _new_flat(self, K, D, device):
+        return torch.empty(K * D + 2 * K + 2, dtype=torch.float32, device=device)
+
+    def _alloc_grad(self, K, D, device):
+        """Called by the CodeBook's backward: grad_E is the head of a fresh flat buffer (fresh per step, because autograd
+        may keep the tensor as ``weight.grad``)."""
+        self._flat = self._new_flat(K, D, device)
+        return self._flat[:K * D].view(K, D)
+
+    def _fill_stats(self, flat, K, D):
+        hist, loss = self._local
+        tail = flat[K * D:]
+        pack_hist(hist, tail)
+        tail[2 * K] = loss
+        tail[2 * K + 1] = 1.0
+
     def _on_grad_ready(self, param):
-        if self.world_size > 1 and self.sync_grads:
-            self._pending.append(dist.all_reduce(param.grad, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        if self.world_size <= 1 or not self.sync_grads or self._local is None:
+            return
+        K, D = param.shape
+        flat = self._flat
+        aliased = flat is not None and param.grad is not None and param.grad.data_ptr() == flat.data_ptr()
+        if not aliased:
+            # autograd accumulated into an existing .grad (gradient accumulation) or copied: exchange a packed copy
+            flat = self._new_flat(K, D, param.device)
+            flat[:K * D].view(K, D).copy_(param.grad)
+        self._fill_stats(flat, K, D)
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._work = (work, flat, K, D, None if aliased else param)
+        self._local = None
+        self._flat = None
 
     def forward(self, z, **kw):
         out = self.codebook_module(z, **kw)
         z_q, idx, loss = out
         cb = self.codebook_module
         if loss is not None and cb.last_histogram is not None:
-            # the module hands out fresh tensors every call, so they can be reduced in place
-            self._hist = cb.last_histogram
-            self._loss_sum = loss.detach().clone()
-            if self.world_size > 1:
-                self._pending.append(dist.all_reduce(self._hist, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-                self._pending.append(dist.all_reduce(self._loss_sum, op=dist.ReduceOp.SUM, group=self.group,
-                                                     async_op=True))
+            self._local = (cb.last_histogram, loss.detach())
+            self._reduced = None
         return out
 
     def wait(self):
-        """Join the outstanding all-reduces (stream-ordered on GPU: the current stream waits, the host does not)."""
-        for w in self._pending:
-            if w is not None:
-                w.wait()
-        self._pending.clear()
+        """Join the outstanding all-reduce (stream-ordered on GPU: the current stream waits, the host does not)."""
+        if self._work is not None:
+            work, flat, K, D, copy_back = self._work
+            if work is not None:
+                work.wait()
+            if copy_back is not None and copy_back.grad is not None:
+                copy_back.grad.copy_(flat[:K * D].view(K, D))
+            self._reduced = (flat, K, D)
+            self._work = None
+
+    def _ensure_stats(self):
+        """Histogram / loss exchange for steps without a backward (evaluation): a small collective of its own."""
+        self.wait()
+        if self._reduced is None and self._local is not None:
+            hist, loss = self._local
+            K = hist.numel()
+            flat = torch.zeros(2 * K + 2, dtype=torch.float32, device=hist.device)
+            pack_hist(hist, flat)
+            flat[2 * K] = loss
+            flat[2 * K + 1] = 1.0
+            if self.world_size > 1:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group)
+            self._reduced = (flat, K, 0)
+            self._local = None
 
     @property
     def global_histogram(self):
-        return self._hist
+        self._ensure_stats()
+        if self._reduced is None:
+            return None
+        flat, K, D = self._reduced
+        return unpack_hist(flat[K * D:K * D + 2 * K])
 
     @property
     def global_loss(self):
-        return None if self._loss_sum is None else self._loss_sum / self.world_size
+        self._ensure_stats()
+        if self._reduced is None:
+            return None
+        flat, K, D = self._reduced
+        return flat[K * D + 2 * K] / flat[K * D + 2 * K + 1]
 
     def no_sync(self):
         """Context manager: skip the gradient all-reduce (gradient-accumulation micro-steps)."""

@@ -4,6 +4,7 @@
   network/vqDiffusion/submodule/diffusion_vq_official.py:53-60: ``(B, ...)`` int64 tokens -> ``(B, num_classes, ...)`` fp32
   ``log(one_hot.clamp(min=1e-30))``, written once by ``vq_index_to_log_onehot`` instead of the reference's int64 one-hot,
   float copy, clamp and log passes.
+* :func:`log_onehot_to_index` -- ``log_onehot_to_index(log_x)`` of network/vq_diffusion/vq_diffusion.py:37-38 (``argmax(1)``).
 * :func:`mask_and_replace` -- the input corruption of ``VQTransformer.forward`` (network/vqTransformer/vqTransformer.py:117-141):
   the Bernoulli keep-mask and the random replacement tokens are drawn by torch exactly as the reference draws them (same
   calls, same order, same generator), the round / cast / blend / sos concatenation run as one ``vq_mask_replace`` launch.
@@ -36,7 +37,7 @@ def index_to_log_onehot(x: torch.Tensor, num_classes: int, *, validate: bool = T
     if num_classes < 1:
         raise RuntimeError("num_classes must be positive")
     if validate and x.numel() > 0:
-        lo, hi = int(x.min()), int(x.max())
+        lo, hi = (int(v) for v in torch.aminmax(x))          # one reduction, one host synchronisation
         if lo < 0:
             raise RuntimeError("Class values must be non-negative.")
         if hi >= num_classes:
@@ -51,6 +52,28 @@ def index_to_log_onehot(x: torch.Tensor, num_classes: int, *, validate: bool = T
     with torch.cuda.device(x.device):
         rc = _native.lib().vq_index_to_log_onehot(_ptr(xc), B, L, num_classes, _CLAMP_MIN, _ptr(out), _stream_ptr(x.device))
         _native.check(rc, "vq_index_to_log_onehot")
+    return out
+
+
+def log_onehot_to_index(log_x: torch.Tensor) -> torch.Tensor:
+    """``log_x.argmax(1)`` (network/vq_diffusion/vq_diffusion.py:37-38): ``(B, C, ...)`` fp32 -> ``(B, ...)`` int64, the first
+    maximal class wins and a NaN counts as the maximum, as in ``torch.argmax``.  One pass over the input."""
+    if not log_x.is_cuda:
+        raise RuntimeError("log_onehot_to_index has no CPU path")
+    if log_x.dtype != torch.float32 or log_x.dim() < 2:
+        raise RuntimeError("log_onehot_to_index expects a float32 (B, C, ...) tensor")
+    B, C = log_x.shape[0], log_x.shape[1]
+    if C < 1:
+        raise RuntimeError("argmax over an empty class axis")
+    rest = tuple(log_x.shape[2:])
+    L = 1
+    for s in rest:
+        L *= s
+    xc = log_x.contiguous()
+    out = torch.empty((B,) + rest, dtype=torch.int64, device=log_x.device)
+    with torch.cuda.device(log_x.device):
+        rc = _native.lib().vq_log_onehot_to_index(_ptr(xc), B, L, C, _ptr(out), _stream_ptr(log_x.device))
+        _native.check(rc, "vq_log_onehot_to_index")
     return out
 
 
