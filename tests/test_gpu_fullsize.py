@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from parity import assert_close, classify_index_mismatches
+from parity import assert_close, classify_index_mismatches, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -176,7 +176,9 @@ def test_deterministic_backward_is_bit_reproducible(vq, oracle):
     z_np, E_np = z.cpu().numpy(), E.cpu().numpy()
     gz_o, gE_o = oracle.backward(gout.cpu().numpy(), 1.0, z_np, idx.cpu().numpy(), E_np, beta=0.25)
     assert_close(gE0.cpu().numpy(), gE_o, "deterministic grad_E")
-    assert_close(gE_f.cpu().numpy(), gE_o, "atomic grad_E")
+    # (float atomics land in a varying order: with ~64 colliding latents per code only the max-norm bound is meaningful for
+    #  elements that are sums of large cancelling terms)
+    assert rel_err(gE_f.cpu().numpy(), gE_o) <= 1e-5
     assert_close(gz0.cpu().numpy(), gz_o, "grad_z")
     # frozen encoder input (no grad_z), and the tiny-magnitude regime (fixed-point scale follows the data)
     cb.deterministic = True

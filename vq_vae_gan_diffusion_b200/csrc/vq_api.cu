@@ -59,6 +59,31 @@ bool gemm_share() {
     return v;
 }
 
+// Programmatic dependent launch of the kernels inside one call (vq_common.cuh: pdl_wait / pdl_trigger); VQ_PDL=0 launches
+// them as ordinary stream-ordered kernels (A/B runs).
+bool use_pdl() {
+    static const bool v = [] {
+        const char* e = getenv("VQ_PDL");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    return v;
+}
+
+template <typename Kernel, typename... Args>
+cudaError_t launch_chained(Kernel kernel, unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = use_pdl() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 // launch of one GEMM variant: as clusters of two CTAs (one cluster per pair of row tiles, at most one per two SMs) when
 // `share`, else one CTA per row tile up to one per SM
 template <bool kDebug, bool kTimeline>
@@ -67,18 +92,26 @@ cudaError_t launch_gemm(const vq::GemmParams& gp, bool share, int sms, cudaStrea
     cfg.blockDim = dim3(vq::kGemmThreads);
     cfg.dynamicSmemBytes = vq::kGemmSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    int n_attr = 0;
+    if (use_pdl()) {                                          // chained behind vq_prep_z_kernel
+        attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+        n_attr++;
+    }
+    cfg.attrs = attr;
     if (share) {
         const int pairs = (gp.row_tiles + 1) / 2;
         cfg.gridDim = dim3(2 * (pairs < sms / 2 ? pairs : sms / 2));
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+        attr[n_attr].val.clusterDim.x = 2;
+        attr[n_attr].val.clusterDim.y = 1;
+        attr[n_attr].val.clusterDim.z = 1;
+        n_attr++;
+        cfg.numAttrs = n_attr;
         return cudaLaunchKernelEx(&cfg, vq::vq_argmin_gemm_kernel<kDebug, kTimeline, true>, gp);
     }
+    cfg.numAttrs = n_attr;
     cfg.gridDim = dim3(gp.row_tiles < sms ? gp.row_tiles : sms);
     return cudaLaunchKernelEx(&cfg, vq::vq_argmin_gemm_kernel<kDebug, kTimeline, false>, gp);
 }
@@ -144,6 +177,8 @@ struct Workspace {
     int32_t* fb_count;           // (1)
     float4* fb_part;             // (kFbMaxGroups * kFbGroup, kFbMaxParts)
     unsigned int* fb_arrive;     // (kFbMaxGroups)
+    int32_t* ovf_count;          // (1) entries on the overflow list
+    uint4* ovf;                  // (kOvfCap) candidate entries that found no room on chip (vq_argmin_sm100.cuh)
     unsigned long long* stats;   // (VQ_STAT_COUNT) internal copy when the caller passes none
     size_t control_bytes;        // blocks_done .. fb_arrive, cleared by one memset per call
     size_t bytes;
@@ -166,11 +201,13 @@ Workspace carve(void* base, int64_t N) {
     w.loss_partial = static_cast<double*>(take((size_t)(n_pad / vq::kSelRows) * 8));
     w.fb_rows = static_cast<int32_t*>(take((size_t)n_pad * 2 * 4));
     w.fb_part = static_cast<float4*>(take((size_t)vq::kFbMaxGroups * vq::kFbGroup * vq::kFbMaxParts * sizeof(float4)));
-    // control words, contiguous so that one memset per call clears them all: [blocks_done | fb_count | fb_arrive]
+    w.ovf = static_cast<uint4*>(take((size_t)vq::kOvfCap * sizeof(uint4)));
+    // control words, contiguous so that the first kernel of a call clears them all: [blocks_done | fb_count | ovf_count | fb_arrive]
     w.blocks_done = static_cast<unsigned int*>(take(256));
     w.fb_count = static_cast<int32_t*>(take(256));
+    w.ovf_count = static_cast<int32_t*>(take(256));
     w.fb_arrive = static_cast<unsigned int*>(take((size_t)vq::kFbMaxGroups * sizeof(unsigned int)));
-    w.control_bytes = 512 + (size_t)vq::kFbMaxGroups * sizeof(unsigned int);
+    w.control_bytes = 768 + (size_t)vq::kFbMaxGroups * sizeof(unsigned int);
     w.stats = static_cast<unsigned long long*>(take(256));
     w.bytes = off;
     return w;
@@ -235,6 +272,9 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, int recipe, const
     gp.out_q = w.out_q;
     gp.fb_rows = w.fb_rows;
     gp.fb_count = w.fb_count;
+    gp.ovf = w.ovf;
+    gp.ovf_count = w.ovf_count;
+    gp.ovf_cap = vq::kOvfCap;
     gp.dbg_scores = dbg_scores;
     gp.recipe = recipe;
     gp.timeline = g_timeline;
@@ -381,14 +421,15 @@ static int forward_impl(bool training, bool rows, int recipe, const float* z, in
         if (rc != VQ_OK) return rc;
         // the kernel sizes its own work split from the worklist length so that one wave of resident CTAs covers it
         const unsigned fgrid = (unsigned)(vq::kFbCtasPerSm * dev->sms);
-        if (recipe == vq::kRecipeDiffSq) vq::vq_fallback_kernel<true><<<fgrid, vq::kFbThreads, 0, st>>>(fp);
-        else                             vq::vq_fallback_kernel<false><<<fgrid, vq::kFbThreads, 0, st>>>(fp);
+        if (recipe == vq::kRecipeDiffSq) VQ_CUDA(launch_chained(vq::vq_fallback_kernel<true>, fgrid, vq::kFbThreads, st, fp));
+        else                             VQ_CUDA(launch_chained(vq::vq_fallback_kernel<false>, fgrid, vq::kFbThreads, st, fp));
         VQ_LAUNCH_CHECK("vq_fallback_kernel");
     }
 
     vq::SelectParams sp;
     sp.z = z; sp.E = E; sp.e2 = e2; sp.z2 = w.z2;
     sp.out_cnt = w.out_cnt; sp.out_q = w.out_q;
+    sp.ovf = w.ovf; sp.ovf_count = w.ovf_count;
     sp.N = N; sp.HW = HW; sp.K = K; sp.beta = beta;
     sp.idx = idx; sp.idx_bits = idx_bits; sp.recipe = recipe; sp.zq = zq;
     sp.hist = reinterpret_cast<unsigned long long*>(hist);
@@ -397,12 +438,12 @@ static int forward_impl(bool training, bool rows, int recipe, const float* z, in
     const unsigned grid = (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows);
     const int layout = pick_layout(z, HW, rows);
     if (training) {
-        if (layout == vq::kLayoutVec) vq::vq_select_kernel<true, vq::kLayoutVec><<<grid, vq::kSelThreads, 0, st>>>(sp);
-        else                          vq::vq_select_kernel<true, vq::kLayoutGeneric><<<grid, vq::kSelThreads, 0, st>>>(sp);
+        if (layout == vq::kLayoutVec) VQ_CUDA(launch_chained(vq::vq_select_kernel<true, vq::kLayoutVec>, grid, vq::kSelThreads, st, sp));
+        else                          VQ_CUDA(launch_chained(vq::vq_select_kernel<true, vq::kLayoutGeneric>, grid, vq::kSelThreads, st, sp));
     } else {
-        if (layout == vq::kLayoutRows)     vq::vq_select_kernel<false, vq::kLayoutRows><<<grid, vq::kSelThreads, 0, st>>>(sp);
-        else if (layout == vq::kLayoutVec) vq::vq_select_kernel<false, vq::kLayoutVec><<<grid, vq::kSelThreads, 0, st>>>(sp);
-        else                               vq::vq_select_kernel<false, vq::kLayoutGeneric><<<grid, vq::kSelThreads, 0, st>>>(sp);
+        if (layout == vq::kLayoutRows)     VQ_CUDA(launch_chained(vq::vq_select_kernel<false, vq::kLayoutRows>, grid, vq::kSelThreads, st, sp));
+        else if (layout == vq::kLayoutVec) VQ_CUDA(launch_chained(vq::vq_select_kernel<false, vq::kLayoutVec>, grid, vq::kSelThreads, st, sp));
+        else                               VQ_CUDA(launch_chained(vq::vq_select_kernel<false, vq::kLayoutGeneric>, grid, vq::kSelThreads, st, sp));
     }
     VQ_LAUNCH_CHECK("vq_select_kernel");
     return VQ_OK;

@@ -14,7 +14,19 @@ constexpr int kDChunk = 64;         // 16-bit elements per 128-byte swizzle row
 constexpr int kNumDChunks = kD / kDChunk;
 constexpr int kRingCap = 8;      // candidate ring per (row, epilogue group) in shared memory inside the GEMM epilogue
 constexpr int kOutCap = 16;         // surviving candidate quads handed to the exact stage, per row (half per group)
+constexpr int kOvfCap = 2048;       // entries of the per-call overflow list (candidates that found no room on chip)
 constexpr int kSelRows = 32;        // latents per CTA in the fp32 kernels (prep / select / backward)
+
+// Programmatic dependent launch (PDL).  The kernels of one call form a chain prep_z -> GEMM -> fallback -> select; all but the
+// first are launched with cudaLaunchAttributeProgrammaticStreamSerialization, every kernel calls pdl_trigger() when it starts
+// (its successor may then be scheduled as soon as all of THIS grid's CTAs are resident and resources free up: block
+// scheduling, barrier / TMEM set-up and loads of call inputs overlap this grid's tail) and pdl_wait() before it touches
+// anything a predecessor in the chain wrote (returns once the predecessor grid has completed and its writes are visible;
+// every kernel of the chain calls it, so completion is transitive).  The first kernel of a call is launched normally, so
+// nothing of a call starts before the previous work in the stream -- e.g. the layer that produced z -- has finished.
+// Both are no-ops for a kernel launched without the attribute / without a dependent.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // Tensor-core operands are fp16 scaled by exact powers of two so that the largest magnitude lands in
 // [2^14, 2^15): per latent row for z, per tensor for the codebook.  exponent_of() returns ex with |x| < 2^ex.

@@ -38,6 +38,7 @@ vq_prep_z_kernel(const float* __restrict__ z, int64_t N, int64_t HW, int64_t n_p
     __shared__ __align__(16) float tile[kSelRows * kD];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n0 = (int64_t)blockIdx.x * kSelRows;
+    pdl_trigger();                                            // first kernel of the chain (vq_common.cuh): the GEMM may be scheduled
 
     {   // grid-strided clears (a few KiB in total)
         const int64_t gtid = (int64_t)blockIdx.x * kPrepThreads + tid, gsz = (int64_t)gridDim.x * kPrepThreads;

@@ -47,6 +47,8 @@ struct SelectParams {
     const float* z2;           // (N)
     const int32_t* out_cnt;    // (N, 2)
     const uint32_t* out_q;     // (N, kOutCap)
+    const uint4* ovf;          // overflow list of the GEMM epilogue: (row, chunk id, code mask, chunk minimum)
+    const int32_t* ovf_count;  // entries claimed (clamped to kOvfCap here)
     int64_t N, HW;
     int K;
     float beta;
@@ -62,12 +64,31 @@ struct SelectParams {
 };
 
 // One canonical partial sum of the dot product of latent row r (tile row) with code k: the terms d == j (mod 4) in
-// ascending d, one fma each (oracle/vq_oracle.c: vqo_dot).  Four lanes (j = 0..3) share a (row, code) pair; all 64
-// code-row loads of a lane are independent and issued in two batches of 32, so a pass costs two L2 round trips.
+// ascending d, one fma each (oracle/vq_oracle.c: vqo_dot).  Four lanes (j = 0..3, a "quad") share a (row, code) pair.
+// Code-row loads: the quad reads the row as float4s, lane j taking float4 number 4 s + j of step s (64 contiguous bytes per
+// quad and step, 16 steps), and a 4 x 4 register transpose inside the quad (two butterfly rounds of shuffles) hands lane
+// j the four values d = 16 s + 4 j' + j, j' = 0..3 -- exactly the next four terms of its chain, in order.  A warp request
+// then touches 8 lines for 512 useful bytes instead of 8 lines for 128: the scalar version (one 4-byte load per term, 64
+// requests of 8 wavefronts each per pass) kept the L1 data pipe busy 70 % of the kernel (ncu, round 1: 224 k of 320 k
+// wavefronts per SM came from these loads); the transpose costs 4 shuffles and 12 selects per step on otherwise idle
+// issue slots.  The latent values come from the shared-memory tile with 4-byte loads (four rows per warp: one wavefront).
 // kDiffSq: the terms are fl(fl(z - e)^2) added one by one (v_vq_diffusion.py:121) instead of fused z * e products.
+__device__ __forceinline__ float4 quad_transpose(const float4 a, const bool b0, const bool b1) {
+    // lanes = rows j, components = columns c; returns column j of rows 0..3 (x, y, z, w = rows 0, 1, 2, 3)
+    const float s1 = b1 ? a.x : a.z, s2 = b1 ? a.y : a.w;                  // round 1: 2 x 2 blocks with lane j ^ 2
+    const float r1 = __shfl_xor_sync(0xffffffffu, s1, 2), r2 = __shfl_xor_sync(0xffffffffu, s2, 2);
+    const float x0 = b1 ? r1 : a.x, x1 = b1 ? r2 : a.y, x2 = b1 ? a.z : r1, x3 = b1 ? a.w : r2;
+    const float t1 = b0 ? x0 : x1, t2 = b0 ? x2 : x3;                      // round 2: single elements with lane j ^ 1
+    const float q1 = __shfl_xor_sync(0xffffffffu, t1, 1), q2 = __shfl_xor_sync(0xffffffffu, t2, 1);
+    return make_float4(b0 ? q1 : x0, b0 ? x1 : q1, b0 ? q2 : x2, b0 ? x3 : q2);
+}
+
+// All 32 lanes must call this (shuffles); lanes whose pair is invalid pass k < 0 and get 0.
 template <bool kDiffSq>
 __device__ __forceinline__ float exact_partial_tile(const float* tile, int r, const float* __restrict__ E, int k, int j) {
-    const float* e = E + (int64_t)k * kD + j;
+    const bool live = k >= 0;
+    const float4* e4 = reinterpret_cast<const float4*>(E + (int64_t)(live ? k : 0) * kD) + j;
+    const bool b0 = (j & 1) != 0, b1 = (j & 2) != 0;
     const int g = tile_swz(r);
     const float* zrow = tile + r * kD + j;
     int zo[8];
@@ -76,21 +97,27 @@ __device__ __forceinline__ float exact_partial_tile(const float* tile, int r, co
     float p = 0.0f;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-        float ev[32];
+        float4 v[8];
 #pragma unroll
-        for (int i = 0; i < 32; i++) ev[i] = __ldg(e + 4 * (32 * h + i));
+        for (int s = 0; s < 8; s++) v[s] = live ? __ldg(e4 + 4 * (8 * h + s)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-            const float zv = zrow[32 * (4 * h + (i >> 3)) + zo[i & 7]];
-            if (kDiffSq) {
-                const float diff = __fsub_rn(zv, ev[i]);
-                p = __fadd_rn(p, __fmul_rn(diff, diff));
-            } else {
-                p = __fmaf_rn(zv, ev[i], p);
+        for (int s = 0; s < 8; s++) {
+            const float4 e = quad_transpose(v[s], b0, b1);                 // e_d for d = 16 (8 h + s) + 4 j' + j
+            const float ev[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int i = 4 * (8 * h + s) + jj;                        // term index of the chain: d = 4 i + j
+                const float zv = zrow[32 * (i >> 3) + zo[i & 7]];
+                if (kDiffSq) {
+                    const float diff = __fsub_rn(zv, ev[jj]);
+                    p = __fadd_rn(p, __fmul_rn(diff, diff));
+                } else {
+                    p = __fmaf_rn(zv, ev[jj], p);
+                }
             }
         }
     }
-    return p;
+    return live ? p : 0.0f;
 }
 
 // Distances as unsigned keys whose integer order is torch.argmin's order (codebook.py:82): NaN -> 0, smaller than every
@@ -128,6 +155,10 @@ vq_select_kernel(const SelectParams p) {
         for (int i = 0; i < 8; i++) zreg[i] = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)((warp * 8 + i) * 4) * p.HW));
     }
 
+    // PDL (vq_common.cuh): z is an input of the call, so the loads above were issued while the GEMM / fallback kernels were
+    // finishing; the candidate lists below are theirs
+    pdl_wait();
+
     // 2a. expand this warp's candidate entries (32-code chunk + code mask) into code lists
     //     (counts and entry slots are fetched together, unconditionally: one DRAM round trip instead of two; the 16
     //     slots of a row are one 128-byte line)
@@ -150,29 +181,50 @@ vq_select_kernel(const SelectParams p) {
         const int64_t n = n0 + warp * 4 + rr;
         nq[rr] = 0;
         if (n >= p.N) continue;                               // warp-uniform
-        const int c0 = cnt2[rr].x, c1 = cnt2[rr].y;
+        int c0 = cnt2[rr].x, c1 = cnt2[rr].y;
         const bool resolved = (c0 == -2);
         if (resolved) resolved_mask |= 1u << rr;
+        // bit 8 of a group's count: the group also put entries of this row on the overflow list
+        const bool has_ovf = !resolved && (((c0 >= 0 ? c0 : 0) | (c1 >= 0 ? c1 : 0)) & 0x100) != 0;
+        if (c0 >= 0) c0 &= 0xff;
+        if (c1 >= 0) c1 &= 0xff;
         const int g = lane >> 3, i = lane & 7;                // slot = lane: group g owns slots [8g, 8g + 8)
         const bool valid = resolved ? (lane == 0) : (lane < kOutCap && i < (g ? c1 : c0));
         uint2 e = eq[rr];                                     // (chunk id, mask of candidate codes in the chunk)
         if (!valid) e = make_uint2(0u, 0u);
-        const int pc = __popc(e.y);
-        int incl = pc;
+        int filled = 0;                                       // codes listed so far (warp-uniform)
+        // append the codes of the entries the lanes hold (one entry per lane, in lane order)
+        auto append = [&](uint2 ent) {
+            const int pc = __popc(ent.y);
+            int incl = pc;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int pos = filled + incl - pc;
+            uint32_t bits = ent.y;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (pos < kMaxCands) clist[warp][rr][pos] = (int)ent.x * 32 + b;
+                pos++;
+            }
+            filled += __shfl_sync(0xffffffffu, incl, 31);
+        };
+        append(e);
+        if (has_ovf) {
+            // rare: collect this row's entries from the overflow list (a few dozen entries in all on realistic data)
+            const int n_ovf = min(__ldg(p.ovf_count), kOvfCap);
+            for (int base = 0; base < n_ovf; base += 32) {
+                uint4 oe = make_uint4(0xffffffffu, 0u, 0u, 0u);
+                if (base + lane < n_ovf) oe = __ldcg(p.ovf + base + lane);
+                const bool match = oe.x == (uint32_t)n;
+                if (__ballot_sync(0xffffffffu, match) == 0u) continue;
+                append(match ? make_uint2(oe.y, oe.z) : make_uint2(0u, 0u));
+            }
         }
-        int pos = incl - pc;
-        uint32_t bits = e.y;
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            if (pos < kMaxCands) clist[warp][rr][pos] = (int)e.x * 32 + b;
-            pos++;
-        }
-        nq[rr] = min(kMaxCands, __shfl_sync(0xffffffffu, incl, 31));
+        nq[rr] = min(kMaxCands, filled);
     }
 
     // 1b. z tile into shared memory.  Tokeniser mode loads it only when some row of this CTA has more than one
@@ -208,25 +260,23 @@ vq_select_kernel(const SelectParams p) {
     // 2b. exact distances.  The candidates of the warp's rows that need a decision (>= 2 candidates) are pooled into
     //     one list and dealt out one (row, code) pair per lane, so a pass keeps all 32 lanes busy whatever the split
     //     between rows.  Per pass and row: first minimum over the row's lanes with two redux.sync (distance key, then
-    //     lowest index at that key) and a ballot for the multiplicity; every lane tracks all four rows' results.
+    //     lowest index at that key) and a ballot for the multiplicity; lane rr keeps the running result of row rr.
     {
         int off[5];
         off[0] = 0;
 #pragma unroll
         for (int rr = 0; rr < 4; rr++) off[rr + 1] = off[rr] + (nq[rr] > 1 ? nq[rr] : 0);
         const int total = off[4];
-        uint32_t best_u[4];
-        int best_k[4], n_at_min[4];
-#pragma unroll
-        for (int rr = 0; rr < 4; rr++) {
-            best_u[rr] = 0xffffffffu; best_k[rr] = 0x7fffffff; n_at_min[rr] = 0;
-            if (nq[rr] == 1) {
-                // a single candidate is decided without any arithmetic: the margin argument guarantees that the
-                // oracle's argmin is among the candidates
-                best_k[rr] = clist[warp][rr][0];
-                if (best_k[rr] >= p.K) best_k[rr] = 0;
-                n_at_min[rr] = 1;
-            }
+        // running result of row rr of this warp, kept by lane rr (the per-pass minima below are warp-uniform)
+        uint32_t best_u = 0xffffffffu;
+        int best_k = 0x7fffffff, n_at_min = 0;
+        const int my_nq = (lane == 0) ? nq[0] : (lane == 1) ? nq[1] : (lane == 2) ? nq[2] : nq[3];
+        if (lane < 4 && my_nq == 1) {
+            // a single candidate is decided without any arithmetic: the margin argument guarantees that the
+            // oracle's argmin is among the candidates
+            best_k = clist[warp][lane][0];
+            if (best_k >= p.K) best_k = 0;
+            n_at_min = 1;
         }
         for (int base = 0; base < total; base += 8) {
             const int f = base + (lane >> 2), j = lane & 3;    // pair index, canonical partial sum of this lane
@@ -236,8 +286,8 @@ vq_select_kernel(const SelectParams p) {
             int k = active ? clist[warp][rr][pos] : -1;
             if (k >= p.K) k = -1;                              // pad codes of the last chunk
             const int r = warp * 4 + rr;
-            float pj = 0.0f;
-            if (k >= 0) pj = (p.recipe == kRecipeDiffSq) ? exact_partial_tile<true>(tile, r, p.E, k, j)
+            // (every lane calls: the code-row transpose inside the quad uses shuffles)
+            const float pj = (p.recipe == kRecipeDiffSq) ? exact_partial_tile<true>(tile, r, p.E, k, j)
                                                          : exact_partial_tile<false>(tile, r, p.E, k, j);
             const float dot = combine4(pj);                    // (p0 + p1) + (p2 + p3) on all four lanes
             const bool lead = (k >= 0) && (j == 0);
@@ -251,8 +301,10 @@ vq_select_kernel(const SelectParams p) {
                 const bool at = mine && (u == um);
                 const int km = (int)__reduce_min_sync(0xffffffffu, at ? (uint32_t)k : 0x7fffffffu);
                 const int c = __popc(__ballot_sync(0xffffffffu, at));
-                if (um < best_u[r2]) { best_u[r2] = um; best_k[r2] = km; n_at_min[r2] = c; }
-                else if (um == best_u[r2]) { n_at_min[r2] += c; best_k[r2] = min(best_k[r2], km); }
+                if (lane == r2) {
+                    if (um < best_u) { best_u = um; best_k = km; n_at_min = c; }
+                    else if (um == best_u) { n_at_min += c; best_k = min(best_k, km); }
+                }
             }
         }
         // lane rr publishes row rr of this warp
@@ -260,9 +312,8 @@ vq_select_kernel(const SelectParams p) {
             const int rr = lane;
             const int r = warp * 4 + rr;
             const int64_t n = n0 + r;
-            int bk = (rr == 0) ? best_k[0] : (rr == 1) ? best_k[1] : (rr == 2) ? best_k[2] : best_k[3];
-            const int na = (rr == 0) ? n_at_min[0] : (rr == 1) ? n_at_min[1] : (rr == 2) ? n_at_min[2] : n_at_min[3];
-            const int my_nq = (rr == 0) ? nq[0] : (rr == 1) ? nq[1] : (rr == 2) ? nq[2] : nq[3];
+            int bk = best_k;
+            const int na = n_at_min;
             if (bk == 0x7fffffff) bk = 0;                     // no candidate at all (cannot happen for a row the GEMM listed)
             if (n < p.N) {
                 idx_s[r] = bk;
@@ -402,7 +453,9 @@ vq_fallback_kernel(const FallbackParams p) {
     __shared__ int64_t row_s[kFbGroup], zoff_s[kFbGroup];
     __shared__ int is_final;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int count = __ldg(p.fb_count);
+    pdl_trigger();                                            // PDL (vq_common.cuh): vq_select_kernel may be scheduled ...
+    pdl_wait();                                               // ... and the GEMM's worklist is complete
+    const int count = __ldcg(p.fb_count);
     if (count == 0) return;
     const int groups = (count + kFbGroup - 1) / kFbGroup;
     // code blocks per group: fill the grid once; a multiple of one CTA pass (128 codes) each; never more than kFbMaxParts
