@@ -318,6 +318,9 @@ def main():
     ap.add_argument("--distribution", default="init", choices=["init", "trained"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cuda-graphs", action="store_true",
+                    help="drive the module through its CUDA-graph fast path (CodeBook.use_cuda_graphs; for the small, "
+                         "launch-bound workloads cfg1 / cfg2)")
     ap.add_argument("--soak-seconds", type=float, default=2.0,
                     help="after the timed region, keep stepping for about this long and report the distance-GEMM kernel's "
                          "fraction of peak once clocks have settled under the power cap (roofline.frac_sustained_run); 0 = off")
@@ -365,6 +368,9 @@ def main():
     with torch.no_grad():
         cb.codebook.weight.copy_(E)
     cb.count_launches = True
+    if args.cuda_graphs:
+        cb.use_cuda_graphs = True
+        cb.graph_outputs = "static"                 # the step consumes its results before the next call
     dp = DataParallelVQ(cb) if world > 1 else None
     z_req = z.clone().requires_grad_(not tok)
     g_loss = torch.ones((), device=dev)
@@ -554,7 +560,8 @@ def main():
         "config": {"workload": args.workload + ": " + wl["desc"], "K": K, "D": D, "latents_per_gpu": N,
                    "distribution": args.distribution, "l2": "inputs (2 x 268 MB per GPU) larger than the 126 MB L2"
                    if N * D * 4 > 130e6 else "inputs smaller than L2, no flush (launch-latency-bound workload)",
-                   "parallelism": f"dp{world} (batch-sharded latents, replicated codebook, grad_E all-reduce)"},
+                   "parallelism": f"dp{world} (batch-sharded latents, replicated codebook, grad_E all-reduce)",
+                   "cuda_graphs": bool(args.cuda_graphs)},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "select_stats_last_step": stats,
     }

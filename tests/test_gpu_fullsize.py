@@ -188,4 +188,4 @@ def test_deterministic_backward_is_bit_reproducible(vq, oracle):
     z_q, idx2, loss = cb(z * 1e-6)
     loss.backward()
     _, gE_s = oracle.backward(None, 1.0, z_np * np.float32(1e-6), idx2.cpu().numpy(), cb.codebook.weight.detach().cpu().numpy(), beta=0.25)
-    assert_close(cb.codebook.weight.grad.cpu().numpy(), gE_s, "deterministic grad_E, 1e-6 scale")
+    assert rel_err(cb.codebook.weight.grad.cpu().numpy(), gE_s) <= 1e-5, "deterministic grad_E, 1e-6 scale"

@@ -793,3 +793,62 @@ def test_log_onehot_to_index(vq):
         assert np.array_equal(got.cpu().numpy(), log_onehot_to_index_np(v.cpu().numpy()))
     with pytest.raises(RuntimeError):
         vq.log_onehot_to_index(torch.zeros(2, 3))
+
+
+def test_cuda_graph_fast_path_matches_eager(vq, oracle):
+    """CodeBook.use_cuda_graphs: forward / backward replay captured graphs on static buffers.  Same results as the eager path over
+    several optimizer steps (the weight changes between replays), in frozen / no_grad mode, with "static" outputs, and the
+    guard against a backward whose buffers a later forward overwrote."""
+    dev = torch.device("cuda:0")
+    spec = CASES["cfg2s_trained"]
+    z_np, E_np, g_np = make_inputs(spec)
+    K, D = spec["K"], spec["D"]
+    mods = []
+    for graphs in (False, True):
+        cb = vq.CodeBook(K, D).to(dev)
+        with torch.no_grad():
+            cb.codebook.weight.copy_(torch.from_numpy(E_np))
+        cb.use_cuda_graphs = graphs
+        mods.append(cb)
+    eager, graphed = mods
+    opts = [torch.optim.SGD(m.parameters(), lr=0.5) for m in mods]
+    g = torch.from_numpy(g_np).to(dev).permute(0, 3, 1, 2)
+    for step in range(4):
+        z = torch.from_numpy(z_np).to(dev) * (1.0 + 0.1 * step)
+        outs = []
+        for m, opt in zip(mods, opts):
+            opt.zero_grad(set_to_none=True)
+            zt = z.clone().requires_grad_(True)
+            z_q, idx, loss = m(zt)
+            (loss + (z_q * g).sum()).backward()
+            outs.append((z_q.detach().clone(), idx.clone(), loss.detach().clone(), zt.grad.clone(), m.codebook.weight.grad.clone(),
+                         m.last_histogram.clone()))
+            opt.step()
+        a, b = outs
+        assert b[0].stride() == a[0].stride() and torch.equal(a[0], b[0]), f"z_q step {step}"
+        assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[5], b[5])
+        assert torch.equal(a[3], b[3]), "grad_z"
+        assert rel_err(b[4].cpu().numpy(), a[4].cpu().numpy()) <= 1e-5      # scatter-add order differs
+        with torch.no_grad():                                              # keep the two in lockstep bit for bit (the in-place
+            graphed.codebook.weight.copy_(eager.codebook.weight)           # copy also bumps the version, like the optimizer)
+    # frozen codebook under no_grad (the tokenisers' use): cached derived state follows the weight version
+    for m in mods:
+        m.codebook.weight.requires_grad_(False)
+    z = torch.from_numpy(z_np).to(dev)
+    with torch.no_grad():
+        ra, rb = eager(z), graphed(z)
+        assert torch.equal(ra[1], rb[1]) and torch.equal(ra[0], rb[0]) and torch.equal(ra[2], rb[2])
+        graphed.codebook.weight.mul_(1.5)
+        eager.codebook.weight.mul_(1.5)
+        ra, rb = eager(z), graphed(z)
+        assert torch.equal(ra[1], rb[1]) and torch.equal(ra[0], rb[0])
+    # static outputs alias the graph's buffers; a second forward before the first one's backward is refused
+    for m in mods:
+        m.codebook.weight.requires_grad_(True)
+    graphed.graph_outputs = "static"
+    z1 = z.clone().requires_grad_(True)
+    q1, _, l1 = graphed(z1)
+    q2, _, l2 = graphed(z.clone().requires_grad_(True))
+    assert q1.data_ptr() == q2.data_ptr()
+    with pytest.raises(RuntimeError, match="overwritten"):
+        l1.backward()

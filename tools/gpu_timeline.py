@@ -23,6 +23,8 @@ def main():
     dev = torch.device("cuda:0")
     dist = sys.argv[1] if len(sys.argv) > 1 else "init"
     B, H, W, K, D = 256, 32, 32, 16384, 256
+    if len(sys.argv) > 3:                                  # python tools/gpu_timeline.py init <B> <K>: small shapes, raw rows
+        B, K = int(sys.argv[2]), int(sys.argv[3])
     E, z, _ = make_latents(torch, dev, B, H, W, K, dist, 1234)
     cb = vq.CodeBook(K, D).to(dev)
     with torch.no_grad():
@@ -35,6 +37,16 @@ def main():
         torch.cuda.synchronize()
         _native.check(_native.lib().vq_debug_timeline(None, 0), "timeline off")
     t = stamps.cpu().numpy().astype(np.int64)
+    if len(sys.argv) > 3:
+        # raw view of CTA 0's first code tiles: cycles since its first MMA wait; a row tile is K / 256 consecutive tiles
+        kt = (K + 255) // 256
+        t0 = t[0, 0]
+        print(f"B={B} K={K}: {kt} code tiles per row tile; columns: tile, mma_wait_start, mma_wait_end, mma_issued, epi0_woke, epi0_released, epi0_done, b_wait")
+        for i in range(min(tiles, 5 * kt)):
+            if t[i, 1] == 0:
+                break
+            print(i, "|" if i % kt == 0 else " ", *(int(v - t0) for v in t[i, :6]), int(t[i, 8]))
+        return
     t = t[64:448]                                    # steady state (skip pipeline fill, stay inside row tiles)
     names = ["mma_wait_start", "mma_wait_end", "mma_issued", "epi0_woke", "epi0_released", "epi0_done", "epi1_released", "epi1_done"]
     per_tile = np.diff(t[:, 1]).mean()

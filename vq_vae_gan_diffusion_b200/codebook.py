@@ -168,6 +168,142 @@ class _VQFunction(torch.autograd.Function):
         return grad_z, grad_E, None, None
 
 
+class _GraphState:
+    """CUDA-graph fast path for one (module, input shape, device): static buffers and the captured launch sequences.
+
+    Small shapes (BASELINE.json configs[0] / configs[1]: 200 to 16 384 latents) are bound by launch latency and by the host
+    time of the eager path (~180 us of Python / ctypes / allocator work per step against ~80 us of kernels); replaying a
+    captured graph costs one launch per direction.  The graphs read and write fixed buffers, so a call copies its input in
+    and -- unless ``graph_outputs == "static"`` -- clones its results out."""
+
+    def __init__(self, module, weight, shape):
+        B, D, H, W = shape
+        K = weight.shape[0]
+        dev = weight.device
+        self.shape, self.K, self.dev, self.weight = shape, K, dev, weight
+        self.generation = 0
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.z = torch.empty((B, D, H, W), **f32)
+        self.zq = torch.empty((B, H, W, D), **f32)
+        self.idx = torch.empty((B * H * W,), dtype=torch.int64, device=dev)
+        self.loss = torch.empty((), **f32)
+        self.hist = torch.empty((K,), dtype=torch.int64, device=dev)
+        self.stats = torch.empty((4,), dtype=torch.int64, device=dev)
+        self.g = torch.zeros((B, H, W, D), **f32)                      # upstream gradient, channels-last like z_q
+        self.g_loss = torch.ones((), **f32)
+        self.grad_z = torch.empty((B, D, H, W), **f32)
+        self.grad_E = torch.empty((K, D), **f32)
+        k_pad = _native.padded_codes(K)
+        self.E_h = torch.empty((k_pad, D), dtype=torch.float16, device=dev)
+        self.e2 = torch.empty((k_pad,), **f32)
+        self.cb = torch.empty((4,), **f32)
+        self.ws = torch.empty(_native.workspace_bytes_cached(B * H * W, K, D), dtype=torch.uint8, device=dev)
+        self.ws_bwd = torch.empty(_native.backward_workspace_bytes_cached(K, D), dtype=torch.uint8, device=dev)
+        self.derived_key = None
+        self.beta = float(module.beta)
+        self.graphs = {}
+
+    # ---- what the graphs contain (also used eagerly for the warm-up run before capture)
+    def _prepare(self):
+        K, D = self.weight.shape
+        rc = _native.lib().vq_prepare_codebook(_ptr(self.weight), K, D, _ptr(self.E_h), _ptr(self.e2), _ptr(self.cb),
+                                               _stream_ptr(self.dev))
+        _native.check(rc, "vq_prepare_codebook")
+
+    def _forward(self, refresh):
+        B, D, H, W = self.shape
+        if refresh:
+            self._prepare()
+        rc = _native.lib().vq_forward(_ptr(self.z), B, H * W, D, _ptr(self.weight), _ptr(self.E_h), _ptr(self.e2), _ptr(self.cb),
+                                      self.K, self.beta, _ptr(self.zq), _ptr(self.idx), _ptr(self.loss), _ptr(self.hist),
+                                      _ptr(self.stats), _ptr(self.ws), self.ws.numel(), _stream_ptr(self.dev))
+        _native.check(rc, "vq_forward")
+
+    def _backward(self, need_z, need_w, has_g, scale, det):
+        B, D, H, W = self.shape
+        strides = (ctypes.c_int64 * 3)(H * W * D, 1, D)
+        rc = _native.lib().vq_backward_ex(_ptr(self.g) if has_g else 0, strides, 0.0, _ptr(self.g_loss), _ptr(self.z), _ptr(self.idx),
+                                          _ptr(self.weight), B, H * W, D, self.K, self.beta, B * H * W, float(scale), 1 if det else 0,
+                                          _ptr(self.grad_z) if need_z else 0, _ptr(self.grad_E) if need_w else 0,
+                                          _ptr(self.ws_bwd), self.ws_bwd.numel(), _stream_ptr(self.dev))
+        _native.check(rc, "vq_backward_ex")
+
+    def _graph(self, key, fn):
+        g = self.graphs.get(key)
+        if g is None:
+            cur = torch.cuda.current_stream(self.dev)
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):                              # warm-up outside capture (module load, attributes)
+                fn()
+            cur.wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
+            self.graphs[key] = g
+        return g
+
+    def run_forward(self, z, refresh):
+        self.z.copy_(z)
+        if not refresh:                                                # frozen codebook: derived state follows the weight's version
+            key = (self.weight.data_ptr(), self.weight._version)
+            if key != self.derived_key:
+                self._prepare()
+                self.derived_key = key
+        else:
+            self.derived_key = None
+        self._graph(("fwd", bool(refresh)), lambda: self._forward(refresh)).replay()
+        self.generation += 1
+        return self.generation
+
+    def run_backward(self, g_zq, g_loss, need_z, need_w, scale, det):
+        has_g = g_zq is not None and need_z
+        if has_g:
+            self.g.permute(0, 3, 1, 2).copy_(g_zq)
+        if g_loss is not None:
+            self.g_loss.copy_(g_loss)
+        else:
+            self.g_loss.zero_()
+        key = ("bwd", need_z, need_w, has_g, float(scale), bool(det))
+        self._graph(key, lambda: self._backward(need_z, need_w, has_g, scale, det)).replay()
+
+
+class _VQGraphFunction(torch.autograd.Function):
+    """The CodeBook step through captured CUDA graphs (see _GraphState)."""
+
+    @staticmethod
+    def forward(ctx, z, weight, module, refresh):
+        st = module._graph_state(weight, tuple(z.shape))
+        with _on_device(z.device):
+            gen = st.run_forward(z, refresh)
+            static = module.graph_outputs == "static"
+            zq = st.zq if static else st.zq.clone()
+            idx = st.idx if static else st.idx.clone()
+            loss = st.loss if static else st.loss.clone()
+            hist = st.hist if static else st.hist.clone()
+        object.__setattr__(module, "last_histogram", hist)
+        object.__setattr__(module, "last_stats", st.stats)
+        ctx.state, ctx.generation, ctx.module = st, gen, module
+        ctx.mark_non_differentiable(idx)
+        return zq.permute(0, 3, 1, 2), idx, loss
+
+    @staticmethod
+    def backward(ctx, g_zq, _g_idx, g_loss):
+        st, module = ctx.state, ctx.module
+        need_z, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if not (need_z or need_w):
+            return None, None, None, None
+        if st.generation != ctx.generation:
+            raise RuntimeError("CodeBook(use_cuda_graphs=True): the graph's static buffers were overwritten by a later forward "
+                               "before this backward ran; use the eager path (use_cuda_graphs = False) for this call pattern")
+        with _on_device(st.dev):
+            st.run_backward(g_zq, g_loss, need_z, need_w, module.grad_scale, bool(module.deterministic) and need_w)
+            static = module.graph_outputs == "static"
+            grad_z = (st.grad_z if static else st.grad_z.clone()) if need_z else None
+            grad_E = st.grad_E.clone() if need_w else None               # autograd may keep it as weight.grad: never the static buffer
+        return grad_z, grad_E, None, None
+
+
 class CodeBook(nn.Module):
     """Vector quantiser with the reference's interface (codebook.py:13-111), computed by sm_100a kernels.
 
@@ -206,6 +342,12 @@ class CodeBook(nn.Module):
         # so that the SUM over ranks is the gradient of the global-batch mean.  grad_alloc lets the wrapper place grad_E.
         self.grad_scale = 1.0
         self.grad_alloc = None
+        # use_cuda_graphs=True: forward and backward replay captured CUDA graphs on static buffers (one launch per direction
+        # instead of 3-7 kernels plus ~180 us of host work): for the small, launch-bound shapes.  graph_outputs = "clone"
+        # hands out copies (safe to keep); "static" hands out the graph's own buffers, valid until the next call.
+        self.use_cuda_graphs = False
+        self.graph_outputs = "clone"
+        self._graph_states = {}
         self.last_histogram = None
         self.last_stats = None
 
@@ -240,11 +382,24 @@ class CodeBook(nn.Module):
             self._E_h, self._e2, self._cb, self._derived_key = ent[0], ent[1], ent[2], key
         return ent[0], ent[1], ent[2]
 
+    def _graph_state(self, weight, shape):
+        key = (shape, weight.device, weight.data_ptr())
+        st = self._graph_states.get(key)
+        if st is None:
+            if len(self._graph_states) >= 4:                 # a handful of static shapes, not a cache of everything ever seen
+                self._graph_states.clear()
+            if not (weight.is_contiguous() and weight.data_ptr() % 16 == 0):
+                raise RuntimeError("use_cuda_graphs needs a contiguous, 16-byte aligned codebook weight")
+            st = self._graph_states[key] = _GraphState(self, weight, shape)
+        return st
+
     def refresh_codebook(self) -> None:
         """Drop the cached derived state (needed only after in-place edits through ``weight.data``)."""
         self._derived_key = None
         for ent in self._derived_by_stream.values():
             ent[3] = None
+        for st in self._graph_states.values():
+            st.derived_key = None
 
     def _check_input(self, z: torch.Tensor):
         if self.latent_dim > _KERNEL_D:
@@ -278,6 +433,8 @@ class CodeBook(nn.Module):
         # (grad mode is off inside autograd.Function.forward, so "is the codebook being trained" is decided here)
         refresh = weight.requires_grad and torch.is_grad_enabled()
         if self.latent_dim == _KERNEL_D:
+            if self.use_cuda_graphs and z.numel() > 0 and not torch.cuda.is_current_stream_capturing():
+                return _VQGraphFunction.apply(z, weight, self, refresh)
             return _VQFunction.apply(z, weight, self, refresh)
         # Narrower latents run zero-padded to the kernels' 256 channels.  Exact: a zero channel adds fma(0, 0, p) == p to
         # every norm and dot product, 0 to (e - z)^2 and to every gradient; only the means run over 256 / D times too
@@ -346,6 +503,7 @@ class CodeBook(nn.Module):
         state["_workspace"] = _Workspace()
         state["_workspace_bwd"] = _Workspace()
         state["grad_alloc"] = None
+        state["_graph_states"] = {}
         state["last_histogram"] = None
         state["last_stats"] = None
         return state

@@ -177,8 +177,6 @@ struct Workspace {
     int32_t* fb_count;           // (1)
     float4* fb_part;             // (kFbMaxGroups * kFbGroup, kFbMaxParts)
     unsigned int* fb_arrive;     // (kFbMaxGroups)
-    int32_t* ovf_count;          // (1) entries on the overflow list
-    uint4* ovf;                  // (kOvfCap) candidate entries that found no room on chip (vq_argmin_sm100.cuh)
     unsigned long long* stats;   // (VQ_STAT_COUNT) internal copy when the caller passes none
     size_t control_bytes;        // blocks_done .. fb_arrive, cleared by one memset per call
     size_t bytes;
@@ -201,13 +199,11 @@ Workspace carve(void* base, int64_t N) {
     w.loss_partial = static_cast<double*>(take((size_t)(n_pad / vq::kSelRows) * 8));
     w.fb_rows = static_cast<int32_t*>(take((size_t)n_pad * 2 * 4));
     w.fb_part = static_cast<float4*>(take((size_t)vq::kFbMaxGroups * vq::kFbGroup * vq::kFbMaxParts * sizeof(float4)));
-    w.ovf = static_cast<uint4*>(take((size_t)vq::kOvfCap * sizeof(uint4)));
-    // control words, contiguous so that the first kernel of a call clears them all: [blocks_done | fb_count | ovf_count | fb_arrive]
+    // control words, contiguous so that the first kernel of a call clears them all: [blocks_done | fb_count | fb_arrive]
     w.blocks_done = static_cast<unsigned int*>(take(256));
     w.fb_count = static_cast<int32_t*>(take(256));
-    w.ovf_count = static_cast<int32_t*>(take(256));
     w.fb_arrive = static_cast<unsigned int*>(take((size_t)vq::kFbMaxGroups * sizeof(unsigned int)));
-    w.control_bytes = 768 + (size_t)vq::kFbMaxGroups * sizeof(unsigned int);
+    w.control_bytes = 512 + (size_t)vq::kFbMaxGroups * sizeof(unsigned int);
     w.stats = static_cast<unsigned long long*>(take(256));
     w.bytes = off;
     return w;
@@ -272,9 +268,6 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, int recipe, const
     gp.out_q = w.out_q;
     gp.fb_rows = w.fb_rows;
     gp.fb_count = w.fb_count;
-    gp.ovf = w.ovf;
-    gp.ovf_count = w.ovf_count;
-    gp.ovf_cap = vq::kOvfCap;
     gp.dbg_scores = dbg_scores;
     gp.recipe = recipe;
     gp.timeline = g_timeline;
@@ -429,7 +422,6 @@ static int forward_impl(bool training, bool rows, int recipe, const float* z, in
     vq::SelectParams sp;
     sp.z = z; sp.E = E; sp.e2 = e2; sp.z2 = w.z2;
     sp.out_cnt = w.out_cnt; sp.out_q = w.out_q;
-    sp.ovf = w.ovf; sp.ovf_count = w.ovf_count;
     sp.N = N; sp.HW = HW; sp.K = K; sp.beta = beta;
     sp.idx = idx; sp.idx_bits = idx_bits; sp.recipe = recipe; sp.zq = zq;
     sp.hist = reinterpret_cast<unsigned long long*>(hist);

@@ -49,9 +49,8 @@ constexpr uint32_t kBytesAChunk = kRowTile * kDChunk * 2;    // 16 KiB
 constexpr uint32_t kBytesBStage = kCodeTile * kDChunk * 2;   // 32 KiB
 constexpr uint32_t kBytesE2Tile = kCodeTile * 4;             // 1 KiB
 constexpr uint32_t kTmemCols = 512;
-constexpr int kOutPerGroup = kOutCap / kEpiGroups;           // candidate entries a group may hand over per row in its own slots
-constexpr int kMaxRowCodes = 64;                             // codes per row the exact stage can list (vq_select.cuh: kMaxCands)
-constexpr int kOvfFlag = 0x100;                              // out_cnt bit: this group also put entries on the overflow list
+constexpr int kOutPerGroup = kOutCap / kEpiGroups;           // candidate entries a group may hand over per row
+constexpr int kMaxCodesPerGroup = 32;                        // ... and codes (the exact stage lists <= 64 per row)
 
 struct GemmSmem {
     alignas(1024) uint8_t a[kNumDChunks][kBytesAChunk];      // 64 KiB
@@ -64,7 +63,6 @@ struct GemmSmem {
     int32_t c_part[2][kEpiGroups][kRowTile];                 // 2 KiB   per-group push counts
     float m_live[kEpiGroups][kRowTile];                      // 1 KiB   running minima, refreshed once per code tile
     uint8_t bad_part[kEpiGroups][kRowTile];                  //         per-group "row needs the exact fallback" verdicts
-    uint16_t codes_part[kEpiGroups][kRowTile];               //         per-group number of candidate codes handed over
     alignas(8) uint64_t a_full[kNumDChunks];
     uint64_t a_empty[kNumDChunks];
     uint64_t b_full[2][kStagesB];        // one set per tile parity: each MMA warp sees every phase of its own set
@@ -93,14 +91,6 @@ struct GemmParams {
     uint32_t* out_q;           // (N, kOutCap, 2) entries (chunk id, 32-bit code mask); group g owns slots [g*8, g*8+8)
     int32_t* fb_rows;          // (2N) worklist of the rows flagged -1 (for vq_fallback_kernel)
     int32_t* fb_count;         // (1)  its length, zeroed before launch
-    // Overflow list: candidate entries that found no room in a row's shared-memory ring or in its output slots, as
-    // (row, chunk id, code mask, chunk minimum).  A row whose extra entries all fit here stays on the fast path
-    // (vq_select_kernel collects them); only when the list is full, or a row holds more than kMaxRowCodes candidates,
-    // does the row take the exact full scan.  On the reference's init distribution ~0.02 % of the rows overflow by a few
-    // entries, which used to cost a 50 us scan kernel per call.
-    uint4* ovf;                // (ovf_cap)
-    int32_t* ovf_count;        // (1) entries claimed (may exceed ovf_cap: readers clamp), zeroed before launch
-    int ovf_cap;
     float* dbg_scores;         // (N, K_pad) or null
     int recipe;                // kRecipeExpanded / kRecipeDiffSq: selects the candidate threshold (vq_common.cuh)
     long long* timeline;       // debug: per-tile clock64 stamps of CTA 0 (kTimeline builds), [tile][8]
@@ -311,19 +301,8 @@ vq_argmin_gemm_kernel(const GemmParams p) {
             // score = e2 + cscale * acc,  acc = (z * 2^a) . (e * 2^b)  ->  cscale = -2 * 2^-a * 2^-b  (exact)
             const float cscale = -2.0f * (row_ok ? __ldg(p.z_inv_scale + row) : 1.0f) * e_inv;
             float m_run = INFINITY, thr = INFINITY, lost_min = INFINITY;
-            int cnt = 0, spilled_codes = 0;
+            int cnt = 0;
             uint32_t slot_off = 0;
-            // an entry that cannot stay on chip goes to the global overflow list; when that is full it is "lost" and its
-            // chunk minimum tracked, so that the end of the row knows exactly whether a survivor may be missing
-            auto spill = [&](uint32_t chunk, uint32_t cmask, float cmin) {
-                const int pos = atomicAdd(p.ovf_count, 1);
-                if (pos < p.ovf_cap) {
-                    p.ovf[pos] = make_uint4((uint32_t)row, chunk, cmask, __float_as_uint(cmin));
-                    spilled_codes += __popc(cmask);
-                } else {
-                    lost_min = fminf(lost_min, cmin);
-                }
-            };
 
             for (int kt = 0; kt < p.k_tiles; kt++) {
                 mbar_wait(&s.t_full[buf], phase);
@@ -405,12 +384,7 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                                           (sc[4 * q + 2] <= thr ? 4u : 0u) | (sc[4 * q + 3] <= thr ? 8u : 0u)) << (4 * q);
                             }
                         }
-                        if (cnt >= kRingCap) {
-                            // the ring is full: the oldest entry leaves.  Only one that is still within the (shrinking)
-                            // threshold can survive the final filter and is worth keeping
-                            const float old_s = lds_f32(ring_s_sa + slot_off);
-                            if (old_s <= thr && row_ok) spill(lds_u32(ring_q_sa + slot_off), lds_u32(ring_m_sa + slot_off), old_s);
-                        }
+                        if (cnt >= kRingCap) lost_min = fminf(lost_min, lds_f32(ring_s_sa + slot_off));
                         sts_u32(ring_q_sa + slot_off, (uint32_t)(kt * (kCodeTile / kChunk) + grp * (kGroupCols / kChunk) + c));
                         sts_u32(ring_m_sa + slot_off, cmask);
                         sts_f32(ring_s_sa + slot_off, cm);
@@ -438,38 +412,28 @@ vq_argmin_gemm_kernel(const GemmParams p) {
             if (row_ok) {
                 const float thr_fin = __fmaf_rn(m_fin, cmul, margin);
                 int n_out = 0, n_codes = 0;
+                // nothing recorded at all (NaN row: group 0 reports) or a possible survivor was overwritten
+                bool bad = (cnt_all == 0 && grp == 0) || (lost_min <= thr_fin) || nonfinite;
                 const int live = min(cnt, kRingCap);
                 uint2* dst = reinterpret_cast<uint2*>(p.out_q) + row * kOutCap + grp * kOutPerGroup;
-                if (!nonfinite) {
-                    for (int i = 0; i < live; i++) {
-                        const float cmin = lds_f32(ring_s_sa + i * kSlotStride);
-                        if (cmin <= thr_fin) {
-                            const uint32_t chunk = lds_u32(ring_q_sa + i * kSlotStride);
-                            const uint32_t cmask = lds_u32(ring_m_sa + i * kSlotStride);
-                            if (n_out < kOutPerGroup) { dst[n_out++] = make_uint2(chunk, cmask); n_codes += __popc(cmask); }
-                            else spill(chunk, cmask, cmin);            // more survivors than output slots
-                        }
+                for (int i = 0; i < live && !bad; i++) {
+                    if (lds_f32(ring_s_sa + i * kSlotStride) <= thr_fin) {
+                        const uint32_t chunk = lds_u32(ring_q_sa + i * kSlotStride);
+                        const uint32_t cmask = lds_u32(ring_m_sa + i * kSlotStride);
+                        n_codes += __popc(cmask);
+                        if (n_out < kOutPerGroup && n_codes <= kMaxCodesPerGroup) dst[n_out] = make_uint2(chunk, cmask);
+                        else bad = true;
+                        n_out++;
                     }
                 }
-                // nothing recorded at all (NaN row: group 0 reports), or an entry that may have survived found no room on
-                // the overflow list either
-                const bool bad = (cnt_all == 0 && grp == 0) || (lost_min <= thr_fin) || nonfinite;
-                // (spilled_codes counts the entries spilled during the scan with the threshold of that moment: a superset
-                //  of this group's final survivors among them, which is what the exact stage will see)
-                p.out_cnt[row * kEpiGroups + grp] = bad ? -1 : (n_out | (spilled_codes > 0 ? kOvfFlag : 0));
+                p.out_cnt[row * kEpiGroups + grp] = bad ? -1 : n_out;
                 s.bad_part[grp][trow] = bad ? 1 : 0;
-                s.codes_part[grp][trow] = (uint16_t)min(n_codes + spilled_codes, 0xffff);
             }
-            // a row goes on the fallback worklist ONCE, whichever group(s) flagged it -- or when the two groups together hand
-            // over more codes than the exact stage lists: group 0 decides after seeing group 1's verdict
+            // a row goes on the fallback worklist ONCE, whichever group(s) flagged it: group 0 lists it after seeing
+            // group 1's verdict
             epi_barrier();
-            if (row_ok && grp == 0) {
-                const bool too_many = (int)s.codes_part[0][trow] + (int)s.codes_part[1][trow] > kMaxRowCodes;
-                if ((s.bad_part[0][trow] | s.bad_part[1][trow]) != 0 || too_many) {
-                    if (too_many) p.out_cnt[row * kEpiGroups + 0] = p.out_cnt[row * kEpiGroups + 1] = -1;
-                    p.fb_rows[atomicAdd(p.fb_count, 1)] = (int32_t)row;
-                }
-            }
+            if (row_ok && grp == 0 && (s.bad_part[0][trow] | s.bad_part[1][trow]) != 0)
+                p.fb_rows[atomicAdd(p.fb_count, 1)] = (int32_t)row;
             __syncwarp();
         }
     }

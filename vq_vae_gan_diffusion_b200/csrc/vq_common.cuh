@@ -14,7 +14,6 @@ constexpr int kDChunk = 64;         // 16-bit elements per 128-byte swizzle row
 constexpr int kNumDChunks = kD / kDChunk;
 constexpr int kRingCap = 8;      // candidate ring per (row, epilogue group) in shared memory inside the GEMM epilogue
 constexpr int kOutCap = 16;         // surviving candidate quads handed to the exact stage, per row (half per group)
-constexpr int kOvfCap = 2048;       // entries of the per-call overflow list (candidates that found no room on chip)
 constexpr int kSelRows = 32;        // latents per CTA in the fp32 kernels (prep / select / backward)
 
 // Programmatic dependent launch (PDL).  The kernels of one call form a chain prep_z -> GEMM -> fallback -> select; all but the

@@ -47,8 +47,6 @@ struct SelectParams {
     const float* z2;           // (N)
     const int32_t* out_cnt;    // (N, 2)
     const uint32_t* out_q;     // (N, kOutCap)
-    const uint4* ovf;          // overflow list of the GEMM epilogue: (row, chunk id, code mask, chunk minimum)
-    const int32_t* ovf_count;  // entries claimed (clamped to kOvfCap here)
     int64_t N, HW;
     int K;
     float beta;
@@ -181,50 +179,29 @@ vq_select_kernel(const SelectParams p) {
         const int64_t n = n0 + warp * 4 + rr;
         nq[rr] = 0;
         if (n >= p.N) continue;                               // warp-uniform
-        int c0 = cnt2[rr].x, c1 = cnt2[rr].y;
+        const int c0 = cnt2[rr].x, c1 = cnt2[rr].y;
         const bool resolved = (c0 == -2);
         if (resolved) resolved_mask |= 1u << rr;
-        // bit 8 of a group's count: the group also put entries of this row on the overflow list
-        const bool has_ovf = !resolved && (((c0 >= 0 ? c0 : 0) | (c1 >= 0 ? c1 : 0)) & 0x100) != 0;
-        if (c0 >= 0) c0 &= 0xff;
-        if (c1 >= 0) c1 &= 0xff;
         const int g = lane >> 3, i = lane & 7;                // slot = lane: group g owns slots [8g, 8g + 8)
         const bool valid = resolved ? (lane == 0) : (lane < kOutCap && i < (g ? c1 : c0));
         uint2 e = eq[rr];                                     // (chunk id, mask of candidate codes in the chunk)
         if (!valid) e = make_uint2(0u, 0u);
-        int filled = 0;                                       // codes listed so far (warp-uniform)
-        // append the codes of the entries the lanes hold (one entry per lane, in lane order)
-        auto append = [&](uint2 ent) {
-            const int pc = __popc(ent.y);
-            int incl = pc;
+        const int pc = __popc(e.y);
+        int incl = pc;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            int pos = filled + incl - pc;
-            uint32_t bits = ent.y;
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                if (pos < kMaxCands) clist[warp][rr][pos] = (int)ent.x * 32 + b;
-                pos++;
-            }
-            filled += __shfl_sync(0xffffffffu, incl, 31);
-        };
-        append(e);
-        if (has_ovf) {
-            // rare: collect this row's entries from the overflow list (a few dozen entries in all on realistic data)
-            const int n_ovf = min(__ldg(p.ovf_count), kOvfCap);
-            for (int base = 0; base < n_ovf; base += 32) {
-                uint4 oe = make_uint4(0xffffffffu, 0u, 0u, 0u);
-                if (base + lane < n_ovf) oe = __ldcg(p.ovf + base + lane);
-                const bool match = oe.x == (uint32_t)n;
-                if (__ballot_sync(0xffffffffu, match) == 0u) continue;
-                append(match ? make_uint2(oe.y, oe.z) : make_uint2(0u, 0u));
-            }
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
         }
-        nq[rr] = min(kMaxCands, filled);
+        int pos = incl - pc;
+        uint32_t bits = e.y;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (pos < kMaxCands) clist[warp][rr][pos] = (int)e.x * 32 + b;
+            pos++;
+        }
+        nq[rr] = min(kMaxCands, __shfl_sync(0xffffffffu, incl, 31));
     }
 
     // 1b. z tile into shared memory.  Tokeniser mode loads it only when some row of this CTA has more than one
@@ -328,9 +305,15 @@ vq_select_kernel(const SelectParams p) {
             }
         }
     }
-    __syncthreads();
-    if (p.stats != nullptr && tid < 4 && st_s[tid] != 0) atomicAdd(p.stats + tid, (unsigned long long)st_s[tid]);
-    if (!kForward) return;
+    if (!kForward) {
+        __syncthreads();
+        if (p.stats != nullptr && tid < 4 && st_s[tid] != 0) atomicAdd(p.stats + tid, (unsigned long long)st_s[tid]);
+        return;
+    }
+    // No CTA-wide barrier here: a warp's tail only needs its OWN rows' decisions (idx_s entries written by its own lanes),
+    // so warps without re-rank work stream their z_q rows while others are still evaluating candidates (ncu, round 2:
+    // 3.9 warps per issue slot were parked at this barrier).  The per-CTA counters are flushed after the loss barrier below.
+    __syncwarp();
 
     // 3. forward tail, 16 bytes per lane and request: lane <-> d in [4 lane, 4 lane + 4) and [128 + 4 lane, ...); all four
     //    code rows of this warp are requested before the first one is consumed
@@ -375,6 +358,7 @@ vq_select_kernel(const SelectParams p) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     if (lane == 0) red_s[warp] = v;
     __syncthreads();
+    if (p.stats != nullptr && tid >= 32 && tid < 36 && st_s[tid - 32] != 0) atomicAdd(p.stats + (tid - 32), (unsigned long long)st_s[tid - 32]);
     if (tid == 0) {
         double sum = 0.0;
         for (int w = 0; w < kSelWarps; w++) sum += red_s[w];
