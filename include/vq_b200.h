@@ -12,7 +12,8 @@
  *   - return value 0 = OK, otherwise a negative VQ_E_* code or a positive cudaError_t;
  *     vq_last_error() gives a thread-local message;
  *   - the library is re-entrant (forward runs on the caller's thread, backward on PyTorch's autograd thread);
- *   - D (latent_dim) must be 256 -- the value of every reference config (configs/*.yml) -- else VQ_E_UNSUPPORTED;
+ *   - D (latent_dim) must be 256 for the NCHW CodeBook entry points -- the value of every reference config
+ *     (configs/*.yml) -- else VQ_E_UNSUPPORTED; the row-major searches (vq_argmin_rows) take any 1 <= D <= 512;
  *   - N = B*HW latents in (b, h, w) order, z is contiguous NCHW (B, D, HW).
  *   - there is NO CPU fallback: on a device that is not sm_100 every compute entry point fails with
  *     VQ_E_DEVICE.
@@ -46,6 +47,7 @@ typedef struct CUstream_st* vq_stream_t; /* == cudaStream_t */
 /* fp32 distance recipes of the reference's nearest-code searches (vq_argmin_rows) */
 #define VQ_RECIPE_EXPANDED 0  /* |x|^2 + |e|^2 - 2 x.e   codebook.py:70-79, diffusion_gaussian2d.py:334-339 */
 #define VQ_RECIPE_DIFFSQ   1  /* sum_d (x_d - e_d)^2     continous_vq_diffusion/v_vq_diffusion.py:114-123 */
+#define VQ_RECIPE_CDIST_NORMALIZED 2  /* cdist(normalize(x), normalize(T)): vqDiffusion/submodule/diffusion_gaussian3d.py:543-570 */
 
 int         vq_abi_version(void);
 const char* vq_last_error(void);
@@ -105,8 +107,13 @@ int vq_argmin_narrow(const float* z_nchw, int64_t B, int64_t HW, int D,
  *   VQ_RECIPE_DIFFSQ    replaces the search at the end of V_VQDiffusion.sample
  *                       (network/continous_vq_diffusion/v_vq_diffusion.py:114-123: sum((x - e)^2) over a broadcast
  *                       (B, L, K, D) difference, which this path never materialises).
- * D must be 256 here; narrower vectors (gaussian_dim = 96 in
- * configs/*.yml) are zero-padded by the caller, which changes no distance (see nearest.py).
+ *   VQ_RECIPE_CDIST_NORMALIZED  replaces VQGaussianDiffusion3DWrapper.gaussian_to_indices
+ *                       (network/vqDiffusion/submodule/diffusion_gaussian3d.py:543-570): both sides L2-normalised
+ *                       (F.normalize), torch.cdist, argmin.  The query rows are normalised inside the call; E / E_h /
+ *                       e_norm2 must describe the NORMALISED table (vq_normalize_rows, then vq_prepare_codebook).
+ * Any width 1 <= D <= 512 (gaussian_dim = 96 in configs/*.yml, 512 in the 3D wrapper's own runs): the contraction is
+ * padded to a multiple of 64 inside the kernels, nothing is padded in memory; vq_workspace_bytes and vq_prepare_codebook
+ * take the same D.
  *   x_rows  (N, D) fp32, contiguous
  *   idx     (N) integers of idx_bits (64 / 32 / 16)
  */
@@ -114,6 +121,10 @@ int vq_argmin_rows(const float* x_rows, int64_t N, int D,
                    const float* E, const void* E_h, const float* e_norm2, const float* cb_scalars, int K,
                    int recipe, void* idx, int idx_bits, unsigned long long* stats,
                    void* workspace, size_t workspace_bytes, vq_stream_t stream);
+
+/* F.normalize(x, p=2, dim=-1) of row-major vectors: out = x / max(|x|_2, 1e-12) (diffusion_gaussian3d.py:560-563), the norm
+ * summed in the oracle's canonical order.  1 <= D <= 512. */
+int vq_normalize_rows(const float* x_rows, int64_t N, int D, float* out_rows, vq_stream_t stream);
 
 /*
  * Training forward.  Replaces CodeBook.forward, codebook.py:47-111.

@@ -300,6 +300,74 @@ VQO_API int vq_oracle_nearest_diffsq(const float* x_rows, int64_t N, int D, cons
 }
 
 /*
+ * Nearest table row under the recipe of VQGaussianDiffusion3DWrapper.gaussian_to_indices
+ * (/root/reference/network/vqDiffusion/submodule/diffusion_gaussian3d.py:543-570):
+ *     table = F.normalize(table, p=2, dim=-1); x = F.normalize(x, p=2, dim=-1)        :560-563
+ *     distances = torch.cdist(x, table); distances.argmin(-1)                          :566-569
+ * F.normalize divides by max(|v|_2, 1e-12) (clamp_min keeps a NaN).  torch.cdist (p = 2, more than 25 rows: the matmul
+ * path, aten/src/ATen/native/Distance.cpp _euclidean_dist) evaluates the squared distance as ONE matrix product of the
+ * augmented vectors [-2 x, |x|^2, 1] . [y, 1, |y|^2], then clamp_min(0).sqrt().  Canonical restatement: the D + 2 terms run
+ * through vqo_dot's four fma chains (term d goes to chain d mod 4, ascending), so the two norm terms are the last terms of
+ * chains D mod 4 and (D + 1) mod 4; norms are canonical dot products; first minimum of the square roots, NaN counts as
+ * the minimum.
+ *   x_rows (N, D), table (K, D) raw (normalised here); idx (N); dist_min (N), tie_rows, table_hat (K, D) optional outputs.
+ */
+static inline float vqo_normalize_denom(float norm2) {
+    const float nrm = sqrtf(norm2);
+    return (nrm < 1e-12f) ? 1e-12f : nrm;
+}
+
+static inline float vqo_cdist(const float* x, float xn, const float* y, float yn, int D) {
+    float p[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int d = 0; d < D; d++) p[d & 3] = fmaf(-2.0f * x[d], y[d], p[d & 3]);
+    p[D & 3] = fmaf(xn, 1.0f, p[D & 3]);
+    p[(D + 1) & 3] = fmaf(1.0f, yn, p[(D + 1) & 3]);
+    volatile float a = p[0] + p[1], b = p[2] + p[3];
+    volatile float d2 = a + b;
+    return sqrtf(d2 < 0.0f ? 0.0f : d2);                  /* clamp_min(0).sqrt(); a NaN stays a NaN */
+}
+
+VQO_API int vq_oracle_nearest_cdist(const float* x_rows, int64_t N, int D, const float* table, int K,
+                                    int64_t* idx, float* dist_min, uint64_t* tie_rows, float* table_hat) {
+    if (N < 0 || D <= 0 || K <= 0 || !idx) return -1;
+    float* th = table_hat ? table_hat : (float*)malloc(sizeof(float) * (size_t)K * (size_t)D);
+    float* tn = (float*)malloc(sizeof(float) * (size_t)K);
+    if (!th || !tn) return -2;
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < K; k++) {
+        const float* t = table + (int64_t)k * D;
+        const float den = vqo_normalize_denom(vqo_dot(t, 1, t, 1, D));
+        for (int d = 0; d < D; d++) th[(int64_t)k * D + d] = t[d] / den;
+        tn[k] = vqo_dot(th + (int64_t)k * D, 1, th + (int64_t)k * D, 1, D);
+    }
+    uint64_t ties = 0;
+#pragma omp parallel reduction(+ : ties)
+    {
+        float* xh = (float*)malloc(sizeof(float) * (size_t)D);
+#pragma omp for schedule(dynamic, 16)
+        for (int64_t n = 0; n < N; n++) {
+            const float* x = x_rows + n * (int64_t)D;
+            const float den = vqo_normalize_denom(vqo_dot(x, 1, x, 1, D));
+            for (int d = 0; d < D; d++) xh[d] = x[d] / den;
+            const float xn = vqo_dot(xh, 1, xh, 1, D);
+            float best = INFINITY;
+            int64_t best_k = 0;
+            int n_best = 0;
+            for (int k = 0; k < K; k++)
+                vqo_argmin_step(k, vqo_cdist(xh, xn, th + (int64_t)k * D, tn[k], D), &best, &best_k, &n_best);
+            idx[n] = best_k;
+            if (dist_min) dist_min[n] = best;
+            if (n_best > 1) ties++;
+        }
+        free(xh);
+    }
+    if (tie_rows) *tie_rows = ties;
+    if (!table_hat) free(th);
+    free(tn);
+    return 0;
+}
+
+/*
  * Distances of selected (row, code) pairs in canonical order -- lets the tests classify a
  * disagreement without recomputing whole rows.
  */

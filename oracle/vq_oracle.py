@@ -62,6 +62,8 @@ class COracle:
         L.vq_oracle_pair_dist.restype = None
         L.vq_oracle_nearest_diffsq.argtypes = [_f32p, ctypes.c_int64, ctypes.c_int, _f32p, ctypes.c_int, _i64p, _f32p, _u64p]
         L.vq_oracle_nearest_diffsq.restype = ctypes.c_int
+        L.vq_oracle_nearest_cdist.argtypes = [_f32p, ctypes.c_int64, ctypes.c_int, _f32p, ctypes.c_int, _i64p, _f32p, _u64p, _f32p]
+        L.vq_oracle_nearest_cdist.restype = ctypes.c_int
         L.vq_oracle_backward.argtypes = [_f32p, _i64p, ctypes.c_float, _f32p, _i64p, _f32p, ctypes.c_int64,
                                          ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int64,
                                          _f32p, _f32p]
@@ -120,6 +122,23 @@ class COracle:
         if rc != 0:
             raise RuntimeError(f"vq_oracle_nearest_diffsq rc={rc}")
         return dict(idx=idx, dist_min=dmin, tie_rows=int(ties.value))
+
+    def nearest_cdist(self, x: np.ndarray, table: np.ndarray):
+        """x: (..., D) fp32 rows, table: (K, D) raw -> dict(idx (N,), dist_min, tie_rows, table_hat) under the recipe of
+        VQGaussianDiffusion3DWrapper.gaussian_to_indices (diffusion_gaussian3d.py:543-570): both sides L2-normalised, torch.cdist's
+        augmented matrix product, clamp_min(0).sqrt(), first minimum (canonical order)."""
+        table = np.ascontiguousarray(table, dtype=np.float32)
+        rows = np.ascontiguousarray(np.asarray(x, dtype=np.float32).reshape(-1, table.shape[1]))
+        N = rows.shape[0]
+        idx = np.empty(N, np.int64)
+        dmin = np.empty(N, np.float32)
+        th = np.empty_like(table)
+        ties = ctypes.c_uint64(0)
+        rc = self.lib.vq_oracle_nearest_cdist(_p(rows, _f32p), N, table.shape[1], _p(table, _f32p), table.shape[0], _p(idx, _i64p),
+                                              _p(dmin, _f32p), ctypes.byref(ties), _p(th, _f32p))
+        if rc != 0:
+            raise RuntimeError(f"vq_oracle_nearest_cdist rc={rc}")
+        return dict(idx=idx, dist_min=dmin, tie_rows=int(ties.value), table_hat=th)
 
     def pair_dist(self, z: np.ndarray, E: np.ndarray, rows, codes) -> np.ndarray:
         z = np.ascontiguousarray(z, dtype=np.float32)

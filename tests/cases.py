@@ -120,6 +120,44 @@ def make_diffsq_inputs(spec: dict):
     return np.ascontiguousarray(x.reshape(B, L, D), dtype=np.float32), E
 
 
+# Normalise + cdist search of VQGaussianDiffusion3DWrapper.gaussian_to_indices (diffusion_gaussian3d.py:543-570).  The wrapper's
+# table is positional_encoding(gaussian_dim, vocab_size) (diffusion_gaussian3d.py:48-54, :513): sin / cos of position x
+# frequency -- restated here because it is the realistic input (neighbouring rows are close: near-ties), next to random tables.
+CDIST_CASES = {
+    "cd_pe512":     dict(B=2, L=64, K=1024, D=512, table="pe", noise=0.05, seed=501),     # the 3D wrapper's own shape family
+    "cd_pe96":      dict(B=3, L=50, K=1024, D=96, table="pe", noise=0.3, seed=502),       # gaussian_dim: 96 of configs/*.yml
+    "cd_rand96":    dict(B=2, L=40, K=2048, D=96, table="rand", noise=1.0, seed=503),     # far from every row
+    "cd_ragged":    dict(B=3, L=37, K=333, D=70, table="rand", noise=0.2, seed=504),      # width off every vector path
+    "cd_rand256":   dict(B=2, L=32, K=512, D=256, table="rand", noise=0.5, seed=505),
+    "cd_dup128":    dict(B=2, L=48, K=300, D=128, table="dup", noise=0.1, seed=506),      # every row three times: lowest index wins
+}
+
+
+def positional_table(dim: int, num_vectors: int) -> np.ndarray:
+    """diffusion_gaussian3d.py:48-54 (float64 numpy, then float32)."""
+    position = np.arange(num_vectors)[:, np.newaxis]
+    div_term = np.exp(np.arange(0, dim, 2) * -(np.log(10000.0) / dim))
+    pe = np.zeros((num_vectors, dim))
+    pe[:, 0::2] = np.sin(position * div_term)
+    pe[:, 1::2] = np.cos(position * div_term)
+    return pe.astype(np.float32)
+
+
+def make_cdist_inputs(spec: dict):
+    """-> x (B, L, D) fp32 (unnormalised predictions around table rows), table (K, D) fp32."""
+    rng = np.random.default_rng(spec["seed"])
+    B, L, K, D = spec["B"], spec["L"], spec["K"], spec["D"]
+    if spec["table"] == "pe":
+        table = positional_table(D, K)
+    elif spec["table"] == "dup":
+        base = rng.standard_normal((K // 3, D), dtype=np.float32)
+        table = np.concatenate([base, base, base], axis=0)[:K]
+    else:
+        table = rng.standard_normal((K, D), dtype=np.float32)
+    x = table[rng.integers(0, K, size=B * L)] * np.float32(1.7) + np.float32(spec["noise"]) * rng.standard_normal((B * L, D), dtype=np.float32)
+    return np.ascontiguousarray(x.reshape(B, L, D), dtype=np.float32), np.ascontiguousarray(table)
+
+
 # Token-stream formats after the tokeniser (SURVEY.md 8(f) n4).  index_to_log_onehot: the vector path (L % 4 == 0), the
 # scalar path, trailing dims beyond one (the VQ-Diffusion tokens are (B, L); the function is rank-generic), the class
 # count off the 32-class tile, the [MASK] class (num_classes = K + 1) unused.

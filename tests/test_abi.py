@@ -38,7 +38,11 @@ def test_host_side_validation_without_gpu():
     assert L.vq_workspace_bytes(1000, 1024, 256, ctypes.byref(out)) == 0 and out.value > 1000 * 256 * 2
     small = out.value
     assert L.vq_workspace_bytes(100000, 1024, 256, ctypes.byref(out)) == 0 and out.value > small
-    assert L.vq_workspace_bytes(1000, 1024, 128, ctypes.byref(out)) == -2          # VQ_E_UNSUPPORTED: D != 256
+    # the row-major searches take any width up to 512 (narrower contraction -> smaller operand image); beyond that: unsupported
+    assert L.vq_workspace_bytes(1000, 1024, 96, ctypes.byref(out)) == 0 and out.value < small
+    assert L.vq_workspace_bytes(1000, 1024, 512, ctypes.byref(out)) == 0 and out.value > small
+    assert L.vq_workspace_bytes(1000, 1024, 513, ctypes.byref(out)) == -2          # VQ_E_UNSUPPORTED
+    assert L.vq_workspace_bytes(1000, 1024, 0, ctypes.byref(out)) == -2
     assert b"256" in L.vq_last_error()
     assert L.vq_workspace_bytes(-1, 1024, 256, ctypes.byref(out)) == -1            # VQ_E_INVALID
     # compute entry points reject bad arguments before touching the device
@@ -113,10 +117,13 @@ def test_nearest_search_host_side_validation():
     with pytest.raises(RuntimeError, match="no CPU path"):
         vq.CodeTable(torch.zeros(4, 96))                       # CPU table
     with pytest.raises(ValueError):
-        vq.CodeTable(torch.zeros(4, 300))                      # wider than the kernels
+        vq.CodeTable(torch.zeros(4, 600))                      # wider than the kernels (D <= 512)
     L = _native.lib()
-    # row-major / narrow entry points validate before touching the device: unknown recipe, bad index width, D != 256
-    assert L.vq_argmin_rows(None, 0, 128, None, None, None, None, 16, 0, None, 64, None, None, 0, None) == -2
+    # row-major / narrow entry points validate before touching the device: width beyond 512, unknown recipe, bad index width
+    assert L.vq_argmin_rows(None, 0, 513, None, None, None, None, 16, 0, None, 64, None, None, 0, None) == -2
+    assert L.vq_argmin_rows(None, 0, 128, None, None, None, None, 16, 7, None, 64, None, None, 0, None) == -1
+    assert L.vq_argmin_rows(None, 0, 128, None, None, None, None, 16, 2, None, 24, None, None, 0, None) == -1
+    assert L.vq_normalize_rows(None, 4, 600, None, None) == -2
     assert L.vq_argmin_narrow(None, 1, 1, 64, None, None, None, None, 16, None, 32, None, None, 0, None) == -2
 
 

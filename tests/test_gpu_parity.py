@@ -852,3 +852,85 @@ def test_cuda_graph_fast_path_matches_eager(vq, oracle):
     assert q1.data_ptr() == q2.data_ptr()
     with pytest.raises(RuntimeError, match="overwritten"):
         l1.backward()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SURVEY.md 8(f) n2, third site: VQGaussianDiffusion3DWrapper.gaussian_to_indices (normalise + cdist + argmin), and the
+# native table widths of all three recipes
+from cases import CDIST_CASES, make_cdist_inputs  # noqa: E402
+from test_oracle_golden import classify_cdist  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(CDIST_CASES))
+def test_gaussian_to_indices_3d_vs_oracle_and_reference(name, vq, oracle):
+    spec = CDIST_CASES[name]
+    dev = torch.device("cuda:0")
+    x, table = make_cdist_inputs(spec)
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    tab = vq.CodeTable(torch.from_numpy(table).to(dev))
+    xt = torch.from_numpy(x).to(dev)
+    idx = vq.gaussian_to_indices(xt, tab)
+    assert idx.shape == (spec["B"], spec["L"]) and idx.dtype == torch.int64
+    assert torch.equal(vq.gaussian_to_indices(xt.unsqueeze(1), tab), idx)            # (B, 1, L, D) is squeezed like :547-548
+    ref = oracle.nearest_cdist(x, table)
+    got = idx.reshape(-1).cpu().numpy()
+    assert np.array_equal(got, ref["idx"]), np.nonzero(got != ref["idx"])[0][:8]
+    st = dict(zip(vq._native.VQ_STAT_NAMES, tab.last_stats.tolist()))
+    assert st["tie_rows"] == ref["tie_rows"], (st, ref["tie_rows"])
+    cls = classify_cdist(x, table, got, gold["idx"].reshape(-1).astype(np.int64))
+    assert cls["real"] == 0, cls
+    # the other two recipes at the same (native) width
+    xr = x.reshape(-1, spec["D"])
+    z_grid = np.ascontiguousarray(xr.reshape(-1, 1, 1, spec["D"]).transpose(0, 3, 1, 2))
+    assert np.array_equal(tab.nearest(xt, recipe="expanded").reshape(-1).cpu().numpy(), oracle.forward(z_grid, table, want_zq=False)["idx"])
+    assert np.array_equal(tab.nearest(xt, recipe="diffsq").reshape(-1).cpu().numpy(), oracle.nearest_diffsq(xr, table)["idx"])
+    assert torch.equal(tab.nearest(xt, recipe="cdist_normalized", dtype=torch.int32).long(), idx)
+
+
+@pytest.mark.parametrize("D,K,N", [(512, 1024, 4096), (96, 2048, 5003), (33, 70, 300), (64, 256, 257), (128, 4100, 2000), (500, 300, 129)])
+def test_rows_path_native_widths_large_ragged(D, K, N, vq, oracle):
+    """Every contraction width (1, 2, 4, 8 chunks of 64), ragged N / K / D, all three recipes; NaN / Inf rows and a cluster of
+    near-identical table rows (more than 64 candidates -> exact-scan fallback) follow the oracle."""
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(1000 + D)
+    table = rng.standard_normal((K, D)).astype(np.float32)
+    if K >= 300:
+        v = rng.standard_normal(D).astype(np.float32)
+        table[100:200] = v + 1e-5 * rng.standard_normal((100, D)).astype(np.float32)      # 100 near-identical rows
+        table[250:260] = table[7]                                                          # exact duplicates of row 7
+    x = table[rng.integers(0, K, N)] + 0.3 * rng.standard_normal((N, D)).astype(np.float32)
+    if K >= 300:
+        x[:5] = v + 0.01 * rng.standard_normal((5, D)).astype(np.float32)
+        x[5:9] = table[7]
+    x[9, D // 2] = np.nan
+    x[10, 0] = np.inf
+    x[11] = 0.0
+    tab = vq.CodeTable(torch.from_numpy(table).to(dev))
+    xt = torch.from_numpy(x).to(dev)
+    for recipe in ("expanded", "diffsq", "cdist_normalized"):
+        idx = tab.nearest(xt, recipe=recipe).cpu().numpy()
+        if recipe == "expanded":
+            ref = oracle.forward(np.ascontiguousarray(x.reshape(N, 1, 1, D).transpose(0, 3, 1, 2)), table, want_zq=False, fast=True)
+        elif recipe == "diffsq":
+            ref = oracle.nearest_diffsq(x, table)
+        else:
+            ref = oracle.nearest_cdist(x, table)
+        bad = np.nonzero(idx != ref["idx"])[0]
+        assert bad.size == 0, (recipe, bad[:8], idx[bad[:8]], ref["idx"][bad[:8]])
+        st = dict(zip(vq._native.VQ_STAT_NAMES, tab.last_stats.tolist()))
+        assert st["tie_rows"] == ref["tie_rows"], (recipe, st, ref["tie_rows"])
+        if K >= 300:
+            assert st["fallback_rows"] >= 2, (recipe, st)          # the NaN / Inf rows at least
+
+
+def test_normalize_rows_matches_oracle(vq, oracle):
+    """vq_normalize_rows == F.normalize in the canonical order (bit-exact against the oracle's normalised table)."""
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(3)
+    for K, D in ((300, 96), (1024, 512), (17, 5), (64, 256)):
+        t = rng.standard_normal((K, D)).astype(np.float32) * 5
+        t[3] = 0.0
+        tab = vq.CodeTable(torch.from_numpy(t).to(dev))
+        E_hat = tab._prepare(True)[0]
+        ref = oracle.nearest_cdist(t[:4], t)
+        assert np.array_equal(E_hat.cpu().numpy(), ref["table_hat"])

@@ -362,3 +362,58 @@ def test_log_onehot_to_index_oracle_matches_torch_argmax():
     v[1, 6, 2] = np.nan                                 # first NaN wins
     v[2, :, 0] = -np.inf
     assert np.array_equal(log_onehot_to_index_np(v), torch.from_numpy(v).argmax(1).numpy())
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Normalise + cdist recipe (VQGaussianDiffusion3DWrapper.gaussian_to_indices, diffusion_gaussian3d.py:543-570)
+from cases import CDIST_CASES, make_cdist_inputs  # noqa: E402
+
+
+def classify_cdist(x, table, idx_a, idx_b):
+    """Disagreeing rows between two index vectors under the normalise + cdist recipe: a real mismatch is one whose two
+    float64 distances (on float64-normalised vectors) differ by more than the fp32 rounding band of the matmul-form squared
+    distance (magnitudes ~|x|^2 + |y|^2 = 2, a D + 2 term fp32 sum and the normalisation's own roundings)."""
+    rows = x.reshape(-1, x.shape[-1]).astype(np.float64)
+    t = table.astype(np.float64)
+    rows /= np.maximum(np.linalg.norm(rows, axis=1, keepdims=True), 1e-12)
+    t /= np.maximum(np.linalg.norm(t, axis=1, keepdims=True), 1e-12)
+    bad = np.nonzero(idx_a != idx_b)[0]
+    real = 0
+    for r in bad:
+        da = ((rows[r] - t[idx_a[r]]) ** 2).sum()
+        db = ((rows[r] - t[idx_b[r]]) ** 2).sum()
+        if abs(da - db) > (x.shape[-1] + 16) * 2.0 ** -23:
+            real += 1
+    return dict(mismatch=int(bad.size), real=real)
+
+
+@pytest.mark.parametrize("name", sorted(CDIST_CASES))
+def test_oracle_matches_reference_cdist(name, oracle):
+    spec = CDIST_CASES[name]
+    gold = np.load(os.path.join(GOLDEN, name + ".npz"))
+    x, table = make_cdist_inputs(spec)
+    ref = oracle.nearest_cdist(x, table)
+    gidx = gold["idx"].reshape(-1).astype(np.int64)
+    cls = classify_cdist(x, table, ref["idx"], gidx)
+    assert cls["real"] == 0, cls
+    assert cls["mismatch"] <= int(gold["ref_tie_rows"]) + int(gold["ref_ne_fp64"]) + 2, cls
+    if spec["table"] == "dup":
+        assert ref["tie_rows"] == ref["idx"].size and (ref["idx"] < spec["K"] // 3).all()     # lowest of the three copies
+
+
+def test_cdist_oracle_against_torch_ops(oracle):
+    """The restated pieces against torch on CPU: F.normalize, and argmin(cdist) up to rounding-band rows."""
+    import torch
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((50, 96)).astype(np.float32) * 3
+    t = rng.standard_normal((200, 96)).astype(np.float32)
+    ref = oracle.nearest_cdist(x, t)
+    th = torch.nn.functional.normalize(torch.from_numpy(t), p=2, dim=-1).numpy()
+    assert np.abs(ref["table_hat"] - th).max() <= 2e-7
+    idx = torch.cdist(torch.nn.functional.normalize(torch.from_numpy(x), p=2, dim=-1), torch.from_numpy(th)).argmin(-1).numpy()
+    assert classify_cdist(x, t, ref["idx"], idx)["real"] == 0
+    # zero rows: normalise divides by 1e-12 and leaves them zero; every table row is then at distance sqrt(|y|^2) ~ 1 (the
+    # winner is whichever normalised row rounds lowest: inside the rounding band of any other)
+    z = np.zeros((2, 96), np.float32)
+    out = oracle.nearest_cdist(z, t)
+    assert np.abs(out["dist_min"] - 1.0).max() <= 1e-6

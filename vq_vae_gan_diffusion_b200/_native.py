@@ -23,7 +23,7 @@ NVCC_FLAGS = [
 ]
 
 VQ_STAT_NAMES = ("tie_rows", "rerank_rows", "fallback_rows", "candidates")
-VQ_RECIPES = {"expanded": 0, "diffsq": 1}          # VQ_RECIPE_* of include/vq_b200.h
+VQ_RECIPES = {"expanded": 0, "diffsq": 1, "cdist_normalized": 2}          # VQ_RECIPE_* of include/vq_b200.h
 
 
 class VQNativeError(RuntimeError):
@@ -92,6 +92,7 @@ _SIGNATURES = {
     "vq_argmin": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _sz, _vp]),
     "vq_argmin_narrow": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _int, _vp, _vp, _sz, _vp]),
     "vq_argmin_rows": (_int, [_vp, _i64, _int, _vp, _vp, _vp, _vp, _int, _int, _vp, _int, _vp, _vp, _sz, _vp]),
+    "vq_normalize_rows": (_int, [_vp, _i64, _int, _vp, _vp]),
     "vq_forward": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vq_backward": (_int, [_vp, ctypes.POINTER(_i64), _f32, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _f32, _i64, _vp, _vp, _vp]),
     "vq_backward_workspace_bytes": (_int, [_int, _int, ctypes.POINTER(_sz)]),

@@ -277,10 +277,12 @@ class _VQGraphFunction(torch.autograd.Function):
         with _on_device(z.device):
             gen = st.run_forward(z, refresh)
             static = module.graph_outputs == "static"
-            zq = st.zq if static else st.zq.clone()
-            idx = st.idx if static else st.idx.clone()
-            loss = st.loss if static else st.loss.clone()
-            hist = st.hist if static else st.hist.clone()
+            # "static": fresh VIEWS of the graph's buffers (never the same tensor objects twice: autograd would re-point the
+            # earlier call's outputs at this call's node)
+            zq = st.zq.view(st.zq.shape) if static else st.zq.clone()
+            idx = st.idx.view(-1) if static else st.idx.clone()
+            loss = st.loss.view(()) if static else st.loss.clone()
+            hist = st.hist.view(-1) if static else st.hist.clone()
         object.__setattr__(module, "last_histogram", hist)
         object.__setattr__(module, "last_stats", st.stats)
         ctx.state, ctx.generation, ctx.module = st, gen, module
@@ -299,7 +301,7 @@ class _VQGraphFunction(torch.autograd.Function):
         with _on_device(st.dev):
             st.run_backward(g_zq, g_loss, need_z, need_w, module.grad_scale, bool(module.deterministic) and need_w)
             static = module.graph_outputs == "static"
-            grad_z = (st.grad_z if static else st.grad_z.clone()) if need_z else None
+            grad_z = (st.grad_z.view(st.grad_z.shape) if static else st.grad_z.clone()) if need_z else None
             grad_E = st.grad_E.clone() if need_w else None               # autograd may keep it as weight.grad: never the static buffer
         return grad_z, grad_E, None, None
 

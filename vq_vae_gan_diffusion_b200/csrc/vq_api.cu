@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
 
 #include "../../include/vq_b200.h"
 #include "vq_argmin_sm100.cuh"
@@ -17,6 +18,7 @@
 #include "vq_common.cuh"
 #include "vq_prep.cuh"
 #include "vq_select.cuh"
+#include "vq_rows.cuh"
 #include "vq_tokens.cuh"
 
 #define VQ_EXPORT extern "C" __attribute__((visibility("default")))
@@ -86,11 +88,11 @@ cudaError_t launch_chained(Kernel kernel, unsigned grid, unsigned block, cudaStr
 
 // launch of one GEMM variant: as clusters of two CTAs (one cluster per pair of row tiles, at most one per two SMs) when
 // `share`, else one CTA per row tile up to one per SM
-template <bool kDebug, bool kTimeline>
+template <bool kDebug, bool kTimeline, int kNC = vq::kNumDChunks>
 cudaError_t launch_gemm(const vq::GemmParams& gp, bool share, int sms, cudaStream_t st) {
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(vq::kGemmThreads);
-    cfg.dynamicSmemBytes = vq::kGemmSmemBytes;
+    cfg.dynamicSmemBytes = vq::gemm_smem_bytes<kNC>();
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     int n_attr = 0;
@@ -109,11 +111,11 @@ cudaError_t launch_gemm(const vq::GemmParams& gp, bool share, int sms, cudaStrea
         attr[n_attr].val.clusterDim.z = 1;
         n_attr++;
         cfg.numAttrs = n_attr;
-        return cudaLaunchKernelEx(&cfg, vq::vq_argmin_gemm_kernel<kDebug, kTimeline, true>, gp);
+        return cudaLaunchKernelEx(&cfg, vq::vq_argmin_gemm_kernel<kDebug, kTimeline, true, kNC>, gp);
     }
     cfg.numAttrs = n_attr;
     cfg.gridDim = dim3(gp.row_tiles < sms ? gp.row_tiles : sms);
-    return cudaLaunchKernelEx(&cfg, vq::vq_argmin_gemm_kernel<kDebug, kTimeline, false>, gp);
+    return cudaLaunchKernelEx(&cfg, vq::vq_argmin_gemm_kernel<kDebug, kTimeline, false, kNC>, gp);
 }
 
 // ---- optional timing of the distance-GEMM kernel (bench.py's roofline): a ring of event pairs recorded on the
@@ -158,6 +160,16 @@ int device_info(DevInfo** out) {
                                        (const void*)vq::vq_argmin_gemm_kernel<false, true, true>};
         for (const void* fn : gemm_variants)
             VQ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vq::kGemmSmemBytes));
+        // the other contraction widths (row-major nearest-code searches)
+        const std::pair<const void*, size_t> rows_variants[] = {
+            {(const void*)vq::vq_argmin_gemm_kernel<false, false, false, 1>, vq::gemm_smem_bytes<1>()},
+            {(const void*)vq::vq_argmin_gemm_kernel<false, false, true, 1>, vq::gemm_smem_bytes<1>()},
+            {(const void*)vq::vq_argmin_gemm_kernel<false, false, false, 2>, vq::gemm_smem_bytes<2>()},
+            {(const void*)vq::vq_argmin_gemm_kernel<false, false, true, 2>, vq::gemm_smem_bytes<2>()},
+            {(const void*)vq::vq_argmin_gemm_kernel<false, false, false, 8>, vq::gemm_smem_bytes<8>()},
+            {(const void*)vq::vq_argmin_gemm_kernel<false, false, true, 8>, vq::gemm_smem_bytes<8>()}};
+        for (const auto& v : rows_variants)
+            VQ_CUDA(cudaFuncSetAttribute(v.first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.second));
         d.attrs_set = true;
     }
     *out = &d;
@@ -169,6 +181,7 @@ struct Workspace {
     __half* z_h;            // (N_pad, D)
     float* z2;              // (N)
     float* z_inv_scale;     // (N)
+    float* denom;           // (N) L2-normalisation divisors of the rows (cdist recipe)
     int32_t* out_cnt;       // (N, 2) one count per epilogue group
     uint32_t* out_q;        // (N, kOutCap) candidate entries (chunk << 8 | quad mask)
     double* loss_partial;   // (ceil(N/32))
@@ -182,7 +195,10 @@ struct Workspace {
     size_t bytes;
 };
 
-Workspace carve(void* base, int64_t N) {
+// chunks of 64 the contraction is padded to
+inline int chunks_for(int D) { return D <= 64 ? 1 : D <= 128 ? 2 : D <= 256 ? 4 : 8; }
+
+Workspace carve(void* base, int64_t N, int D = vq::kD) {
     Workspace w;
     const int64_t n_pad = round_up(N > 0 ? N : 1, 2 * vq::kRowTile);      // whole PAIRS of GEMM row tiles
     size_t off = 0;
@@ -191,9 +207,10 @@ Workspace carve(void* base, int64_t N) {
         off += (size_t)round_up((int64_t)bytes, 256);
         return p;
     };
-    w.z_h = static_cast<__half*>(take((size_t)n_pad * vq::kD * 2));
+    w.z_h = static_cast<__half*>(take((size_t)n_pad * (size_t)(chunks_for(D) * vq::kDChunk) * 2));
     w.z2 = static_cast<float*>(take((size_t)n_pad * 4));
     w.z_inv_scale = static_cast<float*>(take((size_t)n_pad * 4));
+    w.denom = static_cast<float*>(take((size_t)n_pad * 4));
     w.out_cnt = static_cast<int32_t*>(take((size_t)n_pad * 2 * 4));
     w.out_q = static_cast<uint32_t*>(take((size_t)n_pad * vq::kOutCap * 8));
     w.loss_partial = static_cast<double*>(take((size_t)(n_pad / vq::kSelRows) * 8));
@@ -294,8 +311,8 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, int recipe, const
     return VQ_OK;
 }
 
-int check_ws(void* ws, size_t ws_bytes, int64_t N, Workspace* w) {
-    *w = carve(ws, N);
+int check_ws(void* ws, size_t ws_bytes, int64_t N, Workspace* w, int D = vq::kD) {
+    *w = carve(ws, N, D);
     if (ws == nullptr) return fail(VQ_E_INVALID, "null workspace");
     if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(VQ_E_INVALID, "workspace must be 256-byte aligned");
     if (ws_bytes < w->bytes)
@@ -303,7 +320,76 @@ int check_ws(void* ws, size_t ws_bytes, int64_t N, Workspace* w) {
     return VQ_OK;
 }
 
-static_assert(VQ_RECIPE_EXPANDED == vq::kRecipeExpanded && VQ_RECIPE_DIFFSQ == vq::kRecipeDiffSq, "header and kernels disagree");
+static_assert(VQ_RECIPE_EXPANDED == vq::kRecipeExpanded && VQ_RECIPE_DIFFSQ == vq::kRecipeDiffSq &&
+              VQ_RECIPE_CDIST_NORMALIZED == vq::kRecipeCdist, "header and kernels disagree");
+
+// ---- row-major nearest-code search at any width D <= 512 (vq_rows.cuh): prep -> GEMM -> exact-scan fallback -> select
+template <int kNC>
+int run_rows_path(const float* x, int64_t N, int D, int recipe, const float* E, const void* E_h, const float* e2, const float* cb, int K,
+                  void* idx, int idx_bits, unsigned long long* stats, const Workspace& w, cudaStream_t st) {
+    using C = vq::RowsCfg<kNC>;
+    DevInfo* dev;
+    int rc = device_info(&dev);
+    if (rc != VQ_OK) return rc;
+    const int64_t n_pad = round_up(N, 2 * vq::kRowTile);
+    const int k_pad = vq_padded_codes(K);
+    const bool normalize = recipe == vq::kRecipeCdist;
+    vq::PrepClear clr;
+    clr.control = w.blocks_done;
+    clr.control_words = (int)(w.control_bytes / sizeof(unsigned int));
+    clr.hist = nullptr;
+    clr.K = K;
+    clr.stats = stats;
+    clr.n_stats = VQ_STAT_COUNT;
+    const unsigned pgrid = (unsigned)(n_pad / C::kRows);
+    if (normalize) vq::vq_prep_rows_kernel<kNC, true><<<pgrid, vq::kPrepThreads, 0, st>>>(x, N, D, n_pad, w.z_h, w.z2, w.z_inv_scale, w.denom, nullptr, clr);
+    else           vq::vq_prep_rows_kernel<kNC, false><<<pgrid, vq::kPrepThreads, 0, st>>>(x, N, D, n_pad, w.z_h, w.z2, w.z_inv_scale, nullptr, nullptr, clr);
+    VQ_LAUNCH_CHECK("vq_prep_rows_kernel");
+
+    vq::GemmParams gp;
+    gp.z_h = w.z_h;
+    gp.e_h = static_cast<const __half*>(E_h);
+    gp.e2 = e2;
+    gp.cb = cb;
+    gp.z2 = w.z2;
+    gp.z_inv_scale = w.z_inv_scale;
+    gp.N = N;
+    gp.k_tiles = k_pad / vq::kCodeTile;
+    gp.row_tiles = (int)(round_up(N, vq::kRowTile) / vq::kRowTile);
+    gp.out_cnt = w.out_cnt;
+    gp.out_q = w.out_q;
+    gp.fb_rows = w.fb_rows;
+    gp.fb_count = w.fb_count;
+    gp.dbg_scores = nullptr;
+    gp.recipe = recipe;
+    gp.timeline = nullptr;
+    gp.timeline_tiles = 0;
+    VQ_CUDA((launch_gemm<false, false, kNC>(gp, gemm_share() && gp.row_tiles >= 2, dev->sms, st)));
+    VQ_LAUNCH_CHECK("vq_argmin_gemm_kernel");
+
+    vq::SelectRowsParams sp;
+    sp.x = x; sp.denom = normalize ? w.denom : nullptr; sp.E = E; sp.e2 = e2; sp.z2 = w.z2;
+    sp.out_cnt = w.out_cnt; sp.out_q = w.out_q;
+    sp.N = N; sp.D = D; sp.K = K;
+    sp.idx = idx; sp.idx_bits = idx_bits; sp.recipe = recipe; sp.stats = stats;
+    sp.fb_rows = w.fb_rows; sp.fb_count = w.fb_count;
+    sp.part = w.fb_part; sp.arrive = w.fb_arrive;
+    VQ_CUDA(launch_chained(vq::vq_fallback_rows_kernel<kNC>, (unsigned)(2 * dev->sms), vq::kSelThreads, st, sp));
+    VQ_LAUNCH_CHECK("vq_fallback_rows_kernel");
+    VQ_CUDA(launch_chained(vq::vq_select_rows_kernel<kNC>, (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows), vq::kSelThreads, st, sp));
+    VQ_LAUNCH_CHECK("vq_select_rows_kernel");
+    return VQ_OK;
+}
+
+template <int kNC>
+int run_table_prep(const float* E, int K, int D, void* E_h, float* e2, float* cb, cudaStream_t st) {
+    const int k_pad = vq_padded_codes(K);
+    vq::vq_table_norms_kernel<kNC><<<k_pad / vq::kSelRows, vq::kPrepThreads, 0, st>>>(E, K, D, k_pad, e2, cb);
+    VQ_LAUNCH_CHECK("vq_table_norms_kernel");
+    vq::vq_table_convert_kernel<kNC><<<k_pad / vq::kSelRows, vq::kPrepThreads, 0, st>>>(E, K, D, k_pad, static_cast<__half*>(E_h), cb);
+    VQ_LAUNCH_CHECK("vq_table_convert_kernel");
+    return VQ_OK;
+}
 
 }  // namespace
 
@@ -344,16 +430,16 @@ VQ_EXPORT int vq_padded_codes(int K) { return (int)round_up(K > 0 ? K : 1, vq::k
 
 VQ_EXPORT int vq_workspace_bytes(int64_t N, int K, int D, size_t* out) {
     if (out == nullptr) return fail(VQ_E_INVALID, "null out pointer");
-    if (D != vq::kD) return fail(VQ_E_UNSUPPORTED, "latent_dim D=%d is not supported (D must be 256)", D);
+    if (D < 1 || D > 512) return fail(VQ_E_UNSUPPORTED, "width D=%d is not supported (1 <= D <= 512; the NCHW CodeBook entry points need 256)", D);
     if (N < 0 || K < 1) return fail(VQ_E_INVALID, "bad shape N=%lld K=%d", (long long)N, K);
-    *out = carve(nullptr, N).bytes;
+    *out = carve(nullptr, N, D).bytes;
     return VQ_OK;
 }
 
 VQ_EXPORT int vq_prepare_codebook(const float* E, int K, int D, void* E_h, float* e_norm2, float* cb_scalars,
                                   vq_stream_t stream) {
     g_launches = 0;
-    if (D != vq::kD) return fail(VQ_E_UNSUPPORTED, "latent_dim D=%d is not supported (D must be 256)", D);
+    if (D < 1 || D > 512) return fail(VQ_E_UNSUPPORTED, "width D=%d is not supported (1 <= D <= 512)", D);
     if (K < 1) return fail(VQ_E_UNSUPPORTED, "K=%d", K);
     if (!E || !E_h || !e_norm2 || !cb_scalars) return fail(VQ_E_INVALID, "null pointer");
     DevInfo* dev;
@@ -362,6 +448,14 @@ VQ_EXPORT int vq_prepare_codebook(const float* E, int K, int D, void* E_h, float
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const int k_pad = vq_padded_codes(K);
     VQ_CUDA(cudaMemsetAsync(cb_scalars, 0, 4 * sizeof(float), st));
+    if (D != vq::kD) {                                        // lookup tables of other widths (operand image of 64-chunk count chunks_for(D))
+        switch (chunks_for(D)) {
+            case 1: return run_table_prep<1>(E, K, D, E_h, e_norm2, cb_scalars, st);
+            case 2: return run_table_prep<2>(E, K, D, E_h, e_norm2, cb_scalars, st);
+            case 4: return run_table_prep<4>(E, K, D, E_h, e_norm2, cb_scalars, st);
+            default: return run_table_prep<8>(E, K, D, E_h, e_norm2, cb_scalars, st);
+        }
+    }
     vq::vq_codebook_norms_kernel<<<k_pad / vq::kSelRows, vq::kPrepThreads, 0, st>>>(E, K, k_pad, e_norm2, cb_scalars);
     VQ_LAUNCH_CHECK("vq_codebook_norms_kernel");
     vq::vq_codebook_convert_kernel<<<k_pad / vq::kSelRows, vq::kPrepThreads, 0, st>>>(E, K, k_pad,
@@ -458,8 +552,59 @@ VQ_EXPORT int vq_argmin_narrow(const float* z_nchw, int64_t B, int64_t HW, int D
 VQ_EXPORT int vq_argmin_rows(const float* x_rows, int64_t N, int D, const float* E, const void* E_h, const float* e_norm2,
                              const float* cb_scalars, int K, int recipe, void* idx, int idx_bits, unsigned long long* stats,
                              void* workspace, size_t workspace_bytes, vq_stream_t stream) {
+    if (D != vq::kD || recipe == vq::kRecipeCdist) {
+        // any other width, and the normalise + cdist recipe: the generic row-major path (vq_rows.cuh)
+        g_launches = 0;
+        if (D < 1 || D > 512) return fail(VQ_E_UNSUPPORTED, "width D=%d is not supported (1 <= D <= 512)", D);
+        if (K < 1) return fail(VQ_E_UNSUPPORTED, "K=%d", K);
+        if (N < 0 || N >= (int64_t)1 << 31) return fail(VQ_E_INVALID, "bad row count N=%lld", (long long)N);
+        if (recipe != vq::kRecipeExpanded && recipe != vq::kRecipeDiffSq && recipe != vq::kRecipeCdist)
+            return fail(VQ_E_INVALID, "unknown distance recipe %d", recipe);
+        if (idx_bits != 64 && idx_bits != 32 && idx_bits != 16) return fail(VQ_E_INVALID, "idx_bits must be 16, 32 or 64, got %d", idx_bits);
+        if (idx_bits == 16 && K > 65536) return fail(VQ_E_INVALID, "16-bit indices need K <= 65536, got K=%d", K);
+        cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+        if (N == 0) {
+            if (stats) VQ_CUDA(cudaMemsetAsync(stats, 0, VQ_STAT_COUNT * sizeof(unsigned long long), st));
+            return VQ_OK;
+        }
+        if (!x_rows || !E || !E_h || !e_norm2 || !cb_scalars || !idx) return fail(VQ_E_INVALID, "null pointer");
+        Workspace w;
+        int rc = check_ws(workspace, workspace_bytes, N, &w, D);
+        if (rc != VQ_OK) return rc;
+        switch (chunks_for(D)) {
+            case 1: return run_rows_path<1>(x_rows, N, D, recipe, E, E_h, e_norm2, cb_scalars, K, idx, idx_bits, stats, w, st);
+            case 2: return run_rows_path<2>(x_rows, N, D, recipe, E, E_h, e_norm2, cb_scalars, K, idx, idx_bits, stats, w, st);
+            case 4: return run_rows_path<4>(x_rows, N, D, recipe, E, E_h, e_norm2, cb_scalars, K, idx, idx_bits, stats, w, st);
+            default: return run_rows_path<8>(x_rows, N, D, recipe, E, E_h, e_norm2, cb_scalars, K, idx, idx_bits, stats, w, st);
+        }
+    }
     return forward_impl(false, true, recipe, x_rows, N, 1, D, E, E_h, e_norm2, cb_scalars, K, 0.0f, nullptr, idx, idx_bits, nullptr,
                         nullptr, stats, workspace, workspace_bytes, stream);
+}
+
+VQ_EXPORT int vq_normalize_rows(const float* x_rows, int64_t N, int D, float* out_rows, vq_stream_t stream) {
+    g_launches = 0;
+    if (D < 1 || D > 512) return fail(VQ_E_UNSUPPORTED, "width D=%d is not supported (1 <= D <= 512)", D);
+    if (N < 0) return fail(VQ_E_INVALID, "bad row count N=%lld", (long long)N);
+    if (N == 0) return VQ_OK;
+    if (!x_rows || !out_rows) return fail(VQ_E_INVALID, "null pointer");
+    DevInfo* dev;
+    int rc = device_info(&dev);
+    if (rc != VQ_OK) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    vq::PrepClear clr = {};
+#define VQ_NORM_LAUNCH(NC)                                                                                                   \
+    vq::vq_prep_rows_kernel<NC, true><<<(unsigned)((N + vq::RowsCfg<NC>::kRows - 1) / vq::RowsCfg<NC>::kRows), vq::kPrepThreads, 0, st>>>( \
+        x_rows, N, D, N, nullptr, nullptr, nullptr, nullptr, out_rows, clr)
+    switch (chunks_for(D)) {
+        case 1: VQ_NORM_LAUNCH(1); break;
+        case 2: VQ_NORM_LAUNCH(2); break;
+        case 4: VQ_NORM_LAUNCH(4); break;
+        default: VQ_NORM_LAUNCH(8);
+    }
+#undef VQ_NORM_LAUNCH
+    VQ_LAUNCH_CHECK("vq_prep_rows_kernel");
+    return VQ_OK;
 }
 
 VQ_EXPORT int vq_forward(const float* z_nchw, int64_t B, int64_t HW, int D, const float* E, const void* E_h,

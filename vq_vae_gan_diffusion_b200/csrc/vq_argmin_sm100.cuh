@@ -39,7 +39,9 @@
 
 namespace vq {
 
-constexpr int kStagesB = 4;
+// Operand-ring depth for a contraction of kNC chunks of 64: four 32 KiB stages next to a resident latent tile of up to
+// 64 KiB (kNC <= 4); D = 512 (kNC = 8) keeps a 128 KiB latent tile resident and is left with two stages.
+__host__ __device__ constexpr int gemm_stages(int nc) { return nc == 8 ? 2 : 4; }
 constexpr int kEpiGroups = 2;
 constexpr int kGroupCols = kCodeTile / kEpiGroups;           // 128 accumulator columns per epilogue group
 constexpr int kChunk = 32;                                   // codes per tcgen05.ld / per candidate entry
@@ -52,8 +54,10 @@ constexpr uint32_t kTmemCols = 512;
 constexpr int kOutPerGroup = kOutCap / kEpiGroups;           // candidate entries a group may hand over per row
 constexpr int kMaxCodesPerGroup = 32;                        // ... and codes (the exact stage lists <= 64 per row)
 
-struct GemmSmem {
-    alignas(1024) uint8_t a[kNumDChunks][kBytesAChunk];      // 64 KiB
+template <int kNC>
+struct GemmSmemT {
+    static constexpr int kStagesB = gemm_stages(kNC);
+    alignas(1024) uint8_t a[kNC][kBytesAChunk];              // 64 KiB at D = 256
     alignas(1024) uint8_t b[kStagesB][kBytesBStage];         // 128 KiB
     alignas(16) float e2s[2][kCodeTile];                     // 2 KiB   |e|^2 of the code tile in accumulator buffer b
     uint32_t ring_q[kEpiGroups][kRingCap][kRowTile];         // 8 KiB   chunk ids, [slot][row]: conflict-free
@@ -63,8 +67,8 @@ struct GemmSmem {
     int32_t c_part[2][kEpiGroups][kRowTile];                 // 2 KiB   per-group push counts
     float m_live[kEpiGroups][kRowTile];                      // 1 KiB   running minima, refreshed once per code tile
     uint8_t bad_part[kEpiGroups][kRowTile];                  //         per-group "row needs the exact fallback" verdicts
-    alignas(8) uint64_t a_full[kNumDChunks];
-    uint64_t a_empty[kNumDChunks];
+    alignas(8) uint64_t a_full[kNC];
+    uint64_t a_empty[kNC];
     uint64_t b_full[2][kStagesB];        // one set per tile parity: each MMA warp sees every phase of its own set
     uint64_t b_empty[kStagesB];
     uint64_t t_full[2];
@@ -73,9 +77,11 @@ struct GemmSmem {
     uint64_t e2_empty[2];
     uint32_t tmem_base;
 };
-constexpr size_t kGemmSmemBytes = sizeof(GemmSmem) + 1024;   // + slack for manual 1024 B alignment
-static_assert(kStagesB == kNumDChunks, "the MMA issuers assume the operand ring holds exactly one code tile");
-static_assert(kGemmSmemBytes <= 232448, "exceeds the 227 KiB of shared memory a CTA can opt into");
+template <int kNC>
+constexpr size_t gemm_smem_bytes() { return sizeof(GemmSmemT<kNC>) + 1024; }   // + slack for manual 1024 B alignment
+constexpr size_t kGemmSmemBytes = gemm_smem_bytes<kNumDChunks>();
+static_assert(gemm_smem_bytes<1>() <= 232448 && gemm_smem_bytes<2>() <= 232448 && gemm_smem_bytes<4>() <= 232448 &&
+              gemm_smem_bytes<8>() <= 232448, "exceeds the 227 KiB of shared memory a CTA can opt into");
 
 struct GemmParams {
     const __half* z_h;         // operand image of the latents  [row tile][D chunk][128][64] (vq_prep.cuh)
@@ -109,10 +115,15 @@ __device__ __forceinline__ void epi_barrier() {               // the 256 epilogu
 
 // kShare: launched as clusters of two CTAs that share the codebook stream (see the header); a work unit is then a PAIR of
 // row tiles (row tile 2u + rank for the CTA of that rank; z_h is padded to whole pairs), otherwise one row tile.
-template <bool kDebugScores, bool kTimeline = false, bool kShare = false>
+// kNC: the contraction runs over kNC chunks of 64 (D padded to 64 kNC; 4 = the CodeBook's 256, the others serve the
+// row-major nearest-code searches at their native widths, vq_rows.cuh).
+template <bool kDebugScores, bool kTimeline = false, bool kShare = false, int kNC = kNumDChunks>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 vq_argmin_gemm_kernel(const GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
+    using GemmSmem = GemmSmemT<kNC>;
+    constexpr int kStagesB = GemmSmem::kStagesB;
+    constexpr int kTilesInRing = (kNC < kStagesB) ? kStagesB / kNC : 1;     // whole code tiles the operand ring holds
     GemmSmem& s = *reinterpret_cast<GemmSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
     const int warp = threadIdx.x >> 5;
@@ -123,7 +134,7 @@ vq_argmin_gemm_kernel(const GemmParams p) {
     const int n_units = kShare ? (p.row_tiles + 1) / 2 : p.row_tiles;
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < kNumDChunks; i++) { mbar_init(&s.a_full[i], 1); mbar_init(&s.a_empty[i], 1); }
+        for (int i = 0; i < kNC; i++) { mbar_init(&s.a_full[i], 1); mbar_init(&s.a_empty[i], 1); }
         // (a shared stage is refilled when BOTH CTAs' MMAs on it have committed)
         for (int i = 0; i < kStagesB; i++) { mbar_init(&s.b_full[0][i], 1); mbar_init(&s.b_full[1][i], 1); mbar_init(&s.b_empty[i], kShare ? 2 : 1); }
         for (int i = 0; i < 2; i++) {
@@ -159,17 +170,17 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                 const int64_t rt = kShare ? 2 * (int64_t)u + rank : u;
                 for (int kt = 0; kt < p.k_tiles; kt++, it++) {
                     uint64_t* const bfull = s.b_full[it & 1];
-                    for (int dc = 0; dc < kNumDChunks; dc++) {
+                    for (int dc = 0; dc < kNC; dc++) {
                         if (kt == 0) {
                             mbar_wait(&s.a_empty[dc], a_phase ^ 1);
                             if (elect_one()) {
                                 mbar_expect_tx(&s.a_full[dc], kBytesAChunk);
-                                bulk_load_1d_hint(s.a[dc], p.z_h + (rt * kNumDChunks + dc) * (kRowTile * kDChunk),
+                                bulk_load_1d_hint(s.a[dc], p.z_h + (rt * kNC + dc) * (kRowTile * kDChunk),
                                                   kBytesAChunk, &s.a_full[dc], pol_stream);
                             }
                             __syncwarp();
                         }
-                        const __half* src = p.e_h + ((int64_t)kt * kNumDChunks + dc) * (kCodeTile * kDChunk);
+                        const __half* src = p.e_h + ((int64_t)kt * kNC + dc) * (kCodeTile * kDChunk);
                         if (kShare) {
                             // this CTA fetches the codes [128 rank, 128 rank + 128) of the stage for both CTAs; each CTA arms
                             // its own barrier for the whole stage
@@ -220,10 +231,11 @@ vq_argmin_gemm_kernel(const GemmParams p) {
             long long it = 0;                                   // global code-tile counter of this CTA
             int rti = 0, tl_seq = 0;
             for (int u = unit0; u < n_units; u += unit_step, rti++) {
-                // both warps look at every row tile's z chunks (even when a short codebook gives a warp no code tile in
-                // this row tile): an mbarrier parity wait must never fall a whole phase behind
-#pragma unroll
-                for (int dc = 0; dc < kNumDChunks; dc++) mbar_wait(&s.a_full[dc], rti & 1);
+                // Both warps look at every row tile's z chunks (even when a short codebook gives a warp no code tile in
+                // this row tile): an mbarrier parity wait must never fall a whole phase behind.  The looks happen chunk by
+                // chunk inside the warp's first code tile of the row tile, so its MMAs start when chunk 0 has landed (short
+                // codebooks spend a visible share of a row tile at this boundary: profiles/r2_gemm_timeline_cfg5.log).
+                bool a_seen = false;
                 for (int kt = 0; kt < p.k_tiles; kt++, it++) {
                     if ((uint32_t)(it & 1) != buf) continue;
                     const uint32_t use = (uint32_t)(it >> 1);    // how often this buffer was used before
@@ -237,34 +249,46 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                     }
                     long long tl_bwait = 0;
 #pragma unroll
-                    for (int dc = 0; dc < kNumDChunks; dc++) {
-                        // the ring holds exactly one code tile: stage == dc, and its parity flips every tile
+                    for (int dc = 0; dc < kNC; dc++) {
+                        // Where chunk (it, dc) sits in the operand ring and how often THIS warp's barrier set has seen that
+                        // stage before (its parity).  The ring holds kTilesInRing whole code tiles (slots it % kTilesInRing;
+                        // an even number of them, or one: a stage then alternates between the two warps' sets), or -- D = 512
+                        // -- a quarter of one, each stage being used kNC / kStagesB times per tile.
+                        const int stage = (kNC <= kStagesB) ? (int)(it % kTilesInRing) * kNC + dc : dc % kStagesB;
+                        const uint32_t seen = (kNC < kStagesB) ? (uint32_t)(it / kTilesInRing)
+                                            : (kNC == kStagesB) ? use : use * (uint32_t)(kNC / kStagesB) + (uint32_t)(dc / kStagesB);
                         long long tb0 = 0;
                         if (kTimeline) tb0 = clock64();
-                        if (kShare) mbar_wait_cluster(&s.b_full[buf][dc], use & 1);    // half of it was written by the peer's copy
-                        else mbar_wait(&s.b_full[buf][dc], use & 1);
+                        if (!a_seen) mbar_wait(&s.a_full[dc], rti & 1);
+                        if (kShare) mbar_wait_cluster(&s.b_full[buf][stage], seen & 1);    // half of it was written by the peer's copy
+                        else mbar_wait(&s.b_full[buf][stage], seen & 1);
                         tc_fence_after();
                         if (kTimeline) tl_bwait += clock64() - tb0;
                         const uint64_t adesc = umma_desc_sw128(smem_u32(s.a[dc]));
-                        const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[dc]));
+                        const uint64_t bdesc = umma_desc_sw128(smem_u32(s.b[stage]));
                         if (elect_one()) {
 #pragma unroll
                             for (int k = 0; k < kDChunk / 16; k++) {
                                 // advance 16 elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
                                 umma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (dc | k) != 0);
                             }
-                            if (kShare) umma_commit_multicast(&s.b_empty[dc], (uint16_t)3);
-                            else umma_commit(&s.b_empty[dc]);
+                            if (kShare) umma_commit_multicast(&s.b_empty[stage], (uint16_t)3);
+                            else umma_commit(&s.b_empty[stage]);
                             if (kt == p.k_tiles - 1) umma_commit(&s.a_empty[dc]);
-                            if (dc == kNumDChunks - 1) umma_commit(&s.t_full[buf]);
+                            if (dc == kNC - 1) umma_commit(&s.t_full[buf]);
                         }
                         __syncwarp();
                     }
+                    a_seen = true;
                     if (kTimeline && lane == 0 && blockIdx.x == 0 && it < p.timeline_tiles) {
                         p.timeline[it * 12 + 2] = clock64();
                         p.timeline[it * 12 + 8] = tl_bwait;
                     }
                     (void)tl_seq;
+                }
+                if (!a_seen) {
+#pragma unroll
+                    for (int dc = 0; dc < kNC; dc++) mbar_wait(&s.a_full[dc], rti & 1);
                 }
             }
         }

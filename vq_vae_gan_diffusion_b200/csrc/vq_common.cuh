@@ -153,6 +153,7 @@ __device__ __forceinline__ float candidate_margin(float z2, float e2max) {
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kRecipeExpanded = 0;
 constexpr int kRecipeDiffSq = 1;
+constexpr int kRecipeCdist = 2;     // sqrt(clamp_min([-2x, |x|^2, 1] . [e, 1, |e|^2], 0)) on L2-normalised rows, diffusion_gaussian3d.py:543-570
 
 // Candidate threshold as a function of the (running or final) minimal score m:  thr(m) = fma(m, cmul, margin0).
 //   expanded: cmul = 1, margin0 = candidate_margin()  -- thr = m + margin, bit-identical to the plain add.
@@ -163,10 +164,23 @@ constexpr int kRecipeDiffSq = 1;
 //             For k* = argmin d and j = argmin S:  D_k* (1-g) <= d_k* <= d_j <= (S_j + eps1)(1+g), hence
 //             score_k* <= score_j + 2 eps1 + c (score_j + |x|^2 + eps1) with c = 2^-16 >= ((1+g)/(1-g) - 1) -- every code that can
 //             be the exact argmin (or tie with it) satisfies it.
+//   cdist:    the squared distance is ONE canonical product of the augmented vectors, so its fp32 error is that of the
+//             dot product (2^-15 a) plus the roundings of the last fma of chains D mod 4 and (D + 1) mod 4 and of the two
+//             combining adds, each at a magnitude <= r: 4 * 2^-24 r -- the same budget as the expanded formula's -- and the
+//             square root can map two squared distances up to 3 ulp apart (<= 3 * 2^-23 r) onto one value, which must all
+//             stay candidates because the first of them wins: eps <= (2^-9 + 2^-12) a + 2^-20 r.
 __device__ __forceinline__ void candidate_threshold(int recipe, float z2, float e2max, float& cmul, float& margin0) {
     if (recipe == kRecipeExpanded) {
         cmul = 1.0f;
         margin0 = candidate_margin(z2, e2max);
+        return;
+    }
+    if (recipe == kRecipeCdist) {
+        const float a = sqrtf(z2) * sqrtf(e2max) * 1.000001f;
+        const float r = z2 + e2max + 2.0f * a;
+        const float eps = a * (0.001953125f + 0.000244140625f) + r * 9.5367431640625e-07f;
+        cmul = 1.0f;
+        margin0 = 2.0f * eps * 1.0625f + 1e-37f;
         return;
     }
     const float a = sqrtf(z2) * sqrtf(e2max) * 1.000001f;

@@ -217,4 +217,226 @@ vq_codebook_convert_kernel(const float* __restrict__ E, int K, int k_pad, __half
     }
 }
 
+// =====================================================================================================================
+// Row-major vectors of any width D <= 512 (the nearest-code searches of SURVEY.md 8(f) n2: gaussian_dim = 96 in
+// configs/*.yml, 512 in diffusion_gaussian3d.py's own runs).  The contraction is padded to kNC chunks of 64 inside the
+// kernels -- a zero column adds fma(0, 0, p) == p to every canonical chain, so no norm, dot product or tie changes -- and
+// nothing is padded in HBM: rows are read at their own pitch D.
+// =====================================================================================================================
+template <int kNC>
+struct RowsCfg {
+    static constexpr int kDp = 64 * kNC;                     // padded width
+    static constexpr int kRows = (kNC == 8) ? 16 : 32;       // rows per CTA: the fp32 tile stays below 34 KiB of static shared memory
+    static constexpr int kRowsPerWarp = kRows / (kPrepThreads / 32);
+    static constexpr int kPitch = kDp + 4;                   // floats per tile row: consecutive rows start 4 banks apart, so the
+                                                             // (row, j) chains of a warp read distinct banks
+    static constexpr int kPieces = kDp / 4;                  // float4 pieces per row
+};
+
+// F.normalize(x, p=2, dim=-1) as diffusion_gaussian3d.py:560-563 applies it: x / max(|x|_2, 1e-12), with |x|_2^2 in the
+// canonical order.  (clamp_min keeps a NaN norm, fmaxf would drop it.)
+__device__ __forceinline__ float normalize_denom(float norm2) {
+    const float nrm = sqrtf(norm2);
+    return (nrm < 1e-12f) ? 1e-12f : nrm;
+}
+
+// One CTA = RowsCfg::kRows consecutive rows.  Outputs (each optional): the fp16 operand image + |x|^2 + inverse operand
+// scale for the distance GEMM; with kNormalize the rows are L2-normalised first and the divisor / the normalised fp32 rows
+// can be kept (`denom`, `x_hat`: the exact stage divides by the same number; the lookup table is normalised once this way).
+template <int kNC, bool kNormalize>
+__global__ void __launch_bounds__(kPrepThreads)
+vq_prep_rows_kernel(const float* __restrict__ x, int64_t N, int D, int64_t n_pad, __half* __restrict__ z_h,
+                    float* __restrict__ z2, float* __restrict__ z_inv_scale, float* __restrict__ denom,
+                    float* __restrict__ x_hat, const PrepClear clr) {
+    using C = RowsCfg<kNC>;
+    __shared__ __align__(16) float tile[C::kRows * C::kPitch];
+    __shared__ float denom_s[C::kRows];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t n0 = (int64_t)blockIdx.x * C::kRows;
+    pdl_trigger();
+
+    {   // grid-strided clears (a few KiB in total)
+        const int64_t gtid = (int64_t)blockIdx.x * kPrepThreads + tid, gsz = (int64_t)gridDim.x * kPrepThreads;
+        for (int64_t i = gtid; i < clr.control_words; i += gsz) clr.control[i] = 0u;
+        if (clr.hist != nullptr)
+            for (int64_t i = gtid; i < clr.K; i += gsz) clr.hist[i] = 0ull;
+        if (clr.stats != nullptr && gtid < clr.n_stats) clr.stats[gtid] = 0ull;
+    }
+
+    // fill: warp w owns rows kRowsPerWarp * w ..; 16-byte loads when the rows are 16-byte aligned, columns >= D and rows >= N zero
+    const bool vec = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+#pragma unroll
+    for (int rr = 0; rr < C::kRowsPerWarp; rr++) {
+        const int r = warp * C::kRowsPerWarp + rr;
+        const int64_t n = n0 + r;
+        float* trow = tile + r * C::kPitch;
+        if (vec) {
+            const float4* src = reinterpret_cast<const float4*>(x + (n < N ? n : 0) * (int64_t)D);
+#pragma unroll
+            for (int h = 0; h < (C::kPieces + 31) / 32; h++) {
+                const int pi = lane + 32 * h;
+                if (pi < C::kPieces)
+                    *reinterpret_cast<float4*>(trow + 4 * pi) = (n < N && 4 * pi < D) ? __ldg(src + pi) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            const float* src = x + (n < N ? n : 0) * (int64_t)D;
+            for (int d = lane; d < C::kDp; d += 32) trow[d] = (n < N && d < D) ? __ldg(src + d) : 0.0f;
+        }
+    }
+    __syncthreads();
+
+    // canonical |x|^2 and max |x|: lane (row rr = lane >> 2, partial j = lane & 3) runs one chain of kDp / 4 fma
+    auto chains = [&](float& s, float& mx) {
+        const int rr = (lane >> 2) % C::kRowsPerWarp, j = lane & 3;
+        const float* trow = tile + (warp * C::kRowsPerWarp + rr) * C::kPitch + j;
+        float p = 0.0f;
+        mx = 0.0f;
+        if (lane < 4 * C::kRowsPerWarp) {
+#pragma unroll 16
+            for (int q = 0; q < C::kPieces; q++) {
+                const float v = trow[4 * q];
+                p = __fmaf_rn(v, v, p);
+                mx = fmaxf(mx, fabsf(v));
+            }
+        }
+        s = combine4(p);
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    };
+    float s, mx;
+    chains(s, mx);
+    if (kNormalize) {
+        if (lane < 4 * C::kRowsPerWarp && (lane & 3) == 0) denom_s[warp * C::kRowsPerWarp + (lane >> 2)] = normalize_denom(s);
+        __syncwarp();
+#pragma unroll
+        for (int rr = 0; rr < C::kRowsPerWarp; rr++) {
+            const int r = warp * C::kRowsPerWarp + rr;
+            const int64_t n = n0 + r;
+            const float dn = denom_s[r];
+            float* trow = tile + r * C::kPitch;
+            for (int d = lane; d < C::kDp; d += 32) {
+                const float v = __fdiv_rn(trow[d], dn);            // pad columns: 0 / dn == 0
+                trow[d] = v;
+                if (x_hat != nullptr && n < N && d < D) x_hat[n * (int64_t)D + d] = v;
+            }
+            if (denom != nullptr && lane == 0 && n < N) denom[n] = dn;
+        }
+        __syncwarp();
+        chains(s, mx);                                             // norms / operand scale of the normalised rows
+    }
+    const int ex = exponent_of(mx);
+    {
+        const int r = warp * C::kRowsPerWarp + (lane >> 2);
+        if (lane < 4 * C::kRowsPerWarp && (lane & 3) == 0 && n0 + r < N) {
+            if (z2 != nullptr) z2[n0 + r] = s;
+            if (z_inv_scale != nullptr) z_inv_scale[n0 + r] = pow2f(ex - kOperandTopExp);
+        }
+    }
+    if (z_h == nullptr) return;
+    const float sc_row = pow2f(kOperandTopExp - ex);               // valid on lanes < 4 kRowsPerWarp: scale of row (lane >> 2)
+
+    // fp16 operand rows into the image [row tile][64-wide D chunk][128 rows][128 B] (16-byte pieces XOR-swizzled by row & 7)
+#pragma unroll
+    for (int rr = 0; rr < C::kRowsPerWarp; rr++) {
+        const int r = warp * C::kRowsPerWarp + rr;
+        const int64_t n = n0 + r;
+        const float sc = __shfl_sync(0xffffffffu, sc_row, 4 * rr);
+        if (n >= n_pad) continue;                                  // warp-uniform
+        const float* trow = tile + r * C::kPitch;
+        const int rr_t = (int)((uint32_t)n % kRowTile);
+        __half* tile_img = z_h + ((int64_t)((uint32_t)n / kRowTile) * kNC) * (kRowTile * kDChunk) + rr_t * kDChunk;
+#pragma unroll
+        for (int h = 0; h < (C::kPieces + 31) / 32; h++) {
+            const int pi = lane + 32 * h;                          // float4 piece: d = 4 pi .. 4 pi + 3
+            if (pi >= C::kPieces) continue;
+            const float4 v = *reinterpret_cast<const float4*>(trow + 4 * pi);
+            __half2 lo = __floats2half2_rn(v.x * sc, v.y * sc), hi = __floats2half2_rn(v.z * sc, v.w * sc);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            const int c = pi >> 4, dl = 4 * (pi & 15);             // D chunk, first element inside the chunk
+            *reinterpret_cast<uint2*>(tile_img + (int64_t)c * (kRowTile * kDChunk) + ((((dl >> 3) ^ (rr_t & 7)) << 3) | (dl & 7))) = pk;
+        }
+    }
+}
+
+// Codebook / lookup-table preparation at width D <= 64 kNC (row pitch D).  One CTA = 32 codes.  cb[kCbE2Max], cb[kCbMaxAbs]
+// must be zero on entry.
+template <int kNC>
+__global__ void __launch_bounds__(kPrepThreads)
+vq_table_norms_kernel(const float* __restrict__ E, int K, int D, int k_pad, float* __restrict__ e2, float* __restrict__ cb) {
+    constexpr int kDp = 64 * kNC;
+    constexpr int kRowsT = (kNC == 8) ? 16 : 32;                  // codes per pass over the shared tile
+    __shared__ float t[kRowsT][kDp + 1];
+    __shared__ float smax[4], sabs[4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float m_all = 0.0f, mx_all = 0.0f;
+    for (int pass = 0; pass < kSelRows / kRowsT; pass++) {
+        const int k0 = blockIdx.x * kSelRows + pass * kRowsT;
+        __syncthreads();
+        for (int rr = 0; rr < kRowsT / 8; rr++) {
+            const int r = warp * (kRowsT / 8) + rr, k = k0 + r;
+            for (int d = lane; d < kDp; d += 32) t[r][d] = (k < K && d < D) ? __ldg(E + (int64_t)k * D + d) : 0.0f;
+        }
+        __syncthreads();
+        if (tid < 4 * kRowsT) {
+            const int r = tid >> 2, j = tid & 3, k = k0 + r;
+            float p = 0.0f, mx = 0.0f;
+#pragma unroll 16
+            for (int q = 0; q < kDp / 4; q++) {
+                const float v = t[r][4 * q + j];
+                p = __fmaf_rn(v, v, p);
+                mx = fmaxf(mx, fabsf(v));
+            }
+            const float s = combine4(p);
+            if (j == 0 && k < k_pad) e2[k] = (k < K) ? s : INFINITY;
+            const float m = (k < K) ? s : 0.0f;
+            m_all = __uint_as_float(max(__float_as_uint(m_all), __float_as_uint(m)));
+            mx_all = __uint_as_float(max(__float_as_uint(mx_all), __float_as_uint(mx)));
+        }
+    }
+    // maxima over real rows -> one atomic per CTA (values are >= 0, so uint ordering == float ordering; a NaN has a larger
+    // bit pattern than every finite value and therefore propagates)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float m2 = __shfl_xor_sync(0xffffffffu, m_all, o), x2 = __shfl_xor_sync(0xffffffffu, mx_all, o);
+        m_all = __uint_as_float(max(__float_as_uint(m_all), __float_as_uint(m2)));
+        mx_all = __uint_as_float(max(__float_as_uint(mx_all), __float_as_uint(x2)));
+    }
+    if (lane == 0 && warp < 4) { smax[warp] = m_all; sabs[warp] = mx_all; }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned a = 0, b = 0;
+        for (int w = 0; w < 4; w++) { a = max(a, __float_as_uint(smax[w])); b = max(b, __float_as_uint(sabs[w])); }
+        atomicMax(reinterpret_cast<unsigned int*>(cb + kCbE2Max), a);
+        atomicMax(reinterpret_cast<unsigned int*>(cb + kCbMaxAbs), b);
+    }
+}
+
+// One CTA = 32 codes; E fp32 (K, D) -> operand image [code tile][kNC chunks][256 codes][128 B], pad rows / columns zero.
+template <int kNC>
+__global__ void __launch_bounds__(kPrepThreads)
+vq_table_convert_kernel(const float* __restrict__ E, int K, int D, int k_pad, __half* __restrict__ e_h, float* __restrict__ cb) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int k0 = blockIdx.x * kSelRows;
+    const int ex = exponent_of(cb[kCbMaxAbs]);
+    const float sc = pow2f(kOperandTopExp - ex);
+    if (blockIdx.x == 0 && tid == 0) cb[kCbInvScale] = pow2f(ex - kOperandTopExp);
+#pragma unroll
+    for (int rr = 0; rr < 4; rr++) {
+        const int k = k0 + warp * 4 + rr;
+        if (k >= k_pad) break;
+        const float* src = E + (int64_t)k * D;
+#pragma unroll
+        for (int i = 0; i < kNC; i++) {
+            const int d = 64 * i + 2 * lane;
+            const float v0 = (k < K && d < D) ? __ldg(src + d) : 0.0f;
+            const float v1 = (k < K && d + 1 < D) ? __ldg(src + d + 1) : 0.0f;
+            __half2* dst = reinterpret_cast<__half2*>(
+                e_h + operand_image_offset((int64_t)(k / kCodeTile) * kNC + i, kCodeTile, k % kCodeTile, 2 * lane));
+            *dst = __floats2half2_rn(v0 * sc, v1 * sc);
+        }
+    }
+}
+
 }  // namespace vq
