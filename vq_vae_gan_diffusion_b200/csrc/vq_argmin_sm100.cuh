@@ -231,11 +231,12 @@ vq_argmin_gemm_kernel(const GemmParams p) {
             long long it = 0;                                   // global code-tile counter of this CTA
             int rti = 0, tl_seq = 0;
             for (int u = unit0; u < n_units; u += unit_step, rti++) {
-                // Both warps look at every row tile's z chunks (even when a short codebook gives a warp no code tile in
-                // this row tile): an mbarrier parity wait must never fall a whole phase behind.  The looks happen chunk by
-                // chunk inside the warp's first code tile of the row tile, so its MMAs start when chunk 0 has landed (short
-                // codebooks spend a visible share of a row tile at this boundary: profiles/r2_gemm_timeline_cfg5.log).
-                bool a_seen = false;
+                // both warps look at every row tile's z chunks (even when a short codebook gives a warp no code tile in
+                // this row tile): an mbarrier parity wait must never fall a whole phase behind.  (Looking at them lazily,
+                // chunk by chunk inside the first code tile, so that the MMAs start when chunk 0 has landed, was measured:
+                // no gain at K = 2048 and 3 % slower at K = 16384 -- one more predicated wait per chunk in the issue loop.)
+#pragma unroll
+                for (int dc = 0; dc < kNC; dc++) mbar_wait(&s.a_full[dc], rti & 1);
                 for (int kt = 0; kt < p.k_tiles; kt++, it++) {
                     if ((uint32_t)(it & 1) != buf) continue;
                     const uint32_t use = (uint32_t)(it >> 1);    // how often this buffer was used before
@@ -259,7 +260,6 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                                             : (kNC == kStagesB) ? use : use * (uint32_t)(kNC / kStagesB) + (uint32_t)(dc / kStagesB);
                         long long tb0 = 0;
                         if (kTimeline) tb0 = clock64();
-                        if (!a_seen) mbar_wait(&s.a_full[dc], rti & 1);
                         if (kShare) mbar_wait_cluster(&s.b_full[buf][stage], seen & 1);    // half of it was written by the peer's copy
                         else mbar_wait(&s.b_full[buf][stage], seen & 1);
                         tc_fence_after();
@@ -279,16 +279,11 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                         }
                         __syncwarp();
                     }
-                    a_seen = true;
                     if (kTimeline && lane == 0 && blockIdx.x == 0 && it < p.timeline_tiles) {
                         p.timeline[it * 12 + 2] = clock64();
                         p.timeline[it * 12 + 8] = tl_bwait;
                     }
                     (void)tl_seq;
-                }
-                if (!a_seen) {
-#pragma unroll
-                    for (int dc = 0; dc < kNC; dc++) mbar_wait(&s.a_full[dc], rti & 1);
                 }
             }
         }
