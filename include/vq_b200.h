@@ -129,7 +129,8 @@ int vq_normalize_rows(const float* x_rows, int64_t N, int D, float* out_rows, vq
 /*
  * Training forward.  Replaces CodeBook.forward, codebook.py:47-111.
  *   zq_nhwc (N, D) fp32 -- fl(z + fl(e - z)) in NHWC memory (the caller exposes it as the NCHW view the
- *                          reference returns, codebook.py:109)
+ *                          reference returns, codebook.py:109); may be NULL when nobody reads z_q (a caller that folds
+ *                          post_quant_conv into a lookup, see postconv.py): saves the 4 D bytes per latent it costs
  *   idx     (N) int64
  *   loss    (1) fp32    -- mean((e-z)^2 + beta*mean((e-z)^2)), codebook.py:96-103
  *   hist    (K) int64   -- bincount(idx, minlength=K); optional (may be NULL); overwritten

@@ -934,3 +934,55 @@ def test_normalize_rows_matches_oracle(vq, oracle):
         E_hat = tab._prepare(True)[0]
         ref = oracle.nearest_cdist(t[:4], t)
         assert np.array_equal(E_hat.cpu().numpy(), ref["table_hat"])
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# SURVEY.md 8(f) n1 (decoder side): post_quant_conv folded into a codebook-sized lookup (postconv.py)
+@pytest.mark.parametrize("name,bias", [("cfg2s_trained", True), ("cfg2s_init", True), ("ragged_trained", False)])
+def test_folded_post_quant_conv_matches_fp32_conv(name, bias, vq):
+    """FoldedPostQuant(codebook, post_quant_conv)(z) against the reference composition post_quant_conv(codebook(z)[0])
+    (vqvae.py:131-133) with an fp32 (TF32 off) Conv2d: output, indices, loss and all four gradients within 1e-5."""
+    dev = torch.device("cuda:0")
+    spec = CASES[name]
+    z_np, E_np, g_np = make_inputs(spec)
+    K, D = spec["K"], spec["D"]
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        torch.manual_seed(5)
+        conv = torch.nn.Conv2d(D, D, 1, bias=bias).to(dev)
+        cb = vq.CodeBook(K, D).to(dev)
+        with torch.no_grad():
+            cb.codebook.weight.copy_(torch.from_numpy(E_np))
+        fused = vq.FoldedPostQuant(cb, conv)
+        g = torch.from_numpy(g_np).to(dev).permute(0, 3, 1, 2).contiguous()
+
+        def run(folded):
+            for p in list(cb.parameters()) + list(conv.parameters()):
+                p.grad = None
+            z = torch.from_numpy(z_np).to(dev).requires_grad_(True)
+            if folded:
+                y, idx, loss = fused(z)
+            else:
+                z_q, idx, loss = cb(z)
+                y = conv(z_q)
+            (loss + (y * g).sum()).backward()
+            return (y.detach(), idx, loss.detach(), z.grad, cb.codebook.weight.grad.clone(), conv.weight.grad.clone(),
+                    conv.bias.grad.clone() if bias else None)
+
+        ref, got = run(False), run(True)
+        assert got[0].shape == ref[0].shape and got[0].is_contiguous()
+        assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
+        for i, what in ((0, "post_quant_x"), (3, "grad_z"), (4, "grad_E"), (5, "grad conv weight"), (6, "grad conv bias")):
+            if ref[i] is None:
+                continue
+            err = rel_err(got[i].cpu().numpy(), ref[i].cpu().numpy())
+            assert err <= 1e-5, (what, err)
+        # under no_grad with a frozen codebook (the tokenisers' / inference use)
+        with torch.no_grad():
+            y2, idx2, _ = fused(torch.from_numpy(z_np).to(dev))
+        assert torch.equal(idx2, ref[1]) and rel_err(y2.cpu().numpy(), ref[0].cpu().numpy()) <= 1e-5
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    with pytest.raises(ValueError):
+        vq.FoldedPostQuant(cb, torch.nn.Conv2d(D, D, 3, padding=1))

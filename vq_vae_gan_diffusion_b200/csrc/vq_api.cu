@@ -485,7 +485,7 @@ static int forward_impl(bool training, bool rows, int recipe, const float* z, in
         return VQ_OK;
     }
     if (!idx) return fail(VQ_E_INVALID, "null idx pointer");
-    if (training && (!zq || !loss)) return fail(VQ_E_INVALID, "null zq/loss pointer");
+    if (training && !loss) return fail(VQ_E_INVALID, "null loss pointer");
     Workspace w;
     rc = check_ws(ws, ws_bytes, N, &w);
     if (rc != VQ_OK) return rc;

@@ -53,7 +53,7 @@ struct SelectParams {
     void* idx;                 // (N) int64 / int32 / uint16 according to idx_bits
     int idx_bits;
     int recipe;                // kRecipeExpanded / kRecipeDiffSq
-    float* zq;                 // (N, D) or null
+    float* zq;                 // (N, D) or null (tokeniser mode; or a forward whose z_q nobody reads)
     unsigned long long* hist;  // (K) or null
     double* loss_partial;      // (gridDim.x)
     unsigned int* blocks_done; // (1) zero-initialised, re-armed by the kernel
@@ -336,6 +336,7 @@ vq_select_kernel(const SelectParams p) {
             const float4* zrow4 = reinterpret_cast<const float4*>(tile + r * kD);
             const int g = tile_swz(r);
             float4* out4 = reinterpret_cast<float4*>(p.zq + (n0 + r) * kD);
+            const bool want_zq = p.zq != nullptr;             // a caller that folds post_quant_conv needs only idx / loss / hist
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const float4 zv = zrow4[(lane + 32 * h) ^ g];
@@ -345,7 +346,7 @@ vq_select_kernel(const SelectParams p) {
                 diff.z = __fsub_rn(e.z, zv.z); diff.w = __fsub_rn(e.w, zv.w);
                 o.x = __fadd_rn(zv.x, diff.x); o.y = __fadd_rn(zv.y, diff.y);     // fl(z + fl(e - z)), codebook.py:106
                 o.z = __fadd_rn(zv.z, diff.z); o.w = __fadd_rn(zv.w, diff.w);
-                __stcs(out4 + lane + 32 * h, o);
+                if (want_zq) __stcs(out4 + lane + 32 * h, o);
                 sq = __fmaf_rn(diff.x, diff.x, sq); sq = __fmaf_rn(diff.y, diff.y, sq);
                 sq = __fmaf_rn(diff.z, diff.z, sq); sq = __fmaf_rn(diff.w, diff.w, sq);
             }

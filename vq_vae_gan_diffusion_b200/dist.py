@@ -66,6 +66,7 @@ class DataParallelVQ(torch.nn.Module):
         codebook.grad_scale = 1.0 / self.world_size
         codebook.grad_alloc = self._alloc_grad
         self._flat = None            # the step's exchange buffer
+        self._flat_has_stats = False
         self._work = None
         self._reduced = None         # (flat buffer, K, D) of the last completed exchange
         self._local = None           # (hist, loss) of the last forward, not yet exchanged
@@ -77,17 +78,20 @@ class DataParallelVQ(torch.nn.Module):
         return torch.empty(K * D + 2 * K + 2, dtype=torch.float32, device=device)
 
     def _alloc_grad(self, K, D, device):
-        """Called by the CodeBook's backward: grad_E is the head of a fresh flat buffer (fresh per step, because autograd
-        may keep the tensor as ``weight.grad``)."""
-        self._flat = self._new_flat(K, D, device)
+        """Called by the CodeBook's backward: grad_E is the head of the step's flat buffer (fresh per step, because autograd
+        may keep the tensor as ``weight.grad``; allocated -- and its histogram / loss tail filled -- right after the forward,
+        so that only the collective itself is left to do when the gradient arrives)."""
+        if self._flat is None or self._flat.numel() != K * D + 2 * K + 2 or self._flat.device != device:
+            self._flat = self._new_flat(K, D, device)
+            self._flat_has_stats = False
         return self._flat[:K * D].view(K, D)
 
     def _fill_stats(self, flat, K, D):
         hist, loss = self._local
         tail = flat[K * D:]
         pack_hist(hist, tail)
-        tail[2 * K] = loss
-        tail[2 * K + 1] = 1.0
+        tail[2 * K:2 * K + 1].copy_(loss.reshape(1))
+        tail[2 * K + 1:].fill_(1.0)
 
     def _on_grad_ready(self, param):
         if self.world_size <= 1 or not self.sync_grads or self._local is None:
@@ -99,11 +103,14 @@ class DataParallelVQ(torch.nn.Module):
             # autograd accumulated into an existing .grad (gradient accumulation) or copied: exchange a packed copy
             flat = self._new_flat(K, D, param.device)
             flat[:K * D].view(K, D).copy_(param.grad)
-        self._fill_stats(flat, K, D)
+            self._flat_has_stats = False
+        if not self._flat_has_stats:
+            self._fill_stats(flat, K, D)
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         self._work = (work, flat, K, D, None if aliased else param)
         self._local = None
         self._flat = None
+        self._flat_has_stats = False
 
     def forward(self, z, **kw):
         out = self.codebook_module(z, **kw)
@@ -112,6 +119,14 @@ class DataParallelVQ(torch.nn.Module):
         if loss is not None and cb.last_histogram is not None:
             self._local = (cb.last_histogram, loss.detach())
             self._reduced = None
+            w = cb.codebook.weight
+            if self.world_size > 1 and self.sync_grads and torch.is_grad_enabled() and w.requires_grad and w.dim() == 2:
+                # the step's exchange buffer, its histogram / loss tail filled now (these small kernels run ahead of the
+                # backward pass instead of between the scatter-add and the collective)
+                K, D = w.shape
+                self._flat = self._new_flat(K, D, w.device)
+                self._fill_stats(self._flat, K, D)
+                self._flat_has_stats = True
         return out
 
     def wait(self):
