@@ -973,11 +973,27 @@ def test_folded_post_quant_conv_matches_fp32_conv(name, bias, vq):
         ref, got = run(False), run(True)
         assert got[0].shape == ref[0].shape and got[0].is_contiguous()
         assert torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2])
-        for i, what in ((0, "post_quant_x"), (3, "grad_z"), (4, "grad_E"), (5, "grad conv weight"), (6, "grad conv bias")):
-            if ref[i] is None:
+        # float64 evaluation of what both compute: y = W_p e[idx] + b_p, dW_p = sum_n g[n] (x) e[idx[n]], db_p = sum_n g[n],
+        # grad_z = g W_p + 2 (z - e) / (N D) (straight-through), grad_E = the loss gradient only
+        idx = ref[1]
+        N = idx.numel()
+        e64 = cb.codebook.weight.detach().double()[idx]                                  # (N, D)
+        w64 = conv.weight.detach().double().reshape(D, D)
+        g64 = g.double().permute(0, 2, 3, 1).reshape(N, D)
+        z64 = torch.from_numpy(z_np).to(dev).double().permute(0, 2, 3, 1).reshape(N, D)
+        y64 = e64 @ w64.t() + (conv.bias.detach().double() if bias else 0.0)
+        truth = {0: y64.reshape(g.shape[0], g.shape[2], g.shape[3], D).permute(0, 3, 1, 2),
+                 3: (g64 @ w64 + 2.0 * (z64 - e64) / (N * D)).reshape(g.shape[0], g.shape[2], g.shape[3], D).permute(0, 3, 1, 2),
+                 5: (g64.t() @ e64).reshape(conv.weight.shape), 6: g64.sum(0) if bias else None}
+        for i, what in ((0, "post_quant_x"), (3, "grad_z"), (5, "grad conv weight"), (6, "grad conv bias")):
+            if truth[i] is None:
                 continue
-            err = rel_err(got[i].cpu().numpy(), ref[i].cpu().numpy())
-            assert err <= 1e-5, (what, err)
+            t = truth[i].cpu().numpy()
+            err_fold, err_ref = rel_err(got[i].cpu().numpy(), t), rel_err(ref[i].cpu().numpy(), t)
+            assert err_fold <= 1e-5, (what, err_fold)
+            # the reference composition carries the ulp(|z|) rounding of z + (e - z): up to ~1e-4 of |e| at the init codebook
+            assert err_ref <= (2e-4 if spec["dist"] == "init" else 1e-5), (what, err_ref)
+        assert rel_err(got[4].cpu().numpy(), ref[4].cpu().numpy()) <= 1e-5, "grad_E (loss gradient only, scatter-add order varies)"
         # under no_grad with a frozen codebook (the tokenisers' / inference use)
         with torch.no_grad():
             y2, idx2, _ = fused(torch.from_numpy(z_np).to(dev))

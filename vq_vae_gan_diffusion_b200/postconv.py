@@ -20,9 +20,14 @@ traffic, and 2 D^2 FLOP of library convolution.  The result differs from the ref
 1e-5 bar of the north star; tests/test_gpu_parity.py compares against fp32 ``Conv2d`` on the reference's z_q.
 
 Backward (autograd of vqvae.py:131-133): the upstream gradient on ``post_quant_x`` flows through the convolution to z_q and
-from there -- straight-through -- to z only: ``g_zq = g_y W_p`` (library GEMM) goes into ``vq_backward`` as the upstream
-gradient; ``dW_p = sum_n g_y[n] (x) z_q[n]`` is evaluated as ``(segment-sum of g_y by code)^T E`` (again K-sized instead of
-N-sized), ``db_p = sum_n g_y[n]``.  The codebook receives its loss gradient only, as in the reference.
+from there -- straight-through -- to z only.  The convolution's backward is the library's (``aten.convolution_backward``,
+i.e. cuDNN, exactly what autograd runs for the unfused layer) on the re-materialised lookup ``E[idx]``; its input gradient
+goes into ``vq_backward`` as the upstream gradient.  The codebook receives its loss gradient only, as in the reference.
+
+Accuracy note: the reference's ``z_q = fl(z + fl(e - z))`` carries a rounding error of ulp(|z|), which is NOT small against
+|e| when the codebook is still at its U(-1/K, 1/K) initialisation (|e| << |z|): there the reference's own z_q is ~6e-5
+(relative to |e|) away from e, and so are quantities linear in it (the convolution's weight gradient).  The fold uses e
+itself -- the value the straight-through construction stands for; tests compare both against a float64 evaluation.
 
 The encoder-side ``quant_conv`` (vqvae.py:83,128) is NOT folded: its output z is needed in fp32 by three consumers (operand
 conversion, exact stage / z_q / loss, backward), so fusing it means owning an fp32-accurate 256 x 256 tensor-core
@@ -84,21 +89,23 @@ class _FoldedFunction(torch.autograd.Function):
         K = wk.shape[0]
         dev = zc.device
         need_z, need_E, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2], \
-            ctx.needs_input_grad[3] and ctx.has_bias
-        w2 = conv_w.reshape(conv_w.shape[0], conv_w.shape[1])
-        g_rows = None
-        if g_y is not None:
-            g_rows = g_y.float().permute(0, 2, 3, 1).reshape(B * H * W, -1)            # (N, C_out); a copy unless channels-last
-        grad_w = grad_b = None
-        if g_rows is not None and need_w:
-            seg = torch.zeros((K, g_rows.shape[1]), dtype=torch.float32, device=dev).index_add_(0, idx, g_rows)
-            grad_w = (seg.t() @ wk).reshape(conv_w.shape)                               # sum_n g_y[n] (x) e[idx[n]]
-        if g_rows is not None and need_b:
-            grad_b = g_rows.sum(0)
-        g_zq = None
-        if g_rows is not None and need_z:
-            g_zq = (g_rows @ w2).contiguous()                                           # (N, D) rows = channels-last memory
-        strides = (ctypes.c_int64 * 3)(H * W * D, 1, D) if g_zq is not None else None
+            bool(ctx.needs_input_grad[3] and ctx.has_bias)
+        grad_w = grad_b = g_zq = None
+        strides = None
+        if g_y is not None and (need_z or need_w or need_b):
+            # The convolution's own backward, through the library exactly as autograd would run it for the unfused layer
+            # (cuDNN; honours torch.backends.cudnn.allow_tf32 like the reference's layer does).  Its input z_q is rebuilt as the
+            # NCHW lookup E[idx] (the straight-through value up to one rounding) instead of having been stored by the forward.
+            with _on_device(dev):
+                zq_nchw = torch.empty((B, D, H, W), dtype=torch.float32, device=dev)
+                rc = _native.lib().vq_embed_nchw(_ptr(idx), _ptr(wk), B, H * W, D, K, _ptr(zq_nchw), _stream_ptr(dev))
+                _native.check(rc, "vq_embed_nchw")
+            g_zq, grad_w, grad_b = torch.ops.aten.convolution_backward(
+                g_y.float().contiguous(), zq_nchw, conv_w, [conv_w.shape[0]] if need_b else None, [1, 1], [0, 0], [1, 1], False, [0, 0], 1,
+                [bool(need_z), bool(need_w), bool(need_b)])
+            if g_zq is not None:
+                g_zq = g_zq.contiguous()
+                strides = (ctypes.c_int64 * 3)(D * H * W, H * W, 1)                     # NCHW
         g_loss_t = None if g_loss is None else g_loss.to(device=dev, dtype=torch.float32).contiguous()
         grad_z = grad_E = None
         if need_z or need_E:
