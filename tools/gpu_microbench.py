@@ -115,30 +115,34 @@ def main():
             out["tokenize_hbm_frac"] = N * 1032 / (out["argmin_ms"] / 1e3) / 1e9 / peaks["hbm_gbs"]
             print(json.dumps({k: (round(v, 4) if isinstance(v, float) else v) for k, v in out.items()}))
 
-    # row-major nearest-code search (vq_argmin_rows): the reference's gaussian_to_indices shape
-    # (B*L = 16*256 rows, gaussian_dim 96 zero-padded to 256, K = 1024) and a large one on the headline codebook size
+    # row-major nearest-code search (vq_argmin_rows) at the tables' own widths: the reference's
+    # gaussian_to_indices shapes (B*L = 16*256 rows; gaussian_dim 96 of configs/*.yml, 512 of the 3D wrapper's runs; K = 1024)
+    # and large ones on the headline codebook size
     if args.rows:
-        for label, N, K, Dn in (("gaussian_to_indices 16x256 rows, D=96, K=1024", 4096, 1024, 96),
-                                ("rows 262144 x 256, K=16384", 262144, 16384, 256)):
+        for label, N, K, Dn, recipes in (("gaussian_to_indices 16x256 rows, D=96, K=1024", 4096, 1024, 96, ("expanded", "diffsq", "cdist_normalized")),
+                                         ("3D wrapper 16x256 rows, D=512, K=1024", 4096, 1024, 512, ("cdist_normalized", "expanded")),
+                                         ("rows 262144 x 96, K=16384", 262144, 16384, 96, ("expanded", "cdist_normalized")),
+                                         ("rows 262144 x 256, K=16384", 262144, 16384, 256, ("expanded", "diffsq", "cdist_normalized")),
+                                         ("rows 131072 x 512, K=16384", 131072, 16384, 512, ("cdist_normalized",))):
             g = torch.Generator(device=dev).manual_seed(7)
             table = torch.rand(K, Dn, device=dev, generator=g)
             x = table[torch.randint(0, K, (N,), device=dev, generator=g)] + 0.1 * torch.randn(N, Dn, device=dev, generator=g)
             tab = vq.CodeTable(table)
-            tab.nearest(x)
-            torch.cuda.synchronize()
-            _native.profile_enable(True)
-            t_all = timed(lambda: tab.nearest(x), args.reps, flush)[0]
-            gm = _native.profile_collect()
-            _native.profile_enable(False)
-            t_i32 = timed(lambda: tab.nearest(x, dtype=torch.int32), args.reps, flush)[0]
-            t_dsq = timed(lambda: tab.nearest(x, recipe="diffsq"), args.reps, flush)[0]
-            dsq_stats = dict(zip(_native.VQ_STAT_NAMES, tab.last_stats.tolist()))
-            tab.nearest(x)
-            flops = 2.0 * N * K * 256
-            print(json.dumps({"config": "rows: " + label, "N": N, "K": K, "D": Dn, "nearest_ms": round(t_all, 4),
-                              "nearest_int32_ms": round(t_i32, 4), "nearest_diffsq_ms": round(t_dsq, 4), "diffsq_stats": dsq_stats, "gemm_kernel_ms": round(statistics.median(gm), 4),
-                              "gemm_frac_of_bf16_peak": round(flops / statistics.median(gm) / 1e9 / peaks["bf16_tflops"], 4),
-                              "Mrows_s": round(N / t_all / 1e3, 2), "stats": dict(zip(_native.VQ_STAT_NAMES, tab.last_stats.tolist()))}))
+            out = {"config": "rows: " + label, "N": N, "K": K, "D": Dn}
+            for recipe in recipes:
+                tab.nearest(x, recipe=recipe)
+                torch.cuda.synchronize()
+                _native.profile_enable(True)
+                t_all = timed(lambda: tab.nearest(x, recipe=recipe), args.reps, flush)[0]
+                gm = _native.profile_collect()
+                _native.profile_enable(False)
+                d_pad = 64 * (1 if Dn <= 64 else 2 if Dn <= 128 else 4 if Dn <= 256 else 8)
+                out[recipe] = {"nearest_ms": round(t_all, 4), "Mrows_s": round(N / t_all / 1e3, 2),
+                               "gemm_kernel_ms": round(statistics.median(gm), 4) if gm else None,
+                               "gemm_frac_of_bf16_peak_algorithmic": round(2.0 * N * K * Dn / statistics.median(gm) / 1e9 / peaks["bf16_tflops"], 4) if gm else None,
+                               "gemm_frac_of_bf16_peak_executed": round(2.0 * N * K * d_pad / statistics.median(gm) / 1e9 / peaks["bf16_tflops"], 4) if gm else None,
+                               "stats": dict(zip(_native.VQ_STAT_NAMES, tab.last_stats.tolist()))}
+            print(json.dumps(out))
 
 
 if __name__ == "__main__":
