@@ -231,12 +231,19 @@ vq_argmin_gemm_kernel(const GemmParams p) {
             long long it = 0;                                   // global code-tile counter of this CTA
             int rti = 0, tl_seq = 0;
             for (int u = unit0; u < n_units; u += unit_step, rti++) {
-                // both warps look at every row tile's z chunks (even when a short codebook gives a warp no code tile in
-                // this row tile): an mbarrier parity wait must never fall a whole phase behind.  (Looking at them lazily,
-                // chunk by chunk inside the first code tile, so that the MMAs start when chunk 0 has landed, was measured:
-                // no gain at K = 2048 and 3 % slower at K = 16384 -- one more predicated wait per chunk in the issue loop.)
+                // Both warps look at every row tile's z chunks (even when a short codebook gives a warp no code tile in
+                // this row tile): an mbarrier parity wait must never fall a whole phase behind.  With an operand ring at
+                // least one code tile deep (kNC <= kStagesB) all chunks are awaited up front.  (Looking at them lazily, chunk
+                // by chunk inside the first code tile, so that the MMAs start when chunk 0 has landed, was measured there: no
+                // gain at K = 2048 and 3 % slower at K = 16384 -- one more predicated wait per chunk in the issue loop.)
+                // D = 512 (kNC = 8, two stages) MUST look lazily: the producer interleaves latent chunks with codebook stages
+                // and cannot deliver chunk 2 before the MMAs have freed a stage.
+                constexpr bool kLazyA = kNC > kStagesB;
+                bool a_seen = !kLazyA;
+                if (!kLazyA) {
 #pragma unroll
-                for (int dc = 0; dc < kNC; dc++) mbar_wait(&s.a_full[dc], rti & 1);
+                    for (int dc = 0; dc < kNC; dc++) mbar_wait(&s.a_full[dc], rti & 1);
+                }
                 for (int kt = 0; kt < p.k_tiles; kt++, it++) {
                     if ((uint32_t)(it & 1) != buf) continue;
                     const uint32_t use = (uint32_t)(it >> 1);    // how often this buffer was used before
@@ -260,6 +267,7 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                                             : (kNC == kStagesB) ? use : use * (uint32_t)(kNC / kStagesB) + (uint32_t)(dc / kStagesB);
                         long long tb0 = 0;
                         if (kTimeline) tb0 = clock64();
+                        if (kLazyA && !a_seen) mbar_wait(&s.a_full[dc], rti & 1);
                         if (kShare) mbar_wait_cluster(&s.b_full[buf][stage], seen & 1);    // half of it was written by the peer's copy
                         else mbar_wait(&s.b_full[buf][stage], seen & 1);
                         tc_fence_after();
@@ -279,11 +287,16 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                         }
                         __syncwarp();
                     }
+                    a_seen = true;
                     if (kTimeline && lane == 0 && blockIdx.x == 0 && it < p.timeline_tiles) {
                         p.timeline[it * 12 + 2] = clock64();
                         p.timeline[it * 12 + 8] = tl_bwait;
                     }
                     (void)tl_seq;
+                }
+                if (kLazyA && !a_seen) {                            // this warp had no code tile in the row tile
+#pragma unroll
+                    for (int dc = 0; dc < kNC; dc++) mbar_wait(&s.a_full[dc], rti & 1);
                 }
             }
         }
