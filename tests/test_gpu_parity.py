@@ -1002,3 +1002,45 @@ def test_folded_post_quant_conv_matches_fp32_conv(name, bias, vq):
         torch.backends.cudnn.allow_tf32 = old
     with pytest.raises(ValueError):
         vq.FoldedPostQuant(cb, torch.nn.Conv2d(D, D, 3, padding=1))
+
+
+def test_unaligned_and_noncontiguous_codebook_weights(vq, oracle):
+    """a weight that is a view at a storage offset that is not 16-byte aligned (a slice of a flat parameter buffer)
+    or non-contiguous must give the same results as a dense copy (the module feeds the kernels an aligned clone), and the
+    C-ABI refuses misaligned pointers instead of faulting; vq_embed_nchw checks its table and handles narrow ones."""
+    dev = torch.device("cuda:0")
+    spec = CASES["small_trained"]
+    z_np, E_np, _ = make_inputs(spec)
+    K, D = spec["K"], spec["D"]
+    flat = torch.zeros(K * D + 1, device=dev)
+    flat[1:].copy_(torch.from_numpy(E_np).reshape(-1).to(dev))
+    z = torch.from_numpy(z_np).to(dev)
+    ref = oracle.forward(z_np, E_np)
+    for w in (flat[1:].view(K, D), torch.from_numpy(np.ascontiguousarray(E_np.T)).to(dev).t()):
+        assert w.data_ptr() % 16 != 0 or not w.is_contiguous()
+        cb = vq.CodeBook(K, D).to(dev)
+        cb.codebook.weight = torch.nn.Parameter(w)
+        zt = z.clone().requires_grad_(True)
+        z_q, idx, loss = cb(zt)
+        loss.backward()
+        assert np.array_equal(idx.cpu().numpy(), ref["idx"])
+        assert np.array_equal(z_q.detach().permute(0, 2, 3, 1).reshape(-1, D).cpu().numpy(), ref["zq_nhwc"])
+        assert cb.codebook.weight.grad.shape == (K, D)
+        assert np.array_equal(cb.encode_indices(z).cpu().numpy(), ref["idx"])
+    L = vq._native.lib()
+    ws = torch.empty(vq._native.workspace_bytes(32, K, D), dtype=torch.uint8, device=dev)
+    dense = torch.from_numpy(E_np).to(dev)
+    cb = vq.CodeBook(K, D).to(dev)
+    with torch.no_grad():
+        cb.codebook.weight.copy_(dense)
+    E_h, e2, cbs = cb._derived(cb.codebook.weight)
+    idx = torch.empty(32, dtype=torch.int64, device=dev)
+    rc = L.vq_argmin(z.data_ptr(), 2, 16, D, flat[1:].data_ptr(), E_h.data_ptr(), e2.data_ptr(), cbs.data_ptr(), K, idx.data_ptr(), None,
+                     ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    assert rc == -1 and b"aligned" in L.vq_last_error()
+    # embedding lookup: narrow table, wrong dtype
+    t96 = torch.randn(50, 96, device=dev)
+    ii = torch.randint(0, 50, (2 * 3 * 5,), device=dev)
+    assert torch.equal(vq.vq_embed_nchw(ii, t96, 2, 3, 5), t96[ii].reshape(2, 3, 5, 96).permute(0, 3, 1, 2))
+    with pytest.raises(RuntimeError):
+        vq.vq_embed_nchw(ii, t96.half(), 2, 3, 5)

@@ -513,16 +513,23 @@ class CodeBook(nn.Module):
 
 def vq_embed_nchw(indices: torch.Tensor, weight: torch.Tensor, B: int, H: int, W: int) -> torch.Tensor:
     """``weight[indices].reshape(B, H, W, D).permute(0, 3, 1, 2)`` materialised contiguous NCHW in one kernel
-    (the decode-side lookup of worker/vqganVqvaeWorker.py:459 / vqTransformer.py:98)."""
+    (the decode-side lookup of worker/vqganVqvaeWorker.py:459 / vqTransformer.py:98).  ``weight`` is ``(K, D <= 256)`` fp32;
+    a narrower table runs zero-padded to the kernel's 256 columns and the padding is sliced off again."""
     if not (indices.is_cuda and weight.is_cuda):
         raise RuntimeError("vq_embed_nchw has no CPU path")
-    idx = indices.reshape(-1).to(torch.int64).contiguous()
+    if weight.dtype != torch.float32 or weight.dim() != 2:
+        raise RuntimeError(f"vq_embed_nchw expects a float32 (K, D) table, got {weight.dtype} {tuple(weight.shape)}")
     K, D = weight.shape
+    if D > _KERNEL_D:
+        raise ValueError(f"table width {D} > {_KERNEL_D} is not supported")
+    idx = indices.reshape(-1).to(torch.int64).contiguous()
     if idx.numel() != B * H * W:
         raise ValueError("indices do not match B*H*W")
     w = weight.detach().contiguous()
-    out = torch.empty((B, D, H, W), dtype=torch.float32, device=w.device)
+    if D < _KERNEL_D:
+        w = torch.nn.functional.pad(w, (0, _KERNEL_D - D))
+    out = torch.empty((B, _KERNEL_D, H, W), dtype=torch.float32, device=w.device)
     with torch.cuda.device(w.device):
-        rc = _native.lib().vq_embed_nchw(_ptr(idx), _ptr(w), B, H * W, D, K, _ptr(out), _stream_ptr(w.device))
+        rc = _native.lib().vq_embed_nchw(_ptr(idx), _ptr(w), B, H * W, _KERNEL_D, K, _ptr(out), _stream_ptr(w.device))
         _native.check(rc, "vq_embed_nchw")
-    return out
+    return out if D == _KERNEL_D else out[:, :D].contiguous()

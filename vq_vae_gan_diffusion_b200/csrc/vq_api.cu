@@ -486,6 +486,10 @@ static int forward_impl(bool training, bool rows, int recipe, const float* z, in
     }
     if (!idx) return fail(VQ_E_INVALID, "null idx pointer");
     if (training && !loss) return fail(VQ_E_INVALID, "null loss pointer");
+    // the kernels read code rows and write z_q rows with 16-byte accesses: refuse pointers that would fault instead
+    if ((reinterpret_cast<uintptr_t>(E) & 15) != 0 || (reinterpret_cast<uintptr_t>(zq) & 15) != 0)
+        return fail(VQ_E_INVALID, "E and zq must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(idx) & (uintptr_t)(idx_bits / 8 - 1)) != 0) return fail(VQ_E_INVALID, "idx is not aligned to its element size");
     Workspace w;
     rc = check_ws(ws, ws_bytes, N, &w);
     if (rc != VQ_OK) return rc;
@@ -743,6 +747,8 @@ VQ_EXPORT int vq_embed_nchw(const int64_t* idx, const float* E, int64_t B, int64
     const int64_t N = B * HW;
     if (N == 0) return VQ_OK;
     if (!idx || !E || !out) return fail(VQ_E_INVALID, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(idx) & 7) != 0 || (reinterpret_cast<uintptr_t>(E) & 3) != 0 || (reinterpret_cast<uintptr_t>(out) & 3) != 0)
+        return fail(VQ_E_INVALID, "misaligned pointer");
     DevInfo* dev;
     int rc = device_info(&dev);
     if (rc != VQ_OK) return rc;
