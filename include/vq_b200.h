@@ -165,14 +165,28 @@ int vq_backward(const float* gout, const int64_t* gout_strides_host, float g_los
  *                  is itself order-dependent) runs in 64-bit fixed point -- integer addition is associative, so the
  *                  result is bit-reproducible from run to run whatever order the atomics land in; needs `workspace`
  *                  of vq_backward_workspace_bytes(K, D) bytes (256-byte aligned).  0: red.global.add.v4.f32, no
- *                  workspace needed (may be NULL).
+ *                  workspace needed (may be NULL);
+ *   code_diff_sum  optional (K, D): the per-code sums of (e - z) a vq_forward_ex call accumulated (possibly summed over
+ *                  data-parallel ranks since).  When given, grad_E = g_loss * beta * 2 / (n_global * D) * grad_E_scale *
+ *                  code_diff_sum is all that is left of the codebook gradient (no scatter-add, `deterministic` ignored).
  */
 int vq_backward_workspace_bytes(int K, int D, size_t* out_host);
 int vq_backward_ex(const float* gout, const int64_t* gout_strides_host, float g_loss, const float* g_loss_dev,
                    const float* z_nchw, const int64_t* idx, const float* E,
                    int64_t B, int64_t HW, int D, int K, float beta, int64_t n_global,
-                   float grad_E_scale, int deterministic, float* grad_z_nchw, float* grad_E,
+                   float grad_E_scale, int deterministic, const float* code_diff_sum, float* grad_z_nchw, float* grad_E,
                    void* workspace, size_t workspace_bytes, vq_stream_t stream);
+
+/*
+ * vq_forward that also accumulates, per code, the sum of (e - z) over the latents it won (`code_diff_sum`, (K, D) fp32,
+ * zeroed here; may be NULL = plain vq_forward).  That sum is the codebook gradient up to a scalar (vq_backward_ex), so the
+ * backward's scatter-add disappears and -- the point -- a data-parallel wrapper can all-reduce it right after the forward,
+ * while the rest of the step runs, instead of after the backward (dist.py).
+ */
+int vq_forward_ex(const float* z_nchw, int64_t B, int64_t HW, int D,
+                  const float* E, const void* E_h, const float* e_norm2, const float* cb_scalars, int K,
+                  float beta, float* zq_nhwc, int64_t* idx, float* loss, int64_t* hist, float* code_diff_sum,
+                  unsigned long long* stats, void* workspace, size_t workspace_bytes, vq_stream_t stream);
 
 /*
  * Index -> embedding lookup in NCHW layout (the decode side: codebook(indices).reshape(B,h,w,D).permute(0,3,1,2),

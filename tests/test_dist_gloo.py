@@ -23,7 +23,7 @@ for p in (ROOT, HERE):
 
 
 class OracleCodeBook(torch.nn.Module):
-    """CPU stand-in with the CodeBook module's interface, computed by the oracle (test infrastructure only)."""
+    """CPU stand-in with the CodeBook module's interface towards dist.py, computed by the oracle (test infrastructure only)."""
 
     def __init__(self, E, beta=0.25):
         super().__init__()
@@ -36,6 +36,10 @@ class OracleCodeBook(torch.nn.Module):
         self.beta = beta
         self.grad_scale = 1.0
         self.grad_alloc = None
+        self.scatter_in_forward = False
+        self.scatter_alloc = None
+        self.scatter_ready = None
+        self.deterministic = False
         self.last_histogram = None
 
     def forward(self, z):
@@ -48,6 +52,14 @@ class OracleCodeBook(torch.nn.Module):
                 B, D, H, W = z.shape
                 ctx.save_for_backward(z, w)
                 ctx.idx = out["idx"]
+                ctx.scat = None
+                if mod.scatter_in_forward:                    # vq_forward_ex: per-code sums of (e - z), where the wrapper wants them
+                    zr = np.ascontiguousarray(np.moveaxis(z.detach().numpy().reshape(B, D, -1), 1, 2)).reshape(-1, D)
+                    S = np.zeros_like(w.detach().numpy())
+                    np.add.at(S, out["idx"], w.detach().numpy()[out["idx"]] - zr)
+                    ctx.scat = mod.scatter_alloc(S.shape[0], S.shape[1], w.device) if mod.scatter_alloc is not None else torch.empty(S.shape)
+                    ctx.scat.copy_(torch.from_numpy(S))
+                    ctx.scat_ready = mod.scatter_ready
                 mod.last_histogram = torch.from_numpy(out["hist"])
                 idx = torch.from_numpy(out["idx"])
                 ctx.mark_non_differentiable(idx)
@@ -59,6 +71,11 @@ class OracleCodeBook(torch.nn.Module):
                 z, w = ctx.saved_tensors
                 g = None if g_zq is None else np.ascontiguousarray(g_zq.numpy())
                 gz, gE = mod.oracle.backward(g, float(g_loss), z.detach().numpy(), ctx.idx, w.detach().numpy(), mod.beta)
+                if ctx.scat is not None:                       # vq_backward_ex(code_diff_sum=...): one scaling pass
+                    if ctx.scat_ready is not None:
+                        ctx.scat_ready(ctx.scat)
+                    coef = np.float32(2.0 * float(g_loss) / (ctx.idx.size * z.shape[1]))
+                    return torch.from_numpy(gz), ctx.scat * float(np.float32(mod.beta) * coef * np.float32(mod.grad_scale))
                 gE_t = torch.from_numpy(gE) * mod.grad_scale          # vq_backward_ex's grad_E_scale
                 if mod.grad_alloc is not None:                        # ... written where the wrapper wants it
                     out = mod.grad_alloc(gE_t.shape[0], gE_t.shape[1], gE_t.device)
@@ -82,12 +99,23 @@ def _worker(rank, world, init_file, out_file):
         sl = slice(rank * (B // world), (rank + 1) * (B // world))
         orc = COracle()
 
-        # --- 1. the stand-alone wrapper: hook, ONE async all-reduce, wait()
+        # --- 1. the stand-alone wrapper, ONE async all-reduce per step: post-backward (hook) and overlapped (forward-time sums)
+        gt = torch.from_numpy(np.ascontiguousarray(np.transpose(g[sl], (0, 3, 1, 2))))
+        cb0 = OracleCodeBook(E)
+        dp0 = DataParallelVQ(cb0, overlap=False)
+        z0 = torch.from_numpy(z[sl].copy()).requires_grad_(True)
+        q0, _, l0 = dp0(z0)
+        torch.autograd.backward([q0, l0], [gt, torch.tensor(1.0)])
+        dp0.wait()
+        gE_hook = cb0.codebook.weight.grad.numpy().copy()
+        hist_hook, loss_hook = dp0.global_histogram.numpy(), float(dp0.global_loss)
+        dp0._hook.remove()
+
         cb = OracleCodeBook(E)
         dp = DataParallelVQ(cb)
         zt = torch.from_numpy(z[sl].copy()).requires_grad_(True)
         z_q, idx, loss = dp(zt)
-        gt = torch.from_numpy(np.ascontiguousarray(np.transpose(g[sl], (0, 3, 1, 2))))
+        assert dp._step_overlapped and dp._fwd_work is not None
         torch.autograd.backward([z_q, loss], [gt, torch.tensor(1.0)])
         dp.wait()
         gE_wrap = cb.codebook.weight.grad.numpy().copy()
@@ -100,6 +128,7 @@ def _worker(rank, world, init_file, out_file):
             z_q, _, loss2 = dp(zt)
             torch.autograd.backward([z_q, loss2], [gt, torch.tensor(1.0)])
         z_q, _, loss2 = dp(zt)
+        assert not dp._step_overlapped                      # a .grad is being accumulated: the post-backward path takes over
         torch.autograd.backward([z_q, loss2], [gt, torch.tensor(1.0)])
         dp.wait()
         gE_accum = cb.codebook.weight.grad.numpy().copy()
@@ -144,6 +173,7 @@ def _worker(rank, world, init_file, out_file):
             g_all = torch.from_numpy(np.ascontiguousarray(np.transpose(g, (0, 3, 1, 2))))
             (l1 + (q1 * g_all).sum() / world).backward()
             np.savez(out_file, gE_wrap=gE_wrap, hist_wrap=hist_wrap, loss_wrap=loss_wrap, gz_wrap=zt.grad.numpy() / 3,
+                     gE_hook=gE_hook, hist_hook=hist_hook, loss_hook=loss_hook,
                      gE_accum=gE_accum, hist_eval=hist_eval, loss_eval=loss_eval,
                      gE_full=gE_full, hist_full=full["hist"], loss_full=float(full["loss"]), gz_loc=gz_loc,
                      loss_local=float(loss.detach()), loss_loc_ref=float(loc["loss"]),
@@ -162,9 +192,10 @@ def test_two_rank_gloo_exchange():
         mp.spawn(_worker, args=(2, init_file, out_file), nprocs=2, join=True)
         r = np.load(out_file)
     # stand-alone wrapper: averaged shard gradients == single-device gradient on the concatenated batch
-    assert_close(r["gE_wrap"], r["gE_full"], "averaged shard grad_E")
+    assert_close(r["gE_wrap"], r["gE_full"], "averaged shard grad_E (overlapped exchange of the per-code sums)")
+    assert_close(r["gE_hook"], r["gE_full"], "averaged shard grad_E (post-backward exchange)")
     assert_close(r["gE_accum"], 2 * r["gE_full"], "grad_E after a second accumulated micro-step")
-    for tag in ("wrap", "eval"):
+    for tag in ("wrap", "hook", "eval"):
         assert np.array_equal(r[f"hist_{tag}"], r["hist_full"])
         # equal shard sizes: the mean of the per-rank losses is the global loss
         assert abs(float(r[f"loss_{tag}"]) - float(r["loss_full"])) <= 1e-6 * abs(float(r["loss_full"]))

@@ -32,7 +32,7 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
-def run_checks(rank, world, dev, K=4096, Bl=4, H=32, W=32, deterministic=False):
+def run_checks(rank, world, dev, K=4096, Bl=4, H=32, W=32, deterministic=False, overlap=True):
     """The checks of one rank; returns a dict of error figures.  Needs an initialised process group."""
     import vq_vae_gan_diffusion_b200 as vq
     from vq_vae_gan_diffusion_b200.dist import DataParallelVQ
@@ -55,9 +55,10 @@ def run_checks(rank, world, dev, K=4096, Bl=4, H=32, W=32, deterministic=False):
 
     # --- stand-alone wrapper: ONE all-reduce of [grad_E / W | hist | loss | 1]
     cb = fresh()
-    dp = DataParallelVQ(cb)
+    dp = DataParallelVQ(cb, overlap=overlap)
     zl = z[sl].clone().requires_grad_(True)
     z_q, idx, loss = dp(zl)
+    assert dp._step_overlapped == (overlap and not deterministic and world > 1)
     torch.autograd.backward([z_q, loss], [gout[sl], one])
     dp.wait()
 
@@ -116,8 +117,9 @@ def _worker(rank, world, backend, init_file, out_file):
     try:
         res = run_checks(rank, world, dev)
         res_det = run_checks(rank, world, dev, K=1024, Bl=2, deterministic=True)
+        res_hook = run_checks(rank, world, dev, K=2048, Bl=2, overlap=False)
         gathered = [None] * world
-        dist.all_gather_object(gathered, (res, res_det))
+        dist.all_gather_object(gathered, (res, res_det, res_hook))
         if rank == 0:
             np.save(out_file, np.array(gathered, dtype=object), allow_pickle=True)
         dist.barrier()

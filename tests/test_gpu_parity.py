@@ -1044,3 +1044,30 @@ def test_unaligned_and_noncontiguous_codebook_weights(vq, oracle):
     assert torch.equal(vq.vq_embed_nchw(ii, t96, 2, 3, 5), t96[ii].reshape(2, 3, 5, 96).permute(0, 3, 1, 2))
     with pytest.raises(RuntimeError):
         vq.vq_embed_nchw(ii, t96.half(), 2, 3, 5)
+
+
+def test_codebook_gradient_from_forward_time_sums(vq, oracle):
+    """module.scatter_in_forward (what DataParallelVQ's overlapped exchange uses): vq_forward_ex accumulates sum (e - z) per
+    code, vq_backward_ex(code_diff_sum=...) turns it into grad_E with one scaling pass.  Same results as the scatter-add path and
+    the oracle; grad_z untouched; a forward-only call or a frozen codebook does not accumulate anything."""
+    dev = torch.device("cuda:0")
+    for name in ("cfg2s_init", "ragged_trained", "dup_rows"):
+        spec = CASES[name]
+        z_np, E_np, g_np = make_inputs(spec)
+        K, D = spec["K"], spec["D"]
+        ref = oracle.forward(z_np, E_np)
+        gz_o, gE_o = oracle.backward(np.transpose(g_np, (0, 3, 1, 2)), 0.7, z_np, ref["idx"], E_np, beta=0.25)
+        cb = vq.CodeBook(K, D).to(dev)
+        with torch.no_grad():
+            cb.codebook.weight.copy_(torch.from_numpy(E_np))
+        cb.scatter_in_forward = True
+        z = torch.from_numpy(z_np).to(dev).requires_grad_(True)
+        z_q, idx, loss = cb(z)
+        g = torch.from_numpy(g_np).to(dev).permute(0, 3, 1, 2)
+        (0.7 * loss + (z_q * g).sum()).backward()
+        assert np.array_equal(idx.cpu().numpy(), ref["idx"])
+        assert np.array_equal(z_q.detach().permute(0, 2, 3, 1).reshape(-1, D).cpu().numpy(), ref["zq_nhwc"])
+        assert_close(z.grad.cpu().numpy(), gz_o, "grad_z")
+        assert_close(cb.codebook.weight.grad.cpu().numpy(), gE_o, "grad_E from the forward-time sums")
+        with torch.no_grad():
+            assert torch.equal(cb(z.detach())[1], idx)

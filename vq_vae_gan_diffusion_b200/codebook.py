@@ -106,11 +106,17 @@ class _VQFunction(torch.autograd.Function):
             hist = torch.empty((K,), dtype=torch.int64, device=dev)
             stats = torch.empty((4,), dtype=torch.int64, device=dev)
             ws = module._workspace.get(_native.workspace_bytes_cached(B * H * W, K, D), dev, st)
-            rc = _native.lib().vq_forward(_ptr(zc), B, H * W, D, _ptr(weight), _ptr(E_h), _ptr(e2), _ptr(cb), K,
-                                          float(module.beta), _ptr(zq), _ptr(idx), _ptr(loss), _ptr(hist),
-                                          _ptr(stats), _ptr(ws), ws.numel(), st)
+            # scatter_in_forward (set by a data-parallel wrapper, dist.py): the per-code sums of (e - z) -- the codebook gradient
+            # up to a scalar -- are accumulated by the forward, so that their all-reduce overlaps the rest of the step
+            scat = None
+            if refresh and module.scatter_in_forward and not module.deterministic:
+                scat = module.scatter_alloc(K, D, dev) if module.scatter_alloc is not None else \
+                    torch.empty((K, D), dtype=torch.float32, device=dev)
+            rc = _native.lib().vq_forward_ex(_ptr(zc), B, H * W, D, _ptr(weight), _ptr(E_h), _ptr(e2), _ptr(cb), K,
+                                             float(module.beta), _ptr(zq), _ptr(idx), _ptr(loss), _ptr(hist), _ptr(scat),
+                                             _ptr(stats), _ptr(ws), ws.numel(), st)
             if rc != 0:
-                _native.check(rc, "vq_forward")
+                _native.check(rc, "vq_forward_ex")
             if module.count_launches:
                 module._launches = int(_native.lib().vq_last_launch_count())
         object.__setattr__(module, "last_histogram", hist)   # (plain tensors: skip nn.Module.__setattr__'s bookkeeping)
@@ -118,6 +124,8 @@ class _VQFunction(torch.autograd.Function):
         ctx.save_for_backward(zc, idx, weight)
         ctx.module = module
         ctx.shape = (B, D, H, W)
+        ctx.scat = scat
+        ctx.scat_ready = module.scatter_ready if scat is not None else None
         ctx.mark_non_differentiable(idx)
         # NHWC memory exposed as NCHW: strides (H*W*D, 1, W*D, D), exactly what codebook.py:109 returns
         return zq.permute(0, 3, 1, 2), idx, loss
@@ -148,18 +156,21 @@ class _VQFunction(torch.autograd.Function):
             st = _stream_ptr(dev)
             grad_z = torch.empty((B, D, H, W), dtype=torch.float32, device=dev) if need_z else None
             grad_E = None
+            scat = ctx.scat if need_w else None
+            if scat is not None and ctx.scat_ready is not None:
+                ctx.scat_ready(scat)                         # the wrapper's all-reduce of the sums: the stream waits here
             if need_w:
                 # a data-parallel wrapper may hand out the head of its flat exchange buffer (dist.py): the scatter-add
                 # then lands where the all-reduce reads, with no packing copy
-                grad_E = module.grad_alloc(K, D, dev) if module.grad_alloc is not None else \
+                grad_E = module.grad_alloc(K, D, dev) if (module.grad_alloc is not None and scat is None) else \
                     torch.empty((K, D), dtype=torch.float32, device=dev)
-            det = bool(module.deterministic) and need_w
+            det = bool(module.deterministic) and need_w and scat is None
             ws = None
             if det:
                 ws = module._workspace_bwd.get(_native.backward_workspace_bytes_cached(K, D), dev, st)
             rc = _native.lib().vq_backward_ex(_ptr(g_zq), strides, 0.0, _ptr(g_loss_t), _ptr(zc), _ptr(idx), _ptr(weight),
                                               B, H * W, D, K, float(module.beta), B * H * W, float(module.grad_scale),
-                                              1 if det else 0, _ptr(grad_z), _ptr(grad_E), _ptr(ws),
+                                              1 if det else 0, _ptr(scat), _ptr(grad_z), _ptr(grad_E), _ptr(ws),
                                               0 if ws is None else ws.numel(), st)
             if rc != 0:
                 _native.check(rc, "vq_backward_ex")
@@ -223,7 +234,7 @@ class _GraphState:
         B, D, H, W = self.shape
         strides = (ctypes.c_int64 * 3)(H * W * D, 1, D)
         rc = _native.lib().vq_backward_ex(_ptr(self.g) if has_g else 0, strides, 0.0, _ptr(self.g_loss), _ptr(self.z), _ptr(self.idx),
-                                          _ptr(self.weight), B, H * W, D, self.K, self.beta, B * H * W, float(scale), 1 if det else 0,
+                                          _ptr(self.weight), B, H * W, D, self.K, self.beta, B * H * W, float(scale), 1 if det else 0, 0,
                                           _ptr(self.grad_z) if need_z else 0, _ptr(self.grad_E) if need_w else 0,
                                           _ptr(self.ws_bwd), self.ws_bwd.numel(), _stream_ptr(self.dev))
         _native.check(rc, "vq_backward_ex")
@@ -344,6 +355,11 @@ class CodeBook(nn.Module):
         # so that the SUM over ranks is the gradient of the global-batch mean.  grad_alloc lets the wrapper place grad_E.
         self.grad_scale = 1.0
         self.grad_alloc = None
+        # scatter_in_forward: the forward also accumulates sum (e - z) per code (vq_forward_ex), the backward turns it into the
+        # codebook gradient with one scaling pass; scatter_alloc / scatter_ready let the wrapper place and exchange the sums
+        self.scatter_in_forward = False
+        self.scatter_alloc = None
+        self.scatter_ready = None
         # use_cuda_graphs=True: forward and backward replay captured CUDA graphs on static buffers (one launch per direction
         # instead of 3-7 kernels plus ~180 us of host work): for the small, launch-bound shapes.  graph_outputs = "clone"
         # hands out copies (safe to keep); "static" hands out the graph's own buffers, valid until the next call.
@@ -505,6 +521,8 @@ class CodeBook(nn.Module):
         state["_workspace"] = _Workspace()
         state["_workspace_bwd"] = _Workspace()
         state["grad_alloc"] = None
+        state["scatter_alloc"] = None
+        state["scatter_ready"] = None
         state["_graph_states"] = {}
         state["last_histogram"] = None
         state["last_stats"] = None

@@ -466,13 +466,16 @@ VQ_EXPORT int vq_prepare_codebook(const float* E, int K, int D, void* E_h, float
 
 static int forward_impl(bool training, bool rows, int recipe, const float* z, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
                         const float* e2, const float* cb, int K, float beta, float* zq, void* idx, int idx_bits, float* loss,
-                        int64_t* hist, unsigned long long* stats, void* ws, size_t ws_bytes, vq_stream_t stream) {
+                        int64_t* hist, unsigned long long* stats, void* ws, size_t ws_bytes, vq_stream_t stream,
+                        float* code_diff_sum = nullptr) {
     g_launches = 0;
     int rc = check_common(z, B, HW, D, K);
     if (rc != VQ_OK) return rc;
     if (!E || !E_h || !e2 || !cb) return fail(VQ_E_INVALID, "null codebook pointer");
     const int64_t N = B * HW;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if ((reinterpret_cast<uintptr_t>(code_diff_sum) & 15) != 0) return fail(VQ_E_INVALID, "code_diff_sum must be 16-byte aligned");
+    if (training && code_diff_sum) VQ_CUDA(cudaMemsetAsync(code_diff_sum, 0, (size_t)K * D * sizeof(float), st));
     if (N == 0) {
         // nothing is launched: clear the outputs directly
         if (stats) VQ_CUDA(cudaMemsetAsync(stats, 0, VQ_STAT_COUNT * sizeof(unsigned long long), st));
@@ -522,6 +525,7 @@ static int forward_impl(bool training, bool rows, int recipe, const float* z, in
     sp.out_cnt = w.out_cnt; sp.out_q = w.out_q;
     sp.N = N; sp.HW = HW; sp.K = K; sp.beta = beta;
     sp.idx = idx; sp.idx_bits = idx_bits; sp.recipe = recipe; sp.zq = zq;
+    sp.scat = training ? code_diff_sum : nullptr;
     sp.hist = reinterpret_cast<unsigned long long*>(hist);
     sp.loss_partial = w.loss_partial; sp.blocks_done = w.blocks_done; sp.loss = loss;
     sp.stats = stats;
@@ -619,6 +623,14 @@ VQ_EXPORT int vq_forward(const float* z_nchw, int64_t B, int64_t HW, int D, cons
                         stats, workspace, workspace_bytes, stream);
 }
 
+VQ_EXPORT int vq_forward_ex(const float* z_nchw, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
+                            const float* e_norm2, const float* cb_scalars, int K, float beta, float* zq_nhwc, int64_t* idx,
+                            float* loss, int64_t* hist, float* code_diff_sum, unsigned long long* stats, void* workspace,
+                            size_t workspace_bytes, vq_stream_t stream) {
+    return forward_impl(true, false, VQ_RECIPE_EXPANDED, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, beta, zq_nhwc, idx, 64, loss, hist,
+                        stats, workspace, workspace_bytes, stream, code_diff_sum);
+}
+
 VQ_EXPORT int vq_debug_scores(const float* z_nchw, int64_t B, int64_t HW, int D, const void* E_h, const float* e_norm2,
                               const float* cb_scalars, int K, float* scores, void* workspace, size_t workspace_bytes,
                               vq_stream_t stream) {
@@ -636,8 +648,8 @@ VQ_EXPORT int vq_debug_scores(const float* z_nchw, int64_t B, int64_t HW, int D,
 
 static int backward_impl(const float* gout, const int64_t* gout_strides, float g_loss, const float* g_loss_dev,
                          const float* z_nchw, const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K, float beta,
-                         int64_t n_global, float grad_E_scale, bool deterministic, float* grad_z, float* grad_E,
-                         void* ws, size_t ws_bytes, vq_stream_t stream) {
+                         int64_t n_global, float grad_E_scale, bool deterministic, const float* code_diff_sum, float* grad_z,
+                         float* grad_E, void* ws, size_t ws_bytes, vq_stream_t stream) {
     g_launches = 0;
     int rc = check_common(z_nchw, B, HW, D, K);
     if (rc != VQ_OK) return rc;
@@ -645,14 +657,27 @@ static int backward_impl(const float* gout, const int64_t* gout_strides, float g
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     if ((reinterpret_cast<uintptr_t>(grad_E) & 15) != 0 || (reinterpret_cast<uintptr_t>(E) & 15) != 0)
         return fail(VQ_E_INVALID, "E and grad_E must be 16-byte aligned");
-    if (grad_E) VQ_CUDA(cudaMemsetAsync(grad_E, 0, (size_t)K * D * sizeof(float), st));
+    if ((reinterpret_cast<uintptr_t>(code_diff_sum) & 15) != 0) return fail(VQ_E_INVALID, "code_diff_sum must be 16-byte aligned");
+    const bool from_sum = code_diff_sum != nullptr && grad_E != nullptr;      // the forward already accumulated sum (e - z) per code
+    if (grad_E && !from_sum) VQ_CUDA(cudaMemsetAsync(grad_E, 0, (size_t)K * D * sizeof(float), st));
+    if (!grad_z && !grad_E) return VQ_OK;
+    if (n_global <= 0) n_global = N;
+    float* grad_E_out = grad_E;
+    if (from_sum) {
+        const int64_t n_elems = (int64_t)K * D;
+        const unsigned sgrid = (unsigned)((n_elems + 1023) / 1024 < 4096 ? (n_elems + 1023) / 1024 : 4096);
+        vq::vq_grad_from_sum_kernel<<<sgrid, 256, 0, st>>>(code_diff_sum, n_elems, g_loss, g_loss_dev, 1.0 / ((double)n_global * (double)D), beta,
+                                                           grad_E_scale, grad_E_out);
+        VQ_LAUNCH_CHECK("vq_grad_from_sum_kernel");
+        grad_E = nullptr;                                      // the main kernel only has grad_z left to do
+        deterministic = false;
+    }
     if (N == 0 || (!grad_z && !grad_E)) return VQ_OK;
     if (!idx || !E) return fail(VQ_E_INVALID, "null idx/E pointer");
     if (gout && !gout_strides) return fail(VQ_E_INVALID, "gout given without strides");
     DevInfo* dev;
     rc = device_info(&dev);
     if (rc != VQ_OK) return rc;
-    if (n_global <= 0) n_global = N;
 
     vq::BackwardParams bp;
     bp.gout = gout;
@@ -720,7 +745,7 @@ VQ_EXPORT int vq_backward(const float* gout, const int64_t* gout_strides, float 
                           const float* z_nchw,
                           const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K, float beta,
                           int64_t n_global, float* grad_z, float* grad_E, vq_stream_t stream) {
-    return backward_impl(gout, gout_strides, g_loss, g_loss_dev, z_nchw, idx, E, B, HW, D, K, beta, n_global, 1.0f, false, grad_z,
+    return backward_impl(gout, gout_strides, g_loss, g_loss_dev, z_nchw, idx, E, B, HW, D, K, beta, n_global, 1.0f, false, nullptr, grad_z,
                          grad_E, nullptr, 0, stream);
 }
 
@@ -733,10 +758,10 @@ VQ_EXPORT int vq_backward_workspace_bytes(int K, int D, size_t* out) {
 
 VQ_EXPORT int vq_backward_ex(const float* gout, const int64_t* gout_strides, float g_loss, const float* g_loss_dev,
                              const float* z_nchw, const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K,
-                             float beta, int64_t n_global, float grad_E_scale, int deterministic, float* grad_z, float* grad_E,
-                             void* workspace, size_t workspace_bytes, vq_stream_t stream) {
+                             float beta, int64_t n_global, float grad_E_scale, int deterministic, const float* code_diff_sum,
+                             float* grad_z, float* grad_E, void* workspace, size_t workspace_bytes, vq_stream_t stream) {
     return backward_impl(gout, gout_strides, g_loss, g_loss_dev, z_nchw, idx, E, B, HW, D, K, beta, n_global, grad_E_scale,
-                         deterministic != 0, grad_z, grad_E, workspace, workspace_bytes, stream);
+                         deterministic != 0, code_diff_sum, grad_z, grad_E, workspace, workspace_bytes, stream);
 }
 
 VQ_EXPORT int vq_embed_nchw(const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K, float* out,

@@ -42,9 +42,6 @@ struct BackwardParams {
     const int* fx_shift;      // (1) device scalar written by vq_backward_maxdiff_kernel
 };
 
-__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
 
 __device__ __forceinline__ void red_add_s64(long long* addr, long long v) {
     asm volatile("red.global.add.u64 [%0], %1;" ::"l"(addr), "l"(v) : "memory");
@@ -273,6 +270,20 @@ vq_backward_fxfinish_kernel(const long long* __restrict__ acc, const int* __rest
     const double unit = (double)ce * (double)pow2f(-__ldg(shift));
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n_elems; i += (int64_t)gridDim.x * 256)
         grad_E[i] = (float)((double)acc[i] * unit);
+}
+
+// grad_E = (beta * coef * e_scale) * S, S[k] = sum over the latents of code k of (e_k - z_n), accumulated by the FORWARD
+// (vq_select_kernel with SelectParams::scat): the scatter-add then needs no second pass over z, and a data-parallel wrapper can
+// exchange S while the rest of the step runs (dist.py).
+__global__ void __launch_bounds__(256)
+vq_grad_from_sum_kernel(const float* __restrict__ S, int64_t n_elems, float g_loss, const float* __restrict__ g_loss_dev, double inv_nd,
+                        float beta, float e_scale, float* __restrict__ grad_E) {
+    const float coef = (float)(2.0 * (double)(g_loss_dev != nullptr ? __ldg(g_loss_dev) : g_loss) * inv_nd);
+    const float ce = (beta * coef) * e_scale;
+    for (int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) * 4; i < n_elems; i += (int64_t)gridDim.x * 1024) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(S + i));
+        *reinterpret_cast<float4*>(grad_E + i) = make_float4(ce * v.x, ce * v.y, ce * v.z, ce * v.w);
+    }
 }
 
 // out[b, d, hw] = E[idx[b*HW + hw]][d]  (decode side: worker/vqganVqvaeWorker.py:459, vqTransformer.py:98)

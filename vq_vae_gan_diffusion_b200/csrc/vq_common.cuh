@@ -27,6 +27,10 @@ constexpr int kSelRows = 32;        // latents per CTA in the fp32 kernels (prep
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 // Tensor-core operands are fp16 scaled by exact powers of two so that the largest magnitude lands in
 // [2^14, 2^15): per latent row for z, per tensor for the codebook.  exponent_of() returns ex with |x| < 2^ex.
 constexpr int kOperandTopExp = 15;

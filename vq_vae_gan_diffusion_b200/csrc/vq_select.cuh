@@ -54,6 +54,7 @@ struct SelectParams {
     int idx_bits;
     int recipe;                // kRecipeExpanded / kRecipeDiffSq
     float* zq;                 // (N, D) or null (tokeniser mode; or a forward whose z_q nobody reads)
+    float* scat;               // (K, D) or null: per-code sums of (e - z) for the codebook gradient (zeroed before launch)
     unsigned long long* hist;  // (K) or null
     double* loss_partial;      // (gridDim.x)
     unsigned int* blocks_done; // (1) zero-initialised, re-armed by the kernel
@@ -347,6 +348,7 @@ vq_select_kernel(const SelectParams p) {
                 o.x = __fadd_rn(zv.x, diff.x); o.y = __fadd_rn(zv.y, diff.y);     // fl(z + fl(e - z)), codebook.py:106
                 o.z = __fadd_rn(zv.z, diff.z); o.w = __fadd_rn(zv.w, diff.w);
                 if (want_zq) __stcs(out4 + lane + 32 * h, o);
+                if (p.scat != nullptr) red_add_v4(p.scat + (int64_t)kk[rr] * kD + 4 * (lane + 32 * h), diff.x, diff.y, diff.z, diff.w);
                 sq = __fmaf_rn(diff.x, diff.x, sq); sq = __fmaf_rn(diff.y, diff.y, sq);
                 sq = __fmaf_rn(diff.z, diff.z, sq); sq = __fmaf_rn(diff.w, diff.w, sq);
             }

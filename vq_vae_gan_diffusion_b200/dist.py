@@ -16,14 +16,21 @@ Two ways to get that average:
    :class:`DataParallelVQ` issues exactly ONE collective per training step, a SUM all-reduce (NCCL over NVLink on GPUs,
    gloo in the CPU tests) of one flat fp32 buffer
 
-       [ grad_E (K*D) | hist low 16 bits (K) | hist high bits (K) | loss | 1 ]
+       [ S or grad_E (K*D) | hist low 16 bits (K) | hist high bits (K) | loss | 1 ]
 
-   launched from a post-accumulate-grad hook on the codebook weight, i.e. as soon as the scatter-add kernel has been
-   enqueued; NCCL runs it on its own stream, so the rest of the backward pass (quant_conv, encoder) overlaps it.  The
-   backward writes ``grad_E`` pre-scaled by 1/W straight into the head of that buffer (``vq_backward_ex``'s
-   ``grad_E_scale``; no packing copy, no rescale pass), so the SUM is the average.  Histogram counts travel as two exact
-   fp32 words (low 16 bits and the rest: sums stay below 2^24 for up to 256 ranks and 2^40 latents per code).
-   ``wait()`` joins the collective before the optimizer step (stream-ordered, the host does not block).
+   * ``overlap=True`` (default): the collective leaves the critical path.  The codebook gradient is linear in the per-code
+     sums ``S[k] = sum_{n: idx[n] = k} (e_k - z_n)``, which the FORWARD accumulates (``vq_forward_ex``) straight into the
+     head of the flat buffer; the all-reduce starts right after the forward and runs (on NCCL's stream) under whatever
+     comes between the forward and the codebook's backward -- decoder, losses, the decoder's backward; in bench.py, where
+     nothing comes in between, under the backward kernel itself, which no longer scatters.  The backward waits for it
+     (stream-ordered) and turns the summed S into ``weight.grad`` with one scaling pass
+     (``vq_backward_ex(code_diff_sum=...)``, scale ``g_loss * beta * 2 / (N D W)``).
+   * ``overlap=False``, and automatically for gradient-accumulation steps: the backward writes ``grad_E`` pre-scaled by 1/W
+     into the head of the buffer (no packing copy) and a post-accumulate-grad hook starts the all-reduce as soon as the
+     scatter-add kernel has been enqueued; ``wait()`` joins it before the optimizer step.
+
+   Histogram counts travel as two exact fp32 words (low 16 bits and the rest: sums stay below 2^24 for up to 256 ranks and
+   2^40 latents per code).  ``wait()`` is stream-ordered, the host does not block.
 """
 from __future__ import annotations
 
@@ -50,37 +57,57 @@ class DataParallelVQ(torch.nn.Module):
     """Wraps a stand-alone CodeBook for batch-sharded training (see the module docstring for when NOT to use it).
 
         dp = DataParallelVQ(codebook)             # after dist.init_process_group
-        z_q, idx, loss = dp(z_local)              # local forward
-        (loss + downstream(z_q)).backward()       # the ONE all-reduce starts inside backward, overlapped with what follows
+        z_q, idx, loss = dp(z_local)              # local forward; the ONE all-reduce of the step starts here (overlap=True)
+        (loss + downstream(z_q)).backward()       # ... and is joined inside the codebook's backward
         dp.wait()                                 # before optimizer.step(): weight.grad is the global-batch gradient
         dp.global_histogram, dp.global_loss
 
     Shards must have equal size (the global loss / gradient are means of the per-rank ones).
     """
 
-    def __init__(self, codebook, group=None):
+    def __init__(self, codebook, group=None, overlap: bool = True):
         super().__init__()
         self.codebook_module = codebook
         self.group = group
+        self.overlap = overlap
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         codebook.grad_scale = 1.0 / self.world_size
         codebook.grad_alloc = self._alloc_grad
+        codebook.scatter_alloc = self._alloc_scatter
+        codebook.scatter_ready = self._scatter_ready
         self._flat = None            # the step's exchange buffer
         self._flat_has_stats = False
-        self._work = None
+        self._work = None            # outstanding collective of the post-backward path: (work, flat, K, D, copy_back)
+        self._fwd_work = None        # outstanding collective of the overlapped path: (work, flat, K, D)
+        self._step_overlapped = False
         self._reduced = None         # (flat buffer, K, D) of the last completed exchange
         self._local = None           # (hist, loss) of the last forward, not yet exchanged
         self.sync_grads = True
         self._hook = codebook.codebook.weight.register_post_accumulate_grad_hook(self._on_grad_ready)
 
-    # ---- flat exchange buffer: [grad_E (K*D) | hist lo (K) | hist hi (K) | loss | 1]
+    # ---- flat exchange buffer: [S or grad_E (K*D) | hist lo (K) | hist hi (K) | loss | 1]
     def _new_flat(self, K, D, device):
         return torch.empty(K * D + 2 * K + 2, dtype=torch.float32, device=device)
 
+    def _alloc_scatter(self, K, D, device):
+        """Called by the CodeBook's forward (overlapped path): the per-code sums go into the head of a fresh flat buffer."""
+        self._flat = self._new_flat(K, D, device)
+        self._flat_has_stats = False
+        return self._flat[:K * D].view(K, D)
+
+    def _scatter_ready(self, scat):
+        """Called by the CodeBook's backward before it reads the sums: join their all-reduce (the stream waits, not the host)."""
+        fw = self._fwd_work
+        if fw is not None and fw[1].data_ptr() == scat.data_ptr():
+            if fw[0] is not None:
+                fw[0].wait()
+            self._reduced = (fw[1], fw[2], fw[3])
+            self._fwd_work = None
+
     def _alloc_grad(self, K, D, device):
-        """Called by the CodeBook's backward: grad_E is the head of the step's flat buffer (fresh per step, because autograd
-        may keep the tensor as ``weight.grad``; allocated -- and its histogram / loss tail filled -- right after the forward,
-        so that only the collective itself is left to do when the gradient arrives)."""
+        """Called by the CodeBook's backward (post-backward path): grad_E is the head of the step's flat buffer (fresh per step,
+        because autograd may keep the tensor as ``weight.grad``; allocated -- and its histogram / loss tail filled -- right
+        after the forward, so that only the collective itself is left to do when the gradient arrives)."""
         if self._flat is None or self._flat.numel() != K * D + 2 * K + 2 or self._flat.device != device:
             self._flat = self._new_flat(K, D, device)
             self._flat_has_stats = False
@@ -94,7 +121,7 @@ class DataParallelVQ(torch.nn.Module):
         tail[2 * K + 1:].fill_(1.0)
 
     def _on_grad_ready(self, param):
-        if self.world_size <= 1 or not self.sync_grads or self._local is None:
+        if self._step_overlapped or self.world_size <= 1 or not self.sync_grads or self._local is None:
             return
         K, D = param.shape
         flat = self._flat
@@ -113,20 +140,38 @@ class DataParallelVQ(torch.nn.Module):
         self._flat_has_stats = False
 
     def forward(self, z, **kw):
-        out = self.codebook_module(z, **kw)
-        z_q, idx, loss = out
         cb = self.codebook_module
+        w = cb.codebook.weight
+        training = self.world_size > 1 and self.sync_grads and torch.is_grad_enabled() and w.requires_grad and w.dim() == 2
+        # the overlapped exchange needs this step's gradient to be the whole gradient (no accumulation in progress)
+        self._step_overlapped = bool(training and self.overlap and w.grad is None and not cb.deterministic
+                                     and not kw.get("indices_only", False))
+        cb.scatter_in_forward = self._step_overlapped
+        try:
+            out = cb(z, **kw)
+        finally:
+            cb.scatter_in_forward = False
+        z_q, idx, loss = out
         if loss is not None and cb.last_histogram is not None:
             self._local = (cb.last_histogram, loss.detach())
             self._reduced = None
-            w = cb.codebook.weight
-            if self.world_size > 1 and self.sync_grads and torch.is_grad_enabled() and w.requires_grad and w.dim() == 2:
-                # the step's exchange buffer, its histogram / loss tail filled now (these small kernels run ahead of the
-                # backward pass instead of between the scatter-add and the collective)
+            if training:
                 K, D = w.shape
-                self._flat = self._new_flat(K, D, w.device)
-                self._fill_stats(self._flat, K, D)
-                self._flat_has_stats = True
+                if self._step_overlapped and self._flat is not None:
+                    # the forward filled the head with the per-code sums: complete the buffer and start the step's collective
+                    flat = self._flat
+                    self._fill_stats(flat, K, D)
+                    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                    self._fwd_work = (work, flat, K, D)
+                    self._local = None
+                    self._flat = None
+                else:
+                    self._step_overlapped = False
+                    # post-backward path: the step's exchange buffer, its histogram / loss tail filled now (these small
+                    # kernels run ahead of the backward pass instead of between the scatter-add and the collective)
+                    self._flat = self._new_flat(K, D, w.device)
+                    self._fill_stats(self._flat, K, D)
+                    self._flat_has_stats = True
         return out
 
     def wait(self):
@@ -139,6 +184,12 @@ class DataParallelVQ(torch.nn.Module):
                 copy_back.grad.copy_(flat[:K * D].view(K, D))
             self._reduced = (flat, K, D)
             self._work = None
+        if self._fwd_work is not None:                        # a forward whose backward never ran (or has not run yet)
+            work, flat, K, D = self._fwd_work
+            if work is not None:
+                work.wait()
+            self._reduced = (flat, K, D)
+            self._fwd_work = None
 
     def _ensure_stats(self):
         """Histogram / loss exchange for steps without a backward (evaluation): a small collective of its own."""

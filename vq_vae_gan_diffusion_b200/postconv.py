@@ -116,7 +116,7 @@ class _FoldedFunction(torch.autograd.Function):
                 det = bool(cbm.deterministic) and need_E
                 ws = cbm._workspace_bwd.get(_native.backward_workspace_bytes_cached(K, D), dev, st) if det else None
                 rc = _native.lib().vq_backward_ex(_ptr(g_zq), strides, 0.0, _ptr(g_loss_t), _ptr(zc), _ptr(idx), _ptr(wk), B, H * W, D, K,
-                                                  float(cbm.beta), B * H * W, float(cbm.grad_scale), 1 if det else 0, _ptr(grad_z),
+                                                  float(cbm.beta), B * H * W, float(cbm.grad_scale), 1 if det else 0, 0, _ptr(grad_z),
                                                   _ptr(grad_E), _ptr(ws), 0 if ws is None else ws.numel(), st)
                 _native.check(rc, "vq_backward_ex")
         return grad_z, grad_E, grad_w, grad_b, None, None
