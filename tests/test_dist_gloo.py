@@ -112,7 +112,7 @@ def _worker(rank, world, init_file, out_file):
         dp0._hook.remove()
 
         cb = OracleCodeBook(E)
-        dp = DataParallelVQ(cb)
+        dp = DataParallelVQ(cb, overlap=True)
         zt = torch.from_numpy(z[sl].copy()).requires_grad_(True)
         z_q, idx, loss = dp(zt)
         assert dp._step_overlapped and dp._fwd_work is not None

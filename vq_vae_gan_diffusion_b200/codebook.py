@@ -157,8 +157,6 @@ class _VQFunction(torch.autograd.Function):
             grad_z = torch.empty((B, D, H, W), dtype=torch.float32, device=dev) if need_z else None
             grad_E = None
             scat = ctx.scat if need_w else None
-            if scat is not None and ctx.scat_ready is not None:
-                ctx.scat_ready(scat)                         # the wrapper's all-reduce of the sums: the stream waits here
             if need_w:
                 # a data-parallel wrapper may hand out the head of its flat exchange buffer (dist.py): the scatter-add
                 # then lands where the all-reduce reads, with no packing copy
@@ -168,14 +166,34 @@ class _VQFunction(torch.autograd.Function):
             ws = None
             if det:
                 ws = module._workspace_bwd.get(_native.backward_workspace_bytes_cached(K, D), dev, st)
-            rc = _native.lib().vq_backward_ex(_ptr(g_zq), strides, 0.0, _ptr(g_loss_t), _ptr(zc), _ptr(idx), _ptr(weight),
-                                              B, H * W, D, K, float(module.beta), B * H * W, float(module.grad_scale),
-                                              1 if det else 0, _ptr(scat), _ptr(grad_z), _ptr(grad_E), _ptr(ws),
-                                              0 if ws is None else ws.numel(), st)
-            if rc != 0:
-                _native.check(rc, "vq_backward_ex")
+            L = _native.lib()
+            n_launch = 0
+            if scat is None:
+                rc = L.vq_backward_ex(_ptr(g_zq), strides, 0.0, _ptr(g_loss_t), _ptr(zc), _ptr(idx), _ptr(weight),
+                                      B, H * W, D, K, float(module.beta), B * H * W, float(module.grad_scale),
+                                      1 if det else 0, 0, _ptr(grad_z), _ptr(grad_E), _ptr(ws),
+                                      0 if ws is None else ws.numel(), st)
+                if rc != 0:
+                    _native.check(rc, "vq_backward_ex")
+            else:
+                # The forward accumulated the per-code sums and (data-parallel) their all-reduce is in flight: grad_z first --
+                # it does not depend on them, so the collective keeps running under this kernel --, then the stream waits for
+                # the summed sums and one scaling pass turns them into the codebook gradient.
+                if need_z:
+                    rc = L.vq_backward_ex(_ptr(g_zq), strides, 0.0, _ptr(g_loss_t), _ptr(zc), _ptr(idx), _ptr(weight),
+                                          B, H * W, D, K, float(module.beta), B * H * W, 1.0, 0, 0, _ptr(grad_z), 0, 0, 0, st)
+                    if rc != 0:
+                        _native.check(rc, "vq_backward_ex")
+                    n_launch = int(L.vq_last_launch_count()) if module.count_launches else 0
+                if ctx.scat_ready is not None:
+                    ctx.scat_ready(scat)
+                rc = L.vq_backward_ex(0, None, 0.0, _ptr(g_loss_t), _ptr(zc), _ptr(idx), _ptr(weight),
+                                      B, H * W, D, K, float(module.beta), B * H * W, float(module.grad_scale), 0, _ptr(scat),
+                                      0, _ptr(grad_E), 0, 0, st)
+                if rc != 0:
+                    _native.check(rc, "vq_backward_ex")
             if module.count_launches:
-                module._launches_bwd = int(_native.lib().vq_last_launch_count())
+                module._launches_bwd = n_launch + int(L.vq_last_launch_count())
         return grad_z, grad_E, None, None
 
 

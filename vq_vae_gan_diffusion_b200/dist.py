@@ -18,14 +18,14 @@ Two ways to get that average:
 
        [ S or grad_E (K*D) | hist low 16 bits (K) | hist high bits (K) | loss | 1 ]
 
-   * ``overlap=True`` (default): the collective leaves the critical path.  The codebook gradient is linear in the per-code
+   * ``overlap=True`` (the default from 4 ranks on): the collective leaves the critical path.  The codebook gradient is linear in the per-code
      sums ``S[k] = sum_{n: idx[n] = k} (e_k - z_n)``, which the FORWARD accumulates (``vq_forward_ex``) straight into the
      head of the flat buffer; the all-reduce starts right after the forward and runs (on NCCL's stream) under whatever
      comes between the forward and the codebook's backward -- decoder, losses, the decoder's backward; in bench.py, where
      nothing comes in between, under the backward kernel itself, which no longer scatters.  The backward waits for it
      (stream-ordered) and turns the summed S into ``weight.grad`` with one scaling pass
      (``vq_backward_ex(code_diff_sum=...)``, scale ``g_loss * beta * 2 / (N D W)``).
-   * ``overlap=False``, and automatically for gradient-accumulation steps: the backward writes ``grad_E`` pre-scaled by 1/W
+   * ``overlap=False`` (the default below 4 ranks), and automatically for gradient-accumulation steps: the backward writes ``grad_E`` pre-scaled by 1/W
      into the head of the buffer (no packing copy) and a post-accumulate-grad hook starts the all-reduce as soon as the
      scatter-add kernel has been enqueued; ``wait()`` joins it before the optimizer step.
 
@@ -65,12 +65,15 @@ class DataParallelVQ(torch.nn.Module):
     Shards must have equal size (the global loss / gradient are means of the per-rank ones).
     """
 
-    def __init__(self, codebook, group=None, overlap: bool = True):
+    def __init__(self, codebook, group=None, overlap="auto"):
         super().__init__()
         self.codebook_module = codebook
         self.group = group
-        self.overlap = overlap
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        # "auto": accumulating the sums in the forward costs ~50 us per cfg4 step on the rank itself (the atomics are free inside
+        # the HBM-bound backward kernel but not inside the latency-bound select kernel: tools/scatter_ab.py), so the overlapped
+        # exchange pays off once the all-reduce it hides is longer than that: from 4 ranks on for a 17 MB buffer
+        self.overlap = (self.world_size >= 4) if overlap == "auto" else bool(overlap)
         codebook.grad_scale = 1.0 / self.world_size
         codebook.grad_alloc = self._alloc_grad
         codebook.scatter_alloc = self._alloc_scatter
@@ -159,6 +162,8 @@ class DataParallelVQ(torch.nn.Module):
                 K, D = w.shape
                 if self._step_overlapped and self._flat is not None:
                     # the forward filled the head with the per-code sums: complete the buffer and start the step's collective
+                    # (a side stream for the packing kernels + the launch was tried: record_stream on the 17 MB buffer makes the
+                    # caching allocator fall back to fresh allocations every step, 1.7 ms per step at 2 GPUs)
                     flat = self._flat
                     self._fill_stats(flat, K, D)
                     work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
