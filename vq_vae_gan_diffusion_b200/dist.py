@@ -18,14 +18,14 @@ Two ways to get that average:
 
        [ S or grad_E (K*D) | hist low 16 bits (K) | hist high bits (K) | loss | 1 ]
 
-   * ``overlap=True`` (the default from 4 ranks on): the collective leaves the critical path.  The codebook gradient is linear in the per-code
+   * ``overlap=True`` (opt-in): the collective leaves the critical path.  The codebook gradient is linear in the per-code
      sums ``S[k] = sum_{n: idx[n] = k} (e_k - z_n)``, which the FORWARD accumulates (``vq_forward_ex``) straight into the
      head of the flat buffer; the all-reduce starts right after the forward and runs (on NCCL's stream) under whatever
      comes between the forward and the codebook's backward -- decoder, losses, the decoder's backward; in bench.py, where
      nothing comes in between, under the backward kernel itself, which no longer scatters.  The backward waits for it
      (stream-ordered) and turns the summed S into ``weight.grad`` with one scaling pass
      (``vq_backward_ex(code_diff_sum=...)``, scale ``g_loss * beta * 2 / (N D W)``).
-   * ``overlap=False`` (the default below 4 ranks), and automatically for gradient-accumulation steps: the backward writes ``grad_E`` pre-scaled by 1/W
+   * ``overlap=False`` (default), and automatically for gradient-accumulation steps: the backward writes ``grad_E`` pre-scaled by 1/W
      into the head of the buffer (no packing copy) and a post-accumulate-grad hook starts the all-reduce as soon as the
      scatter-add kernel has been enqueued; ``wait()`` joins it before the optimizer step.
 
@@ -57,23 +57,25 @@ class DataParallelVQ(torch.nn.Module):
     """Wraps a stand-alone CodeBook for batch-sharded training (see the module docstring for when NOT to use it).
 
         dp = DataParallelVQ(codebook)             # after dist.init_process_group
-        z_q, idx, loss = dp(z_local)              # local forward; the ONE all-reduce of the step starts here (overlap=True)
-        (loss + downstream(z_q)).backward()       # ... and is joined inside the codebook's backward
+        z_q, idx, loss = dp(z_local)              # local forward (overlap=True: the ONE all-reduce of the step starts here ...
+        (loss + downstream(z_q)).backward()       # ... and is joined inside the codebook's backward; else it starts here)
         dp.wait()                                 # before optimizer.step(): weight.grad is the global-batch gradient
         dp.global_histogram, dp.global_loss
 
     Shards must have equal size (the global loss / gradient are means of the per-rank ones).
     """
 
-    def __init__(self, codebook, group=None, overlap="auto"):
+    def __init__(self, codebook, group=None, overlap: bool = False):
         super().__init__()
         self.codebook_module = codebook
         self.group = group
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
-        # "auto": accumulating the sums in the forward costs ~50 us per cfg4 step on the rank itself (the atomics are free inside
-        # the HBM-bound backward kernel but not inside the latency-bound select kernel: tools/scatter_ab.py), so the overlapped
-        # exchange pays off once the all-reduce it hides is longer than that: from 4 ranks on for a 17 MB buffer
-        self.overlap = (self.world_size >= 4) if overlap == "auto" else bool(overlap)
+        # The overlapped exchange is opt-in: accumulating the sums in the forward costs ~50-70 us per cfg4 step on the rank itself
+        # (the atomics are free inside the HBM-bound backward kernel but not inside the latency-bound select kernel:
+        # profiles/r2_ab_scatter_in_forward_1gpu.json), about what the hidden all-reduce of a 17 MB buffer takes on 2-8 GPUs -- in
+        # bench.py, where nothing runs between forward and backward, it measured neutral (profiles/r2_ab_overlapped_exchange.jsonl).
+        # It pays off when the collective is slower (more ranks, larger codebooks, a slower fabric).
+        self.overlap = bool(overlap)
         codebook.grad_scale = 1.0 / self.world_size
         codebook.grad_alloc = self._alloc_grad
         codebook.scatter_alloc = self._alloc_scatter
