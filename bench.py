@@ -321,6 +321,9 @@ def main():
     ap.add_argument("--cuda-graphs", action="store_true",
                     help="drive the module through its CUDA-graph fast path (CodeBook.use_cuda_graphs; for the small, "
                          "launch-bound workloads cfg1 / cfg2)")
+    ap.add_argument("--collective", default="nccl", choices=["nccl", "multimem"],
+                    help="N > 1: the all-reduce of the codebook gradient through NCCL, or through the library's own NVLS kernel "
+                         "(multimem.ld_reduce / multimem.st on a symmetric buffer, csrc/vq_allreduce.cuh)")
     ap.add_argument("--soak-seconds", type=float, default=2.0,
                     help="after the timed region, keep stepping for about this long and report the distance-GEMM kernel's "
                          "fraction of peak once clocks have settled under the power cap (roofline.frac_sustained_run); 0 = off")
@@ -371,7 +374,7 @@ def main():
     if args.cuda_graphs:
         cb.use_cuda_graphs = True
         cb.graph_outputs = "static"                 # the step consumes its results before the next call
-    dp = DataParallelVQ(cb) if world > 1 else None
+    dp = DataParallelVQ(cb, collective=args.collective) if world > 1 else None
     z_req = z.clone().requires_grad_(not tok)
     g_loss = torch.ones((), device=dev)
 
@@ -561,7 +564,7 @@ def main():
                    "distribution": args.distribution, "l2": "inputs (2 x 268 MB per GPU) larger than the 126 MB L2"
                    if N * D * 4 > 130e6 else "inputs smaller than L2, no flush (launch-latency-bound workload)",
                    "parallelism": f"dp{world} (batch-sharded latents, replicated codebook, grad_E all-reduce)",
-                   "cuda_graphs": bool(args.cuda_graphs)},
+                   "cuda_graphs": bool(args.cuda_graphs), "collective": args.collective if world > 1 else None},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "select_stats_last_step": stats,
     }

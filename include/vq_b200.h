@@ -189,6 +189,20 @@ int vq_forward_ex(const float* z_nchw, int64_t B, int64_t HW, int D,
                   unsigned long long* stats, void* workspace, size_t workspace_bytes, vq_stream_t stream);
 
 /*
+ * SUM all-reduce, in place, of a symmetric fp32 buffer over NVLink with the NVSwitch doing the additions (NVLS: multimem.ld_reduce /
+ * multimem.st on the buffer's multicast address) -- the data-parallel exchange of the codebook gradient / usage histogram (dist.py;
+ * new in this build, the reference is single-device).  One process per GPU; every rank calls it with the same n_floats.
+ *   multicast_ptr     multicast address of the buffer (torch.distributed._symmetric_memory handle.multicast_ptr); the caller's
+ *                     prior work on `stream` must have produced this rank's contribution in its own copy of the buffer
+ *   signal_pads_dev   DEVICE array of `world` pointers to the ranks' signal pads (handle.signal_pad_ptrs_dev), zero when idle;
+ *                     needs 64 * world words of each pad
+ *   n_floats          multiple of 4 * world
+ * The two device-side barriers spin with a bound (a rank that never arrives traps instead of hanging the box).
+ */
+int vq_allreduce_multimem(void* multicast_ptr, void* const* signal_pads_dev, int rank, int world, int64_t n_floats,
+                          vq_stream_t stream);
+
+/*
  * Index -> embedding lookup in NCHW layout (the decode side: codebook(indices).reshape(B,h,w,D).permute(0,3,1,2),
  * worker/vqganVqvaeWorker.py:459, network/vqTransformer/vqTransformer.py:98).
  *   out_nchw (B, D, HW) fp32

@@ -32,7 +32,7 @@ def rel(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
 
-def run_checks(rank, world, dev, K=4096, Bl=4, H=32, W=32, deterministic=False, overlap=True):
+def run_checks(rank, world, dev, K=4096, Bl=4, H=32, W=32, deterministic=False, overlap=True, collective="nccl"):
     """The checks of one rank; returns a dict of error figures.  Needs an initialised process group."""
     import vq_vae_gan_diffusion_b200 as vq
     from vq_vae_gan_diffusion_b200.dist import DataParallelVQ
@@ -55,10 +55,10 @@ def run_checks(rank, world, dev, K=4096, Bl=4, H=32, W=32, deterministic=False, 
 
     # --- stand-alone wrapper: ONE all-reduce of [grad_E / W | hist | loss | 1]
     cb = fresh()
-    dp = DataParallelVQ(cb, overlap=overlap)
+    dp = DataParallelVQ(cb, overlap=overlap, collective=collective)
     zl = z[sl].clone().requires_grad_(True)
     z_q, idx, loss = dp(zl)
-    assert dp._step_overlapped == (overlap and not deterministic and world > 1)
+    assert dp._step_overlapped == (overlap and not deterministic and world > 1 and collective == "nccl")
     torch.autograd.backward([z_q, loss], [gout[sl], one])
     dp.wait()
 
@@ -118,8 +118,13 @@ def _worker(rank, world, backend, init_file, out_file):
         res = run_checks(rank, world, dev)
         res_det = run_checks(rank, world, dev, K=1024, Bl=2, deterministic=True)
         res_hook = run_checks(rank, world, dev, K=2048, Bl=2, overlap=False)
+        results = [res, res_det, res_hook]
+        if backend == "nccl":
+            # the library's own NVLS all-reduce (csrc/vq_allreduce.cuh) instead of NCCL's, two steps on the persistent buffer
+            results.append(run_checks(rank, world, dev, K=4096, Bl=2, overlap=False, collective="multimem"))
+            results.append(run_checks(rank, world, dev, K=1000, Bl=2, overlap=False, collective="multimem"))
         gathered = [None] * world
-        dist.all_gather_object(gathered, (res, res_det, res_hook))
+        dist.all_gather_object(gathered, tuple(results))
         if rank == 0:
             np.save(out_file, np.array(gathered, dtype=object), allow_pickle=True)
         dist.barrier()

@@ -23,7 +23,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     res = (run_checks(rank, world, dev), run_checks(rank, world, dev, K=1024, Bl=2, deterministic=True),
-           run_checks(rank, world, dev, K=2048, Bl=2, overlap=False))
+           run_checks(rank, world, dev, K=2048, Bl=2, overlap=False),
+           run_checks(rank, world, dev, K=4096, Bl=2, overlap=False, collective="multimem"))
     gathered = [None] * world
     dist.all_gather_object(gathered, res)
     rc = 0

@@ -1,0 +1,73 @@
+// vq_allreduce.cuh -- one-shot-per-slice SUM all-reduce of the data-parallel exchange buffer over NVLink / NVSwitch with the
+// switch doing the arithmetic (NVLS): every rank owns 1/W of the buffer, pulls the SUM of that slice from all ranks with
+// multimem.ld_reduce on the buffer's multicast address (the reduction happens inside the NVSwitch) and pushes it back to all
+// ranks with multimem.st -- each byte crosses a rank's links once in and once out.  The buffer is symmetric memory (same
+// allocation on every rank, bound to one multicast object; torch.distributed._symmetric_memory does the allocation and the
+// handle exchange: plumbing), the ranks meet at two device-side barriers on their signal pads: one before the first load
+// (every rank's contribution is complete: stream order on each rank puts its producer kernel before this one) and one after
+// the last store (every slice has landed everywhere).  For the CodeBook's 16.9 MB buffer on 8 B200s NCCL's all-reduce
+// takes ~100 us (latency-bound at this size); this path is bounded by 2 x 2.1 MB per rank over the links plus two barriers.
+//
+// The barriers spin on flags written by OTHER GPUs: each rank is its own process on its own GPU (never several ranks on one
+// device), and the spins are bounded -- a rank that never arrives turns into a trap, not a hung box.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx_sm100.cuh"
+
+namespace vq {
+
+constexpr int kArThreads = 512;
+constexpr int kArMaxBlocks = 64;         // barrier slots used on the signal pad: blocks x world (<= 2304 words)
+
+__device__ __forceinline__ void ar_put_signal(uint32_t* addr) {               // flag 0 -> 1 on a peer's pad, release
+    const long long t0 = clock64();
+    uint32_t old;
+    do {
+        asm volatile("atom.global.release.sys.cas.b32 %0, [%1], 0, 1;" : "=r"(old) : "l"(addr) : "memory");
+        if (old != 0u && clock64() - t0 > VQ_MBAR_TIMEOUT_CYCLES) {
+            printf("vq_b200: all-reduce barrier (put) timed out, block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    } while (old != 0u);
+}
+__device__ __forceinline__ void ar_wait_signal(uint32_t* addr) {              // flag 1 -> 0 on my pad, acquire
+    const long long t0 = clock64();
+    uint32_t old;
+    do {
+        asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], 1, 0;" : "=r"(old) : "l"(addr) : "memory");
+        if (old != 1u && clock64() - t0 > VQ_MBAR_TIMEOUT_CYCLES) {
+            printf("vq_b200: all-reduce barrier (wait) timed out, block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    } while (old != 1u);
+}
+
+// barrier among the CTAs with this blockIdx on all ranks: thread t < world signals rank t and waits for rank t
+__device__ __forceinline__ void ar_barrier(uint32_t* const* pads, int rank, int world) {
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        ar_put_signal(pads[threadIdx.x] + (size_t)blockIdx.x * world + rank);
+        ar_wait_signal(pads[rank] + (size_t)blockIdx.x * world + threadIdx.x);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kArThreads)
+vq_allreduce_multimem_kernel(float* __restrict__ mc, uint32_t* const* __restrict__ pads, int rank, int world, int64_t n_vec4) {
+    ar_barrier(pads, rank, world);                       // every rank's contribution is in its buffer
+    const int64_t slice = n_vec4 / world;                // (host guarantees divisibility)
+    float4* base = reinterpret_cast<float4*>(mc) + (int64_t)rank * slice;
+    for (int64_t i = (int64_t)blockIdx.x * kArThreads + threadIdx.x; i < slice; i += (int64_t)gridDim.x * kArThreads) {
+        float4 v;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(base + i) : "memory");
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                     :: "l"(base + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    }
+    __threadfence_system();                              // my stores are visible everywhere before I say so
+    ar_barrier(pads, rank, world);                       // every slice has landed in every buffer
+}
+
+}  // namespace vq

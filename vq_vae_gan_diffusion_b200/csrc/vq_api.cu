@@ -13,6 +13,7 @@
 #include <utility>
 
 #include "../../include/vq_b200.h"
+#include "vq_allreduce.cuh"
 #include "vq_argmin_sm100.cuh"
 #include "vq_backward.cuh"
 #include "vq_common.cuh"
@@ -762,6 +763,27 @@ VQ_EXPORT int vq_backward_ex(const float* gout, const int64_t* gout_strides, flo
                              float* grad_z, float* grad_E, void* workspace, size_t workspace_bytes, vq_stream_t stream) {
     return backward_impl(gout, gout_strides, g_loss, g_loss_dev, z_nchw, idx, E, B, HW, D, K, beta, n_global, grad_E_scale,
                          deterministic != 0, code_diff_sum, grad_z, grad_E, workspace, workspace_bytes, stream);
+}
+
+VQ_EXPORT int vq_allreduce_multimem(void* multicast_ptr, void* const* signal_pads_dev, int rank, int world, int64_t n_floats,
+                                    vq_stream_t stream) {
+    g_launches = 0;
+    if (!multicast_ptr || !signal_pads_dev) return fail(VQ_E_INVALID, "null pointer");
+    if (world < 2 || world > 32 || rank < 0 || rank >= world) return fail(VQ_E_INVALID, "bad rank %d / world %d", rank, world);
+    if (n_floats <= 0 || n_floats % (4 * (int64_t)world) != 0)
+        return fail(VQ_E_INVALID, "n_floats=%lld must be a positive multiple of 4 * world", (long long)n_floats);
+    if ((reinterpret_cast<uintptr_t>(multicast_ptr) & 15) != 0) return fail(VQ_E_INVALID, "multicast pointer must be 16-byte aligned");
+    DevInfo* dev;
+    int rc = device_info(&dev);
+    if (rc != VQ_OK) return rc;
+    const int64_t n_vec4 = n_floats / 4, slice = n_vec4 / world;
+    int64_t blocks = (slice + vq::kArThreads - 1) / vq::kArThreads;
+    if (blocks > vq::kArMaxBlocks) blocks = vq::kArMaxBlocks;
+    if (blocks < 1) blocks = 1;
+    vq::vq_allreduce_multimem_kernel<<<(unsigned)blocks, vq::kArThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        static_cast<float*>(multicast_ptr), reinterpret_cast<uint32_t* const*>(signal_pads_dev), rank, world, n_vec4);
+    VQ_LAUNCH_CHECK("vq_allreduce_multimem_kernel");
+    return VQ_OK;
 }
 
 VQ_EXPORT int vq_embed_nchw(const int64_t* idx, const float* E, int64_t B, int64_t HW, int D, int K, float* out,

@@ -65,11 +65,19 @@ class DataParallelVQ(torch.nn.Module):
     Shards must have equal size (the global loss / gradient are means of the per-rank ones).
     """
 
-    def __init__(self, codebook, group=None, overlap: bool = False):
+    def __init__(self, codebook, group=None, overlap: bool = False, collective: str = "nccl"):
         super().__init__()
         self.codebook_module = codebook
         self.group = group
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        # collective = "multimem": the library's own NVLS all-reduce kernel (csrc/vq_allreduce.cuh: multimem.ld_reduce / multimem.st
+        # on a symmetric buffer, the NVSwitch adds) instead of NCCL's, in-stream; "nccl" (default) = torch.distributed.all_reduce.
+        if collective not in ("nccl", "multimem"):
+            raise ValueError("collective must be 'nccl' or 'multimem'")
+        self.collective = collective
+        if collective == "multimem":
+            overlap = False          # the NVLS kernel runs in-stream on one persistent buffer: nothing to overlap with
+        self._symm = None            # (persistent symmetric buffer, handle, padded length) of the multimem path
         # The overlapped exchange is opt-in: accumulating the sums in the forward costs ~50-70 us per cfg4 step on the rank itself
         # (the atomics are free inside the HBM-bound backward kernel but not inside the latency-bound select kernel:
         # profiles/r2_ab_scatter_in_forward_1gpu.json), about what the hidden all-reduce of a 17 MB buffer takes on 2-8 GPUs -- in
@@ -92,7 +100,38 @@ class DataParallelVQ(torch.nn.Module):
 
     # ---- flat exchange buffer: [S or grad_E (K*D) | hist lo (K) | hist hi (K) | loss | 1]
     def _new_flat(self, K, D, device):
+        if self.collective == "multimem" and self.world_size > 1 and device.type == "cuda":
+            return self._symm_flat(K, D, device)
         return torch.empty(K * D + 2 * K + 2, dtype=torch.float32, device=device)
+
+    def _symm_flat(self, K, D, device):
+        """The multimem path exchanges through ONE persistent symmetric-memory buffer (allocation + handle exchange are a
+        rendezvous, far too slow per step): every step reuses it, so what leaves this class is copied out of it."""
+        n = K * D + 2 * K + 2
+        n_pad = -(-n // (4 * self.world_size)) * (4 * self.world_size)
+        if self._symm is None or self._symm[2] != n_pad or self._symm[0].device != device:
+            import torch.distributed._symmetric_memory as symm_mem
+            buf = symm_mem.empty(n_pad, dtype=torch.float32, device=device)
+            grp = self.group if self.group is not None else dist.group.WORLD
+            hdl = symm_mem.rendezvous(buf, grp.group_name)
+            if int(hdl.multicast_ptr) == 0:
+                raise RuntimeError("collective='multimem' needs NVLS multicast support (NVSwitch); use collective='nccl'")
+            buf.zero_()
+            self._symm = (buf, hdl, n_pad)
+        return self._symm[0][:n]
+
+    def _all_reduce(self, flat):
+        """SUM over ranks, in place; returns a work handle to wait on, or None when the collective ran in-stream."""
+        if self.collective == "multimem" and self._symm is not None and flat.data_ptr() == self._symm[0].data_ptr():
+            from . import _native
+            buf, hdl, n_pad = self._symm
+            with torch.cuda.device(buf.device):
+                rc = _native.lib().vq_allreduce_multimem(int(hdl.multicast_ptr), int(hdl.signal_pad_ptrs_dev), int(hdl.rank),
+                                                         int(hdl.world_size), n_pad,
+                                                         int(torch.cuda.current_stream(buf.device).cuda_stream))
+            _native.check(rc, "vq_allreduce_multimem")
+            return None
+        return dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _alloc_scatter(self, K, D, device):
         """Called by the CodeBook's forward (overlapped path): the per-code sums go into the head of a fresh flat buffer."""
@@ -138,7 +177,12 @@ class DataParallelVQ(torch.nn.Module):
             self._flat_has_stats = False
         if not self._flat_has_stats:
             self._fill_stats(flat, K, D)
-        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        work = self._all_reduce(flat)
+        if self._symm is not None and flat.data_ptr() == self._symm[0].data_ptr():
+            # the persistent symmetric buffer is reused next step: weight.grad and the statistics get their own copies
+            flat = flat.clone()
+            param.grad = flat[:K * D].view(K, D)
+            aliased = True
         self._work = (work, flat, K, D, None if aliased else param)
         self._local = None
         self._flat = None
@@ -168,7 +212,7 @@ class DataParallelVQ(torch.nn.Module):
                     # caching allocator fall back to fresh allocations every step, 1.7 ms per step at 2 GPUs)
                     flat = self._flat
                     self._fill_stats(flat, K, D)
-                    work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                    work = self._all_reduce(flat)
                     self._fwd_work = (work, flat, K, D)
                     self._local = None
                     self._flat = None
