@@ -195,12 +195,19 @@ int vq_forward_ex(const float* z_nchw, int64_t B, int64_t HW, int D,
  *   multicast_ptr     multicast address of the buffer (torch.distributed._symmetric_memory handle.multicast_ptr); the caller's
  *                     prior work on `stream` must have produced this rank's contribution in its own copy of the buffer
  *   signal_pads_dev   DEVICE array of `world` pointers to the ranks' signal pads (handle.signal_pad_ptrs_dev), zero when idle;
- *                     needs 64 * world words of each pad
+ *                     needs min(128, 2304 / world) * world words of each pad (torch's default pad is 2304 words)
  *   n_floats          multiple of 4 * world
  * The two device-side barriers spin with a bound (a rank that never arrives traps instead of hanging the box).
  */
 int vq_allreduce_multimem(void* multicast_ptr, void* const* signal_pads_dev, int rank, int world, int64_t n_floats,
                           vq_stream_t stream);
+
+/*
+ * Tail of the data-parallel exchange buffer (dist.py) in one launch:
+ *   tail (2K + 2) fp32 = [hist & 0xffff (K) | hist >> 16 (K) | loss | 1]   -- count words that are exact in fp32 and stay exact
+ * when summed over ranks.  hist (K) int64 and loss (1) fp32 are the outputs of vq_forward.
+ */
+int vq_pack_stats(const int64_t* hist, const float* loss, int K, float* tail, vq_stream_t stream);
 
 /*
  * Index -> embedding lookup in NCHW layout (the decode side: codebook(indices).reshape(B,h,w,D).permute(0,3,1,2),

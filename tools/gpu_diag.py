@@ -112,7 +112,7 @@ def main():
         d64 = z2[:, None] + (E.double() ** 2).sum(1)[None, :] - 2 * zf.double() @ E.double().t()
         e2max = (E.double() ** 2).sum(1).max()
         r = z2 + e2max + 2 * a
-        eps = a * (2 ** -9 + 2 ** -12) + r * 2 ** -22
+        eps = a * (2 ** -9 + 2 ** -12) + (r + e2max + 2 * a) * 2 ** -23       # vq_common.cuh: candidate_margin
         viol = ((got + z2[:, None] - d64).abs() > eps[:, None]).sum().item()
         worst = ((got + z2[:, None] - d64).abs() / eps[:, None]).max().item()
         print(f"   margin bound: violations={viol}, worst |err|/eps={worst:.3f}")

@@ -19,7 +19,10 @@
 namespace vq {
 
 constexpr int kArThreads = 512;
-constexpr int kArMaxBlocks = 64;         // barrier slots used on the signal pad: blocks x world (<= 2304 words)
+constexpr int kArUnroll = 4;             // 16-byte switch reductions in flight per thread (one round trip through the NVSwitch is
+                                         // several microseconds: a single outstanding load per thread leaves the links idle)
+constexpr int kArMaxBlocks = 128;        // CTAs per rank; each uses `world` barrier slots of the signal pad
+constexpr int kArPadWords = 2304;        // words of a signal pad (torch: 32 channels x 72 ranks; vq_allreduce_multimem bounds the grid by it)
 
 __device__ __forceinline__ void ar_put_signal(uint32_t* addr) {               // flag 0 -> 1 on a peer's pad, release
     const long long t0 = clock64();
@@ -59,15 +62,42 @@ vq_allreduce_multimem_kernel(float* __restrict__ mc, uint32_t* const* __restrict
     ar_barrier(pads, rank, world);                       // every rank's contribution is in its buffer
     const int64_t slice = n_vec4 / world;                // (host guarantees divisibility)
     float4* base = reinterpret_cast<float4*>(mc) + (int64_t)rank * slice;
-    for (int64_t i = (int64_t)blockIdx.x * kArThreads + threadIdx.x; i < slice; i += (int64_t)gridDim.x * kArThreads) {
-        float4 v;
-        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(base + i) : "memory");
-        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
-                     :: "l"(base + i), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+    const int64_t stride = (int64_t)gridDim.x * kArThreads;
+    for (int64_t i0 = (int64_t)blockIdx.x * kArThreads + threadIdx.x; i0 < slice; i0 += stride * kArUnroll) {
+        float4 v[kArUnroll];
+#pragma unroll
+        for (int u = 0; u < kArUnroll; u++) {
+            const int64_t i = i0 + u * stride;
+            if (i < slice)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w) : "l"(base + i) : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < kArUnroll; u++) {
+            const int64_t i = i0 + u * stride;
+            if (i < slice)
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                             :: "l"(base + i), "f"(v[u].x), "f"(v[u].y), "f"(v[u].z), "f"(v[u].w) : "memory");
+        }
     }
     __threadfence_system();                              // my stores are visible everywhere before I say so
     ar_barrier(pads, rank, world);                       // every slice has landed in every buffer
+}
+
+// Tail of the data-parallel exchange buffer in one launch: [hist low 16 bits (K) | hist high bits (K) | loss | 1] as fp32 (each
+// count word is exactly representable and exactly summable over ranks, dist.py) -- replaces eight small tensor kernels per step.
+__global__ void __launch_bounds__(256)
+vq_pack_stats_kernel(const long long* __restrict__ hist, const float* __restrict__ loss, int K, float* __restrict__ tail) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < K) {
+        const long long c = hist[i];
+        tail[i] = (float)(c & 0xFFFF);
+        tail[K + i] = (float)(c >> 16);
+    }
+    if (i == 0) {
+        tail[2 * K] = loss[0];
+        tail[2 * K + 1] = 1.0f;
+    }
 }
 
 }  // namespace vq

@@ -5,6 +5,7 @@
 // on anything but an sm_100 device the compute entry points return VQ_E_DEVICE.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -777,12 +778,25 @@ VQ_EXPORT int vq_allreduce_multimem(void* multicast_ptr, void* const* signal_pad
     int rc = device_info(&dev);
     if (rc != VQ_OK) return rc;
     const int64_t n_vec4 = n_floats / 4, slice = n_vec4 / world;
-    int64_t blocks = (slice + vq::kArThreads - 1) / vq::kArThreads;
-    if (blocks > vq::kArMaxBlocks) blocks = vq::kArMaxBlocks;
+    int64_t blocks = (slice + vq::kArThreads * vq::kArUnroll - 1) / (vq::kArThreads * vq::kArUnroll);
+    const int64_t max_blocks = std::min<int64_t>(vq::kArMaxBlocks, vq::kArPadWords / world);   // barrier slots on the signal pad
+    if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
     vq::vq_allreduce_multimem_kernel<<<(unsigned)blocks, vq::kArThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
         static_cast<float*>(multicast_ptr), reinterpret_cast<uint32_t* const*>(signal_pads_dev), rank, world, n_vec4);
     VQ_LAUNCH_CHECK("vq_allreduce_multimem_kernel");
+    return VQ_OK;
+}
+
+VQ_EXPORT int vq_pack_stats(const int64_t* hist, const float* loss, int K, float* tail, vq_stream_t stream) {
+    g_launches = 0;
+    if (!hist || !loss || !tail) return fail(VQ_E_INVALID, "null pointer");
+    if (K < 1) return fail(VQ_E_INVALID, "bad K=%d", K);
+    if ((reinterpret_cast<uintptr_t>(hist) & 7) != 0 || (reinterpret_cast<uintptr_t>(loss) & 3) != 0 || (reinterpret_cast<uintptr_t>(tail) & 3) != 0)
+        return fail(VQ_E_INVALID, "misaligned pointer");
+    vq::vq_pack_stats_kernel<<<(unsigned)((K + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(hist), loss, K, tail);
+    VQ_LAUNCH_CHECK("vq_pack_stats_kernel");
     return VQ_OK;
 }
 

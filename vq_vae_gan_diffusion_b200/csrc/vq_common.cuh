@@ -131,19 +131,25 @@ __device__ __forceinline__ float ref_distance(float z2, float e2, float dot) {
 }
 
 // Rigorous bound eps on | (score_approx + |z|^2) - d_oracle | valid for every code of a row, and the candidate
-// margin derived from it.  score_approx = e2[k] - 2 * (fp16(z) . fp16(e_k)) with fp32 accumulation in the tensor
+// margin derived from it.  score_approx = fl(e2[k] - 2 * (fp16(z) . fp16(e_k))) with fp32 accumulation in the tensor
 // core; d_oracle = ref_distance() with a canonical-order fp32 dot.  With a = |z| * max_k |e_k| (Cauchy-Schwarz
-// bound of sum |z_d e_d|) and r = |z|^2 + max|e|^2 + 2a (bounds every intermediate magnitude):
+// bound of sum |z_d e_d|), r = |z|^2 + max|e|^2 + 2a (bounds every intermediate of the ORACLE's formula, which carries
+// |z|^2) and r' = max|e|^2 + 2a (bounds the approximate scores and the thresholds, which do not):
 //   fp16 rounding of both operands (unit roundoff 2^-11, + subnormal slack)   2 (2^-10 + 2^-22 + 2^-35) a
 //   tensor-core fp32 accumulation over D = 256 products                       <= 2^-13 a (budget, checked on HW)
 //   oracle's own fp32 dot                                                     2 D 2^-24 a = 2^-15 a
-//   fp32 roundings of the two formulas and of the threshold add               <= 2^-22 r
-//   => eps <= (2^-9 + 2^-12) a + 2^-22 r
+//   the oracle's two roundings, fl(|z|^2 + |e|^2) and the subtraction         <= 2 * 2^-24 r  = 2^-23 r
+//   the score's fma rounding and the rounding of the threshold add            <= 2 * 2^-24 r' = 2^-23 r'
+//   => eps <= (2^-9 + 2^-12) a + 2^-23 (r + r')
+// (Round 1 charged all four roundings at magnitude r: 2^-22 r.  On the reference's init distribution -- |e| ~ 1e-3 |z|, so
+// r' << r and the r term is the largest -- that doubled eps and with it the rows that need the exact re-rank: the term that
+// remains, 2^-23 r = one ulp of |z|^2, is the oracle's own quantisation and cannot shrink.)
 // The oracle's argmin k* then satisfies score[k*] <= min_k score + 2 eps.  See DESIGN.md "candidate margin".
 __device__ __forceinline__ float candidate_margin(float z2, float e2max) {
     const float a = sqrtf(z2) * sqrtf(e2max) * 1.000001f;
-    const float r = z2 + e2max + 2.0f * a;
-    const float eps = a * (0.001953125f + 0.000244140625f) + r * 2.384185791015625e-07f;
+    const float rp = e2max + 2.0f * a;
+    const float r = z2 + rp;
+    const float eps = a * (0.001953125f + 0.000244140625f) + (r + rp) * 1.1920928955078125e-07f;
     return 2.0f * eps * 1.0625f + 1e-37f;
 }
 

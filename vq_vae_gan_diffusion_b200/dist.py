@@ -160,6 +160,14 @@ class DataParallelVQ(torch.nn.Module):
     def _fill_stats(self, flat, K, D):
         hist, loss = self._local
         tail = flat[K * D:]
+        if flat.is_cuda and hist.dtype == torch.int64 and hist.is_contiguous() and loss.dtype == torch.float32:
+            # one launch (vq_pack_stats) instead of eight small tensor kernels between the forward and the backward
+            from . import _native
+            from .codebook import _on_device, _stream_ptr
+            with _on_device(flat.device):
+                rc = _native.lib().vq_pack_stats(hist.data_ptr(), loss.data_ptr(), K, tail.data_ptr(), _stream_ptr(flat.device))
+            _native.check(rc, "vq_pack_stats")
+            return
         pack_hist(hist, tail)
         tail[2 * K:2 * K + 1].copy_(loss.reshape(1))
         tail[2 * K + 1:].fill_(1.0)
