@@ -127,6 +127,7 @@ class _VQFunction(torch.autograd.Function):
         ctx.scat = scat
         ctx.scat_ready = module.scatter_ready if scat is not None else None
         ctx.mark_non_differentiable(idx)
+        ctx.set_materialize_grads(False)      # no zeros_like(idx) / zeros for unused outputs: backward handles None
         # NHWC memory exposed as NCHW: strides (H*W*D, 1, W*D, D), exactly what codebook.py:109 returns
         return zq.permute(0, 3, 1, 2), idx, loss
 
@@ -316,6 +317,7 @@ class _VQGraphFunction(torch.autograd.Function):
         object.__setattr__(module, "last_stats", st.stats)
         ctx.state, ctx.generation, ctx.module = st, gen, module
         ctx.mark_non_differentiable(idx)
+        ctx.set_materialize_grads(False)
         return zq.permute(0, 3, 1, 2), idx, loss
 
     @staticmethod

@@ -529,7 +529,7 @@ static int forward_impl(bool training, bool rows, int recipe, const float* z, in
     sp.idx = idx; sp.idx_bits = idx_bits; sp.recipe = recipe; sp.zq = zq;
     sp.scat = training ? code_diff_sum : nullptr;
     sp.hist = reinterpret_cast<unsigned long long*>(hist);
-    sp.loss_partial = w.loss_partial; sp.blocks_done = w.blocks_done; sp.loss = loss;
+    sp.loss_partial = w.loss_partial;
     sp.stats = stats;
     const unsigned grid = (unsigned)((N + vq::kSelRows - 1) / vq::kSelRows);
     const int layout = pick_layout(z, HW, rows);
@@ -542,6 +542,10 @@ static int forward_impl(bool training, bool rows, int recipe, const float* z, in
         else                               VQ_CUDA(launch_chained(vq::vq_select_kernel<false, vq::kLayoutGeneric>, grid, vq::kSelThreads, st, sp));
     }
     VQ_LAUNCH_CHECK("vq_select_kernel");
+    if (training) {
+        VQ_CUDA(launch_chained(vq::vq_loss_finalize_kernel, 1u, vq::kSelThreads, st, (const double*)w.loss_partial, grid, N, beta, loss));
+        VQ_LAUNCH_CHECK("vq_loss_finalize_kernel");
+    }
     return VQ_OK;
 }
 

@@ -416,6 +416,10 @@ vq_argmin_gemm_kernel(const GemmParams p) {
                                           (sc[4 * q + 2] <= thr ? 4u : 0u) | (sc[4 * q + 3] <= thr ? 8u : 0u)) << (4 * q);
                             }
                         }
+                        // (Reusing the slot of an entry that has gone stale -- chunk minimum above the current threshold -- instead
+                        // of overwriting the oldest one takes the overflowed rows of cfg4 / init from 2 to 0, bit-exact, and was
+                        // dropped: the eight extra shared-memory reads on this path slow the kernel by 2.5 %, +35 us against the
+                        // 20 us the scan of two rows costs -- profiles/r2_ab_ring_reuse.jsonl.)
                         if (cnt >= kRingCap) lost_min = fminf(lost_min, lds_f32(ring_s_sa + slot_off));
                         sts_u32(ring_q_sa + slot_off, (uint32_t)(kt * (kCodeTile / kChunk) + grp * (kGroupCols / kChunk) + c));
                         sts_u32(ring_m_sa + slot_off, cmask);

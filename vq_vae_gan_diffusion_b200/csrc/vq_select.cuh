@@ -56,9 +56,7 @@ struct SelectParams {
     float* zq;                 // (N, D) or null (tokeniser mode; or a forward whose z_q nobody reads)
     float* scat;               // (K, D) or null: per-code sums of (e - z) for the codebook gradient (zeroed before launch)
     unsigned long long* hist;  // (K) or null
-    double* loss_partial;      // (gridDim.x)
-    unsigned int* blocks_done; // (1) zero-initialised, re-armed by the kernel
-    float* loss;               // (1)
+    double* loss_partial;      // (gridDim.x) per-CTA sums of (e - z)^2, finished by vq_loss_finalize_kernel
     unsigned long long* stats; // (VQ_STAT_COUNT) or null
 };
 
@@ -136,7 +134,6 @@ vq_select_kernel(const SelectParams p) {
     __shared__ int idx_s[kSelRows];
     __shared__ double red_s[kSelWarps];
     __shared__ unsigned int st_s[4];                          // per-CTA counters (same-address global atomics are slow)
-    __shared__ bool is_last;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int64_t n0 = (int64_t)blockIdx.x * kSelRows;
@@ -270,6 +267,8 @@ vq_select_kernel(const SelectParams p) {
             const float dot = combine4(pj);                    // (p0 + p1) + (p2 + p3) on all four lanes
             const bool lead = (k >= 0) && (j == 0);
             uint32_t u = 0xffffffffu;
+            // (requesting the two norms BEFORE the fma chains, to take one dependent round trip out of the pass, was measured:
+            // +180 us on cfg4 -- profiles/r2_ab_select_tail.jsonl)
             if (lead) u = dist_key(p.recipe == kRecipeDiffSq ? dot : ref_distance(__ldg(p.z2 + n0 + r), __ldg(p.e2 + k), dot));
 #pragma unroll
             for (int r2 = 0; r2 < 4; r2++) {
@@ -355,7 +354,9 @@ vq_select_kernel(const SelectParams p) {
             if (p.hist != nullptr && lane == 0) atomicAdd(p.hist + kk[rr], 1ull);
         }
     }
-    // loss: fp32 per thread (<= 32 terms), fp64 from there on; fixed-order final sum by the last CTA
+    // loss: fp32 per thread (<= 32 terms), fp64 from there on; the per-CTA partial goes to global memory and
+    // vq_loss_finalize_kernel (next in the chain) adds the partials in a fixed order.  (Until round 2 the last CTA to arrive did
+    // that, which put a fence + an atomic round trip at the end of EVERY CTA's latency chain.)
     double v = (double)sq;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -366,26 +367,27 @@ vq_select_kernel(const SelectParams p) {
         double sum = 0.0;
         for (int w = 0; w < kSelWarps; w++) sum += red_s[w];
         p.loss_partial[blockIdx.x] = sum;
-        __threadfence();
-        is_last = (atomicAdd(p.blocks_done, 1u) == gridDim.x - 1);
     }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        double sum = 0.0;
-        for (unsigned i = tid; i < gridDim.x; i += kSelThreads) sum += __ldcg(p.loss_partial + i);
+}
+
+// loss = mean((e - z)^2) * (1 + beta) (codebook.py:96-103: mean(a + beta * mean(b)) with a == b elementwise) from the per-CTA
+// partial sums of vq_select_kernel, added in a fixed order (run-to-run reproducible): one CTA, chained behind the select kernel.
+__global__ void __launch_bounds__(kSelThreads)
+vq_loss_finalize_kernel(const double* __restrict__ loss_partial, unsigned n_parts, int64_t N, float beta, float* __restrict__ loss) {
+    __shared__ double red_s[kSelWarps];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_wait();                                               // the select kernel has completed: every partial is visible
+    double sum = 0.0;
+    for (unsigned i = tid; i < n_parts; i += kSelThreads) sum += __ldcg(loss_partial + i);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        __syncthreads();
-        if (lane == 0) red_s[warp] = sum;
-        __syncthreads();
-        if (tid == 0) {
-            double tot = 0.0;
-            for (int w = 0; w < kSelWarps; w++) tot += red_s[w];
-            const double m = tot / ((double)p.N * (double)kD);
-            *p.loss = (float)(m + (double)p.beta * m);       // mean(a + beta*mean(b)), a == b elementwise
-            *p.blocks_done = 0;                              // re-arm for the next call on this workspace
-        }
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) red_s[warp] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < kSelWarps; w++) tot += red_s[w];
+        const double m = tot / ((double)N * (double)kD);
+        *loss = (float)(m + (double)beta * m);
     }
 }
 
