@@ -321,9 +321,10 @@ def main():
     ap.add_argument("--cuda-graphs", action="store_true",
                     help="drive the module through its CUDA-graph fast path (CodeBook.use_cuda_graphs; for the small, "
                          "launch-bound workloads cfg1 / cfg2)")
-    ap.add_argument("--collective", default="nccl", choices=["nccl", "multimem"],
+    ap.add_argument("--collective", default="auto", choices=["auto", "nccl", "multimem"],
                     help="N > 1: the all-reduce of the codebook gradient through NCCL, or through the library's own NVLS kernel "
-                         "(multimem.ld_reduce / multimem.st on a symmetric buffer, csrc/vq_allreduce.cuh)")
+                         "(multimem.ld_reduce / multimem.st on a symmetric buffer, csrc/vq_allreduce.cuh); auto = the NVLS kernel "
+                         "when every rank can set it up (NVSwitch multicast), else NCCL")
     ap.add_argument("--soak-seconds", type=float, default=2.0,
                     help="after the timed region, keep stepping for about this long and report the distance-GEMM kernel's "
                          "fraction of peak once clocks have settled under the power cap (roofline.frac_sustained_run); 0 = off")
@@ -564,7 +565,7 @@ def main():
                    "distribution": args.distribution, "l2": "inputs (2 x 268 MB per GPU) larger than the 126 MB L2"
                    if N * D * 4 > 130e6 else "inputs smaller than L2, no flush (launch-latency-bound workload)",
                    "parallelism": f"dp{world} (batch-sharded latents, replicated codebook, grad_E all-reduce)",
-                   "cuda_graphs": bool(args.cuda_graphs), "collective": args.collective if world > 1 else None},
+                   "cuda_graphs": bool(args.cuda_graphs), "collective": dp.collective if dp is not None else None},
         "clocks": clocks, "e2e": e2e, "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
         "roofline": roofline, "cpu_baseline": cpu_baseline, "select_stats_last_step": stats,
     }

@@ -195,12 +195,14 @@ int vq_forward_ex(const float* z_nchw, int64_t B, int64_t HW, int D,
  *   multicast_ptr     multicast address of the buffer (torch.distributed._symmetric_memory handle.multicast_ptr); the caller's
  *                     prior work on `stream` must have produced this rank's contribution in its own copy of the buffer
  *   signal_pads_dev   DEVICE array of `world` pointers to the ranks' signal pads (handle.signal_pad_ptrs_dev), zero when idle;
- *                     needs min(128, 2304 / world) * world words of each pad (torch's default pad is 2304 words)
+ *                     uses the first `world` words of each pad
  *   n_floats          multiple of 4 * world
- * The two device-side barriers spin with a bound (a rank that never arrives traps instead of hanging the box).
+ *   local_sync        two 32-bit words of this rank's own device memory, zero before the first call (the kernel re-arms them):
+ *                     only one CTA per rank synchronises with the other GPUs, the rest of the grid through these words
+ * The device-side waits spin with a bound (a rank that never arrives traps instead of hanging the box).
  */
 int vq_allreduce_multimem(void* multicast_ptr, void* const* signal_pads_dev, int rank, int world, int64_t n_floats,
-                          vq_stream_t stream);
+                          unsigned int* local_sync, vq_stream_t stream);
 
 /*
  * Tail of the data-parallel exchange buffer (dist.py) in one launch:

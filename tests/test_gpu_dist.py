@@ -58,7 +58,8 @@ def run_checks(rank, world, dev, K=4096, Bl=4, H=32, W=32, deterministic=False, 
     dp = DataParallelVQ(cb, overlap=overlap, collective=collective)
     zl = z[sl].clone().requires_grad_(True)
     z_q, idx, loss = dp(zl)
-    assert dp._step_overlapped == (overlap and not deterministic and world > 1 and collective == "nccl")
+    assert dp.collective in ("nccl", "multimem")
+    assert dp._step_overlapped == (overlap and not deterministic and world > 1 and dp.collective == "nccl")
     torch.autograd.backward([z_q, loss], [gout[sl], one])
     dp.wait()
 
@@ -123,6 +124,8 @@ def _worker(rank, world, backend, init_file, out_file):
             # the library's own NVLS all-reduce (csrc/vq_allreduce.cuh) instead of NCCL's, two steps on the persistent buffer
             results.append(run_checks(rank, world, dev, K=4096, Bl=2, overlap=False, collective="multimem"))
             results.append(run_checks(rank, world, dev, K=1000, Bl=2, overlap=False, collective="multimem"))
+            # "auto" settles on the NVLS kernel where the box has multicast, on NCCL elsewhere -- the same on every rank
+            results.append(run_checks(rank, world, dev, K=2048, Bl=2, overlap=False, collective="auto"))
         gathered = [None] * world
         dist.all_gather_object(gathered, tuple(results))
         if rank == 0:

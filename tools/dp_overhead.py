@@ -101,11 +101,16 @@ def main():
 
         def ar():
             rc = _native.lib().vq_allreduce_multimem(int(hdl.multicast_ptr), int(hdl.signal_pad_ptrs_dev), int(hdl.rank),
-                                                     int(hdl.world_size), n_pad, int(st))
+                                                     int(hdl.world_size), n_pad, dpm._symm_sync.data_ptr(), int(st))
             _native.check(rc, "vq_allreduce_multimem")
 
         buf.zero_()
         out["ar_multimem_ms"] = timed(ar, 50)
+        for nb in (8, 16, 64, 128):
+            os.environ["VQ_AR_MAX_BLOCKS"] = str(nb)
+            buf.zero_()
+            out[f"ar_multimem_{nb}blocks_ms"] = timed(ar, 50)
+        os.environ.pop("VQ_AR_MAX_BLOCKS")
         # correctness of the stand-alone kernel: every rank contributes rank + 1
         buf.fill_(float(rank + 1))
         torch.cuda.synchronize()

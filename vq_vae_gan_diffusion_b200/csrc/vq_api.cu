@@ -771,23 +771,28 @@ VQ_EXPORT int vq_backward_ex(const float* gout, const int64_t* gout_strides, flo
 }
 
 VQ_EXPORT int vq_allreduce_multimem(void* multicast_ptr, void* const* signal_pads_dev, int rank, int world, int64_t n_floats,
-                                    vq_stream_t stream) {
+                                    unsigned int* local_sync, vq_stream_t stream) {
     g_launches = 0;
-    if (!multicast_ptr || !signal_pads_dev) return fail(VQ_E_INVALID, "null pointer");
+    if (!multicast_ptr || !signal_pads_dev || !local_sync) return fail(VQ_E_INVALID, "null pointer");
     if (world < 2 || world > 32 || rank < 0 || rank >= world) return fail(VQ_E_INVALID, "bad rank %d / world %d", rank, world);
     if (n_floats <= 0 || n_floats % (4 * (int64_t)world) != 0)
         return fail(VQ_E_INVALID, "n_floats=%lld must be a positive multiple of 4 * world", (long long)n_floats);
     if ((reinterpret_cast<uintptr_t>(multicast_ptr) & 15) != 0) return fail(VQ_E_INVALID, "multicast pointer must be 16-byte aligned");
+    if ((reinterpret_cast<uintptr_t>(local_sync) & 7) != 0) return fail(VQ_E_INVALID, "local_sync must be 8-byte aligned");
     DevInfo* dev;
     int rc = device_info(&dev);
     if (rc != VQ_OK) return rc;
     const int64_t n_vec4 = n_floats / 4, slice = n_vec4 / world;
     int64_t blocks = (slice + vq::kArThreads * vq::kArUnroll - 1) / (vq::kArThreads * vq::kArUnroll);
-    const int64_t max_blocks = std::min<int64_t>(vq::kArMaxBlocks, vq::kArPadWords / world);   // barrier slots on the signal pad
+    int64_t max_blocks = std::min<int64_t>(vq::kArMaxBlocks, dev->sms);                        // the CTAs wait for each other: co-resident
+    if (const char* e = getenv("VQ_AR_MAX_BLOCKS")) {                                          // tuning runs (tools/dp_overhead.py)
+        const int64_t v = atoll(e);
+        if (v >= 1 && v <= dev->sms) max_blocks = v;
+    }
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks < 1) blocks = 1;
     vq::vq_allreduce_multimem_kernel<<<(unsigned)blocks, vq::kArThreads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-        static_cast<float*>(multicast_ptr), reinterpret_cast<uint32_t* const*>(signal_pads_dev), rank, world, n_vec4);
+        static_cast<float*>(multicast_ptr), reinterpret_cast<uint32_t* const*>(signal_pads_dev), rank, world, n_vec4, local_sync);
     VQ_LAUNCH_CHECK("vq_allreduce_multimem_kernel");
     return VQ_OK;
 }

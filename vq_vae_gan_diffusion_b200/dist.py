@@ -72,12 +72,16 @@ class DataParallelVQ(torch.nn.Module):
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         # collective = "multimem": the library's own NVLS all-reduce kernel (csrc/vq_allreduce.cuh: multimem.ld_reduce / multimem.st
         # on a symmetric buffer, the NVSwitch adds) instead of NCCL's, in-stream; "nccl" (default) = torch.distributed.all_reduce.
-        if collective not in ("nccl", "multimem"):
-            raise ValueError("collective must be 'nccl' or 'multimem'")
+        # "auto": multimem when every rank can set it up (CUDA ranks behind an NVSwitch with multicast support), else nccl.
+        if collective not in ("nccl", "multimem", "auto"):
+            raise ValueError("collective must be 'nccl', 'multimem' or 'auto'")
+        self._symm = None            # (persistent symmetric buffer, handle, padded length) of the multimem path
+        self._symm_sync = None       # local_sync words of vq_allreduce_multimem
+        if collective == "auto":
+            collective = self._probe_multimem(codebook)
         self.collective = collective
         if collective == "multimem":
             overlap = False          # the NVLS kernel runs in-stream on one persistent buffer: nothing to overlap with
-        self._symm = None            # (persistent symmetric buffer, handle, padded length) of the multimem path
         # The overlapped exchange is opt-in: accumulating the sums in the forward costs ~50-70 us per cfg4 step on the rank itself
         # (the atomics are free inside the HBM-bound backward kernel but not inside the latency-bound select kernel:
         # profiles/r2_ab_scatter_in_forward_1gpu.json), about what the hidden all-reduce of a 17 MB buffer takes on 2-8 GPUs -- in
@@ -97,6 +101,26 @@ class DataParallelVQ(torch.nn.Module):
         self._local = None           # (hist, loss) of the last forward, not yet exchanged
         self.sync_grads = True
         self._hook = codebook.codebook.weight.register_post_accumulate_grad_hook(self._on_grad_ready)
+
+    def _probe_multimem(self, codebook) -> str:
+        """collective="auto": set up the symmetric exchange buffer now (a rendezvous: every rank constructs the wrapper at the
+        same point) and agree across ranks on whether it worked; any rank's failure sends everybody to NCCL."""
+        w = codebook.codebook.weight
+        if self.world_size <= 1 or not w.is_cuda or dist.get_backend(self.group) != "nccl":
+            return "nccl"
+        self.collective = "multimem"
+        ok = 1
+        try:
+            self._symm_flat(w.shape[0], w.shape[1], w.device)
+        except Exception:                                      # noqa: BLE001 -- no symmetric memory / no multicast on this box
+            ok = 0
+            self._symm = None
+        flag = torch.tensor([ok], dtype=torch.int32, device=w.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            return "multimem"
+        self._symm = None
+        return "nccl"
 
     # ---- flat exchange buffer: [S or grad_E (K*D) | hist lo (K) | hist hi (K) | loss | 1]
     def _new_flat(self, K, D, device):
@@ -118,6 +142,7 @@ class DataParallelVQ(torch.nn.Module):
                 raise RuntimeError("collective='multimem' needs NVLS multicast support (NVSwitch); use collective='nccl'")
             buf.zero_()
             self._symm = (buf, hdl, n_pad)
+            self._symm_sync = torch.zeros(2, dtype=torch.int32, device=device)    # local_sync words of vq_allreduce_multimem
         return self._symm[0][:n]
 
     def _all_reduce(self, flat):
@@ -127,7 +152,7 @@ class DataParallelVQ(torch.nn.Module):
             buf, hdl, n_pad = self._symm
             with torch.cuda.device(buf.device):
                 rc = _native.lib().vq_allreduce_multimem(int(hdl.multicast_ptr), int(hdl.signal_pad_ptrs_dev), int(hdl.rank),
-                                                         int(hdl.world_size), n_pad,
+                                                         int(hdl.world_size), n_pad, self._symm_sync.data_ptr(),
                                                          int(torch.cuda.current_stream(buf.device).cuda_stream))
             _native.check(rc, "vq_allreduce_multimem")
             return None
