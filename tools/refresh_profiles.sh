@@ -18,7 +18,7 @@ python tools/fold_postconv_bench.py --workload cfg4 > $O/${TAG}_fold_cfg4.json 2
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --soak-seconds 0 > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --soak-seconds 0 > $O/${TAG}_ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:vq_ --launch-skip 28 --launch-count 7 -f -o $O/${TAG}_full \
+ncu --set full --clock-control none --import-source on -k regex:vq_ --launch-skip 32 --launch-count 8 -f -o $O/${TAG}_full \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --soak-seconds 0 > $O/${TAG}_ncu2.log 2>&1
 ncu -i $O/${TAG}_full.ncu-rep --page raw --csv > $O/${TAG}_full_raw.csv 2>> $O/${TAG}_ncu2.log
 tail -c 600 $O/${TAG}_bench_init.json
