@@ -102,7 +102,8 @@ def _worker(rank, world, init_file, out_file):
         # --- 1. the stand-alone wrapper, ONE async all-reduce per step: post-backward (hook) and overlapped (forward-time sums)
         gt = torch.from_numpy(np.ascontiguousarray(np.transpose(g[sl], (0, 3, 1, 2))))
         cb0 = OracleCodeBook(E)
-        dp0 = DataParallelVQ(cb0, overlap=False)
+        dp0 = DataParallelVQ(cb0, overlap=False, collective="auto")
+        assert dp0.collective == "nccl"       # "auto" only picks the NVLS kernel for CUDA ranks on the nccl backend
         z0 = torch.from_numpy(z[sl].copy()).requires_grad_(True)
         q0, _, l0 = dp0(z0)
         torch.autograd.backward([q0, l0], [gt, torch.tensor(1.0)])
