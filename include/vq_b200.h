@@ -189,6 +189,29 @@ int vq_forward_ex(const float* z_nchw, int64_t B, int64_t HW, int D,
                   unsigned long long* stats, void* workspace, size_t workspace_bytes, vq_stream_t stream);
 
 /*
+ * quant_conv folded into the quantiser (encoder side): the reference runs
+ * `quant_x = self.quant_conv(encoded_images)` -- Conv2d(256, 256, 1), network/vqvae/vqvae.py:83,128 -- right before the CodeBook.
+ *
+ * vq_prepare_quant_conv: the convolution weight W (256 output x 256 input channels, fp32 row-major = Conv2d.weight) ->
+ *   w_img      256 KiB, 16-byte aligned: hi / lo fp16 operand images of W (split precision, see csrc/vq_qconv.cuh)
+ *   w_scalars  4 floats ([0] = inverse operand scale)
+ * Re-run after every change of W.
+ *
+ * vq_forward_qconv: vq_forward on z = W h + bias, the convolution computed with fp32 accuracy on the tensor cores inside the
+ * operand-preparation kernel (no separate convolution pass, no re-read of z):
+ *   h_nchw   (B, 256, HW) fp32 in, 16-byte aligned, HW % 128 == 0 (else VQ_E_UNSUPPORTED: run the convolution separately)
+ *   bias     (256) fp32 or NULL
+ *   z_nchw   (B, 256, HW) fp32 OUT: the convolution's output, |z - conv_fp32(h)| <= 1e-5 max|z|; everything else is computed
+ *            from exactly these values as vq_forward would (indices / z_q / histogram bit-exact given z_nchw)
+ * All other arguments as vq_forward.
+ */
+int vq_prepare_quant_conv(const float* W, void* w_img, float* w_scalars, vq_stream_t stream);
+int vq_forward_qconv(const float* h_nchw, int64_t B, int64_t HW, int D, const void* w_img, const float* w_scalars,
+                     const float* bias, float* z_nchw, const float* E, const void* E_h, const float* e_norm2,
+                     const float* cb_scalars, int K, float beta, float* zq_nhwc, int64_t* idx, float* loss, int64_t* hist,
+                     unsigned long long* stats, void* workspace, size_t workspace_bytes, vq_stream_t stream);
+
+/*
  * SUM all-reduce, in place, of a symmetric fp32 buffer over NVLink with the NVSwitch doing the additions (NVLS: multimem.ld_reduce /
  * multimem.st on the buffer's multicast address) -- the data-parallel exchange of the codebook gradient / usage histogram (dist.py;
  * new in this build, the reference is single-device).  One process per GPU; every rank calls it with the same n_floats.

@@ -258,6 +258,19 @@ def torch_cpu_step(z, E, g_out=None, beta: float = 0.25, indices_only: bool = Fa
 # (tests/golden/make_golden_tokens.py runs the reference's own functions / lines).
 # ----------------------------------------------------------------------------------------------
 
+def quant_conv_fp32(h: np.ndarray, W: np.ndarray, b=None) -> np.ndarray:
+    """The reference's ``quant_conv`` -- ``nn.Conv2d(C, C, 1)``, /root/reference/network/vqvae/vqvae.py:83, applied at
+    vqvae.py:128 -- in fp32 on the CPU: ``z[n, :, hw] = W h[n, :, hw] + bias`` (one sgemm per image, BLAS accumulation order;
+    a 1 x 1 convolution IS that matrix product).  h (B, Ci, H, W) fp32, W (Co, Ci) or (Co, Ci, 1, 1) fp32, b (Co) or None."""
+    h = np.ascontiguousarray(h, np.float32)
+    W2 = np.ascontiguousarray(np.asarray(W, np.float32).reshape(W.shape[0], W.shape[1]))
+    B, Ci, H, Wd = h.shape
+    z = np.matmul(W2[None], h.reshape(B, Ci, H * Wd))                         # (B, Co, HW) fp32
+    if b is not None:
+        z = z + np.asarray(b, np.float32)[None, :, None]
+    return z.reshape(B, W2.shape[0], H, Wd).astype(np.float32, copy=False)
+
+
 def index_to_log_onehot_np(x: np.ndarray, num_classes: int) -> np.ndarray:
     """network/vq_diffusion/vq_diffusion.py:29-35 (== diffusion_vq_official.py:53-60): x (B, ...) int64 ->
     log(clamp(one_hot(x), min=1e-30)) as (B, num_classes, ...) fp32, the class axis moved to position 1."""

@@ -99,6 +99,8 @@ _SIGNATURES = {
     "vq_backward_ex": (_int, [_vp, ctypes.POINTER(_i64), _f32, _vp, _vp, _vp, _vp, _i64, _i64, _int, _int, _f32, _i64, _f32, _int,
                               _vp, _vp, _vp, _vp, _sz, _vp]),
     "vq_forward_ex": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "vq_prepare_quant_conv": (_int, [_vp, _vp, _vp, _vp]),
+    "vq_forward_qconv": (_int, [_vp, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "vq_allreduce_multimem": (_int, [_vp, _vp, _int, _int, _i64, _vp, _vp]),
     "vq_pack_stats": (_int, [_vp, _vp, _int, _vp, _vp]),
     "vq_embed_nchw": (_int, [_vp, _vp, _i64, _i64, _int, _int, _vp, _vp]),

@@ -19,6 +19,7 @@
 #include "vq_backward.cuh"
 #include "vq_common.cuh"
 #include "vq_prep.cuh"
+#include "vq_qconv.cuh"
 #include "vq_select.cuh"
 #include "vq_rows.cuh"
 #include "vq_tokens.cuh"
@@ -172,6 +173,8 @@ int device_info(DevInfo** out) {
             {(const void*)vq::vq_argmin_gemm_kernel<false, false, true, 8>, vq::gemm_smem_bytes<8>()}};
         for (const auto& v : rows_variants)
             VQ_CUDA(cudaFuncSetAttribute(v.first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.second));
+        VQ_CUDA(cudaFuncSetAttribute((const void*)vq::vq_qconv_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)vq::kQcSmemBytes));
         d.attrs_set = true;
     }
     *out = &d;
@@ -245,8 +248,18 @@ int pick_layout(const float* z, int64_t HW, bool rows) {
     return (HW % vq::kSelRows == 0 && aligned) ? vq::kLayoutVec : vq::kLayoutGeneric;
 }
 
+// The folded quant_conv (vq_qconv.cuh): when given, the operand preparation starts from the convolution's INPUT h and also
+// produces the latents z that every later kernel of the call reads.
+struct QconvArgs {
+    const float* h;
+    const void* w_img;
+    const float* w_scalars;
+    const float* bias;
+};
+
 int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, int recipe, const void* E_h, const float* e2, const float* cb, int K,
-             const Workspace& w, float* dbg_scores, int64_t* hist, unsigned long long* stats, cudaStream_t st) {
+             const Workspace& w, float* dbg_scores, int64_t* hist, unsigned long long* stats, cudaStream_t st,
+             const QconvArgs* qc = nullptr) {
     DevInfo* dev;
     int rc = device_info(&dev);
     if (rc != VQ_OK) return rc;
@@ -261,6 +274,17 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, int recipe, const
     clr.K = K;
     clr.stats = stats;
     clr.n_stats = VQ_STAT_COUNT;
+    if (qc != nullptr) {
+        vq::QconvParams qp;
+        qp.h = qc->h; qp.N = N; qp.HW = HW; qp.n_pad = n_pad;
+        qp.w_img = static_cast<const __half*>(qc->w_img); qp.w_scalars = qc->w_scalars; qp.bias = qc->bias;
+        qp.z = const_cast<float*>(z); qp.z_h = w.z_h; qp.z2 = w.z2; qp.z_inv_scale = w.z_inv_scale;
+        qp.row_tiles = (int)(N / vq::kRowTile);
+        qp.clr = clr;
+        const unsigned qgrid = (unsigned)(qp.row_tiles < dev->sms ? qp.row_tiles : dev->sms);
+        vq::vq_qconv_prep_kernel<<<qgrid, vq::kQcThreads, vq::kQcSmemBytes, st>>>(qp);
+        VQ_LAUNCH_CHECK("vq_qconv_prep_kernel");
+    } else {
     switch (pick_layout(z, HW, rows)) {
         case vq::kLayoutRows:
             vq::vq_prep_z_kernel<vq::kLayoutRows><<<pgrid, vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2, w.z_inv_scale, clr);
@@ -272,6 +296,7 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, int recipe, const
             vq::vq_prep_z_kernel<vq::kLayoutGeneric><<<pgrid, vq::kPrepThreads, 0, st>>>(z, N, HW, n_pad, w.z_h, w.z2, w.z_inv_scale, clr);
     }
     VQ_LAUNCH_CHECK("vq_prep_z_kernel");
+    }
 
     vq::GemmParams gp;
     gp.z_h = w.z_h;
@@ -469,7 +494,7 @@ VQ_EXPORT int vq_prepare_codebook(const float* E, int K, int D, void* E_h, float
 static int forward_impl(bool training, bool rows, int recipe, const float* z, int64_t B, int64_t HW, int D, const float* E, const void* E_h,
                         const float* e2, const float* cb, int K, float beta, float* zq, void* idx, int idx_bits, float* loss,
                         int64_t* hist, unsigned long long* stats, void* ws, size_t ws_bytes, vq_stream_t stream,
-                        float* code_diff_sum = nullptr) {
+                        float* code_diff_sum = nullptr, const QconvArgs* qc = nullptr) {
     g_launches = 0;
     int rc = check_common(z, B, HW, D, K);
     if (rc != VQ_OK) return rc;
@@ -502,7 +527,7 @@ static int forward_impl(bool training, bool rows, int recipe, const float* z, in
     if (idx_bits != 64 && idx_bits != 32 && idx_bits != 16) return fail(VQ_E_INVALID, "idx_bits must be 16, 32 or 64, got %d", idx_bits);
     if (idx_bits == 16 && K > 65536) return fail(VQ_E_INVALID, "16-bit indices need K <= 65536, got K=%d", K);
     if (recipe != vq::kRecipeExpanded && recipe != vq::kRecipeDiffSq) return fail(VQ_E_INVALID, "unknown distance recipe %d", recipe);
-    rc = run_gemm(z, N, HW, rows, recipe, E_h, e2, cb, K, w, nullptr, training ? hist : nullptr, stats, st);
+    rc = run_gemm(z, N, HW, rows, recipe, E_h, e2, cb, K, w, nullptr, training ? hist : nullptr, stats, st, qc);
     if (rc != VQ_OK) return rc;
 
     {   // rows whose candidate list overflowed (rare) or that hold Inf / NaN: exact scan; a no-op when the worklist is empty
@@ -635,6 +660,36 @@ VQ_EXPORT int vq_forward_ex(const float* z_nchw, int64_t B, int64_t HW, int D, c
                             size_t workspace_bytes, vq_stream_t stream) {
     return forward_impl(true, false, VQ_RECIPE_EXPANDED, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, beta, zq_nhwc, idx, 64, loss, hist,
                         stats, workspace, workspace_bytes, stream, code_diff_sum);
+}
+
+VQ_EXPORT int vq_prepare_quant_conv(const float* W, void* w_img, float* w_scalars, vq_stream_t stream) {
+    g_launches = 0;
+    if (!W || !w_img || !w_scalars) return fail(VQ_E_INVALID, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(w_img) & 15) != 0) return fail(VQ_E_INVALID, "w_img must be 16-byte aligned");
+    DevInfo* dev;
+    int rc = device_info(&dev);
+    if (rc != VQ_OK) return rc;
+    vq::vq_qconv_weight_kernel<<<1, 1024, 0, reinterpret_cast<cudaStream_t>(stream)>>>(W, static_cast<__half*>(w_img), w_scalars);
+    VQ_LAUNCH_CHECK("vq_qconv_weight_kernel");
+    return VQ_OK;
+}
+
+VQ_EXPORT int vq_forward_qconv(const float* h_nchw, int64_t B, int64_t HW, int D, const void* w_img, const float* w_scalars,
+                               const float* bias, float* z_nchw, const float* E, const void* E_h, const float* e_norm2,
+                               const float* cb_scalars, int K, float beta, float* zq_nhwc, int64_t* idx, float* loss, int64_t* hist,
+                               unsigned long long* stats, void* workspace, size_t workspace_bytes, vq_stream_t stream) {
+    if (D != vq::kD) return fail(VQ_E_UNSUPPORTED, "latent_dim D=%d is not supported (the folded quant_conv is 256 -> 256)", D);
+    if (B < 1 || HW < 1) return fail(VQ_E_INVALID, "bad shape B=%lld HW=%lld", (long long)B, (long long)HW);
+    if (HW % vq::kRowTile != 0)
+        return fail(VQ_E_UNSUPPORTED, "HW=%lld: the folded quant_conv needs HW %% 128 == 0 (a row tile is 128 positions of one image)",
+                    (long long)HW);
+    if (!h_nchw || !w_img || !w_scalars || !z_nchw) return fail(VQ_E_INVALID, "null pointer");
+    if ((reinterpret_cast<uintptr_t>(h_nchw) & 15) != 0 || (reinterpret_cast<uintptr_t>(z_nchw) & 15) != 0 ||
+        (reinterpret_cast<uintptr_t>(w_img) & 15) != 0)
+        return fail(VQ_E_INVALID, "h, z and w_img must be 16-byte aligned");
+    QconvArgs qc{h_nchw, w_img, w_scalars, bias};
+    return forward_impl(true, false, VQ_RECIPE_EXPANDED, z_nchw, B, HW, D, E, E_h, e_norm2, cb_scalars, K, beta, zq_nhwc, idx, 64, loss, hist,
+                        stats, workspace, workspace_bytes, stream, nullptr, &qc);
 }
 
 VQ_EXPORT int vq_debug_scores(const float* z_nchw, int64_t B, int64_t HW, int D, const void* E_h, const float* e_norm2,
