@@ -173,7 +173,9 @@ int device_info(DevInfo** out) {
             {(const void*)vq::vq_argmin_gemm_kernel<false, false, true, 8>, vq::gemm_smem_bytes<8>()}};
         for (const auto& v : rows_variants)
             VQ_CUDA(cudaFuncSetAttribute(v.first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v.second));
-        VQ_CUDA(cudaFuncSetAttribute((const void*)vq::vq_qconv_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VQ_CUDA(cudaFuncSetAttribute((const void*)vq::vq_qconv_prep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)vq::kQcSmemBytes));
+        VQ_CUDA(cudaFuncSetAttribute((const void*)vq::vq_qconv_prep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)vq::kQcSmemBytes));
         d.attrs_set = true;
     }
@@ -248,6 +250,30 @@ int pick_layout(const float* z, int64_t HW, bool rows) {
     return (HW % vq::kSelRows == 0 && aligned) ? vq::kLayoutVec : vq::kLayoutGeneric;
 }
 
+// 2-D tensor map of the NCHW activations for vq_qconv_prep_kernel: [B * 256 channel planes][HW] fp32, box 64 planes x 128
+// positions.  The encoder is a driver entry point fetched through the runtime (the library links no libcuda); false when this
+// driver has none -- the kernel then falls back to one bulk copy per channel plane.
+bool encode_h_tensor_map(const float* h, int64_t B, int64_t HW, CUtensorMap* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        (void)cudaGetLastError();
+        return reinterpret_cast<EncodeFn>(p);
+    }();
+    if (fn == nullptr || getenv("VQ_QCONV_NO_TENSORMAP") != nullptr) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)HW, (cuuint64_t)(B * vq::kD)};
+    const cuuint64_t strides[1] = {(cuuint64_t)HW * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)vq::kRowTile, (cuuint32_t)vq::kQcStageCh};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(h), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // The folded quant_conv (vq_qconv.cuh): when given, the operand preparation starts from the convolution's INPUT h and also
 // produces the latents z that every later kernel of the call reads.
 struct QconvArgs {
@@ -282,7 +308,10 @@ int run_gemm(const float* z, int64_t N, int64_t HW, bool rows, int recipe, const
         qp.row_tiles = (int)(N / vq::kRowTile);
         qp.clr = clr;
         const unsigned qgrid = (unsigned)(qp.row_tiles < dev->sms ? qp.row_tiles : dev->sms);
-        vq::vq_qconv_prep_kernel<<<qgrid, vq::kQcThreads, vq::kQcSmemBytes, st>>>(qp);
+        CUtensorMap tmap;
+        memset(&tmap, 0, sizeof(tmap));
+        if (encode_h_tensor_map(qc->h, N / HW, HW, &tmap)) vq::vq_qconv_prep_kernel<true><<<qgrid, vq::kQcThreads, vq::kQcSmemBytes, st>>>(qp, tmap);
+        else                                               vq::vq_qconv_prep_kernel<false><<<qgrid, vq::kQcThreads, vq::kQcSmemBytes, st>>>(qp, tmap);
         VQ_LAUNCH_CHECK("vq_qconv_prep_kernel");
     } else {
     switch (pick_layout(z, HW, rows)) {

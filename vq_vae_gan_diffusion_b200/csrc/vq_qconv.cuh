@@ -15,9 +15,10 @@
 //
 // One CTA per SM, persistent over row tiles of 128 latents (128 consecutive hw positions of one image: HW % 128 == 0),
 // twelve warps:
-//   warp 0      h producer: the tile's fp32 source, 64 channels x 128 latents (32 KiB) at a time through a two-slot ring of
-//               bulk copies (one 512-byte row per channel) -- TWICE per tile: the first pass finds every row's maximum
-//               (DRAM), the second (L2 hits) is converted
+//   warp 0      h producer: the tile's fp32 source, 64 channels x 128 latents (32 KiB) at a time through a two-slot ring, ONE
+//               2-D tensor-map copy per stage (sixty-four 512-byte bulk copies per stage, one per channel plane, kept the TMA
+//               unit busy for ~2 us a stage: 268 us for the cfg4 call against 156 us with the tensor map) -- TWICE per tile: the
+//               first pass finds every row's maximum (DRAM), the second (L2 hits) is converted
 //   warp 1      W producer: the weight's operand images [hi | lo][4 chunks of 64 input channels][256 x 64 fp16] (256 KiB in
 //               L2) through a two-stage ring, 32 KiB per stage
 //   warp 2      MMA issuer (tcgen05.mma M128 N256 K16, kind::f16): per chunk hi_h hi_W, lo_h hi_W, hi_h lo_W; owns TMEM
@@ -29,11 +30,21 @@
 //               epilogue of tile i overlaps the loads / conversions / MMAs of tile i + 1.
 #pragma once
 
+#include <cuda.h>            // CUtensorMap (type only: the encoder is fetched through cudaGetDriverEntryPoint, no libcuda link)
+
 #include "ptx_sm100.cuh"
 #include "vq_common.cuh"
 #include "vq_prep.cuh"
 
 namespace vq {
+
+// 2-D tiled tensor-map load global -> shared, completion on an mbarrier: one instruction moves a [box rows x box columns] tile
+// of a strided tensor (here: 64 channel planes x 128 consecutive positions of the NCHW activations).
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int32_t x, int32_t y, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
 
 constexpr int kQcThreads = 384;
 constexpr int kQcWarpH = 0, kQcWarpW = 1, kQcWarpMma = 2;      // (warp 3 idles: the converter / epilogue groups stay 4-aligned)
@@ -113,8 +124,11 @@ vq_qconv_weight_kernel(const float* __restrict__ W, __half* __restrict__ w_img, 
     }
 }
 
+// kTensorMap: the activations arrive through `tmap` (2-D view [B * 256 channel planes][HW], box 64 x 128); otherwise -- no
+// tensor-map encoder in the driver -- through one bulk copy per channel plane.
+template <bool kTensorMap>
 __global__ void __launch_bounds__(kQcThreads, 1)
-vq_qconv_prep_kernel(const QconvParams p) {
+vq_qconv_prep_kernel(const QconvParams p, const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ uint8_t smem_raw[];
     QcSmem& s = *reinterpret_cast<QcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -171,12 +185,17 @@ vq_qconv_prep_kernel(const QconvParams p) {
                     mbar_wait(&s.hs_empty[slot], ph ^ 1);
                     if (lane == 0) mbar_expect_tx(&s.hs_full[slot], kQcBytesHs);
                     __syncwarp();
+                    if (kTensorMap) {
+                        if (lane == 0)
+                            tma_load_2d(&s.hs[slot][0][0], &tmap, (int32_t)hw0, (int32_t)(b * kD + kQcStageCh * dc), &s.hs_full[slot]);
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < kQcStageCh / 32; q++) {
-                        const int ch = lane + 32 * q;
-                        const float* src = src0 + (int64_t)(kQcStageCh * dc + ch) * p.HW;
-                        if (pass == 0) bulk_load_1d(&s.hs[slot][ch][0], src, kRowTile * 4, &s.hs_full[slot]);
-                        else bulk_load_1d_hint(&s.hs[slot][ch][0], src, kRowTile * 4, &s.hs_full[slot], pol_stream);
+                        for (int q = 0; q < kQcStageCh / 32; q++) {
+                            const int ch = lane + 32 * q;
+                            const float* src = src0 + (int64_t)(kQcStageCh * dc + ch) * p.HW;
+                            if (pass == 0) bulk_load_1d(&s.hs[slot][ch][0], src, kRowTile * 4, &s.hs_full[slot]);
+                            else bulk_load_1d_hint(&s.hs[slot][ch][0], src, kRowTile * 4, &s.hs_full[slot], pol_stream);
+                        }
                     }
                     __syncwarp();
                 }
