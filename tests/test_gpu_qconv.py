@@ -151,3 +151,61 @@ def test_folded_quant_conv_other_shapes_run_the_composition(vq, oracle):
     rc = L.vq_forward_qconv(h.data_ptr(), 2, 35, D, h.data_ptr(), h.data_ptr(), 0, h.data_ptr(), h.data_ptr(), h.data_ptr(), h.data_ptr(),
                             h.data_ptr(), K, 0.25, 0, h.data_ptr(), h.data_ptr(), 0, 0, h.data_ptr(), 1 << 20, 0)
     assert rc != 0 and b"HW" in L.vq_last_error()
+
+
+@pytest.mark.parametrize("B,H,W,K,dist", [(3, 16, 32, 1024, "trained"), (2, 32, 32, 512, "init")])
+def test_folded_vq_both_convolutions(B, H, W, K, dist, vq, oracle):
+    """FoldedVQ(quant_conv, codebook, post_quant_conv)(h) against the reference composition post_quant_conv(codebook(quant_conv(h))[0])
+    (vqvae.py:128-133): same indices / loss as FoldedQuantConv, output and all six gradients within 1e-5 of a float64 evaluation."""
+    dev = torch.device("cuda:0")
+    D = 256
+    h_np, Wq, bq, E_np, g_np = make_case(B, H, W, K, dist, 77 + K)
+    rng = np.random.default_rng(5)
+    Wp = (rng.uniform(-1, 1, (D, D)) / 16).astype(np.float32)
+    bp = (rng.uniform(-1, 1, D) / 16).astype(np.float32)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        qconv, pconv = torch.nn.Conv2d(D, D, 1).to(dev), torch.nn.Conv2d(D, D, 1).to(dev)
+        cb = vq.CodeBook(K, D).to(dev)
+        with torch.no_grad():
+            qconv.weight.copy_(torch.from_numpy(Wq).reshape(D, D, 1, 1)); qconv.bias.copy_(torch.from_numpy(bq))
+            pconv.weight.copy_(torch.from_numpy(Wp).reshape(D, D, 1, 1)); pconv.bias.copy_(torch.from_numpy(bp))
+            cb.codebook.weight.copy_(torch.from_numpy(E_np))
+        fused = vq.FoldedVQ(qconv, cb, pconv)
+        h = torch.from_numpy(h_np).to(dev).requires_grad_(True)
+        y, idx, loss = fused(h)
+        assert y.shape == (B, D, H, W) and y.is_contiguous()
+        g = torch.from_numpy(g_np).to(dev).permute(0, 3, 1, 2).contiguous()        # gradient on post_quant_x, NCHW
+        (loss + (y * g).sum()).backward()
+        torch.cuda.synchronize()
+        N = B * H * W
+
+        # same quantiser decisions as the encoder-side fold alone
+        with torch.no_grad():
+            zq1, idx1, loss1 = vq.FoldedQuantConv(qconv, cb)(torch.from_numpy(h_np).to(dev))
+        assert torch.equal(idx1, idx) and torch.equal(loss1, loss.detach())
+        idx_np = idx.cpu().numpy()
+        ref = oracle.forward(fused.pre.last_z.cpu().numpy(), E_np, 0.25)
+        assert np.array_equal(idx_np, ref["idx"])
+
+        # float64 truth on those indices
+        hr = h_np.astype(np.float64).transpose(0, 2, 3, 1).reshape(N, D)
+        z64 = hr @ Wq.astype(np.float64).T + bq
+        e = E_np.astype(np.float64)[idx_np]
+        y64 = e @ Wp.astype(np.float64).T + bp
+        gy = g_np.astype(np.float64).reshape(N, D)                                 # rows of the NCHW gradient
+        g_zq = gy @ Wp.astype(np.float64)
+        gz = g_zq + 2.0 * (z64 - e) / (N * D)
+        nchw = lambda a: a.reshape(B, H, W, D).transpose(0, 3, 1, 2)
+        assert rel_err(y.detach().cpu().numpy(), nchw(y64)) <= 1e-5
+        assert rel_err(h.grad.cpu().numpy(), nchw(gz @ Wq.astype(np.float64))) <= 1e-5
+        assert rel_err(qconv.weight.grad.reshape(D, D).cpu().numpy(), gz.T @ hr) <= 1e-5
+        assert rel_err(qconv.bias.grad.cpu().numpy(), gz.sum(0)) <= 1e-5
+        assert rel_err(pconv.weight.grad.reshape(D, D).cpu().numpy(), gy.T @ e) <= 1e-5
+        assert rel_err(pconv.bias.grad.cpu().numpy(), gy.sum(0)) <= 1e-5
+        gE = np.zeros((K, D))
+        np.add.at(gE, idx_np, 0.25 * 2.0 * (e - z64) / (N * D))                    # the loss gradient only, as in the reference
+        assert rel_err(cb.codebook.weight.grad.cpu().numpy(), gE) <= 1e-5
+    finally:
+        torch.backends.cudnn.allow_tf32 = old

@@ -95,6 +95,37 @@ def main():
         out[f"forward_ms_unfused_{tag}"] = timed(unfused_fwd, args.reps)
         out[f"forward_backward_ms_unfused_{tag}"] = timed(unfused_step, args.reps)
     torch.backends.cudnn.allow_tf32 = old
+    # the whole sandwich quant_conv -> CodeBook -> post_quant_conv (vqvae.py:128-133): library convolutions vs FoldedVQ
+    pconv = torch.nn.Conv2d(D, D, 1).to(dev)
+    both = vq.FoldedVQ(conv, cb, pconv)
+    g_y = g_out.contiguous()
+
+    def zero3():
+        zero()
+        for p in pconv.parameters():
+            p.grad = None
+
+    def sandwich_unfused_fwd():
+        with torch.no_grad():
+            return pconv(cb(conv(h))[0])
+
+    def sandwich_fused_fwd():
+        with torch.no_grad():
+            return both(h)[0]
+
+    def sandwich_unfused_step():
+        zero3()
+        z_q, idx, loss = cb(conv(hr))
+        torch.autograd.backward([pconv(z_q), loss], [g_y, one])
+
+    def sandwich_fused_step():
+        zero3()
+        y, idx, loss = both(hr)
+        torch.autograd.backward([y, loss], [g_y, one])
+
+    out["sandwich_forward_ms"] = {"library_tf32_convs": timed(sandwich_unfused_fwd, args.reps), "folded": timed(sandwich_fused_fwd, args.reps)}
+    out["sandwich_forward_backward_ms"] = {"library_tf32_convs": timed(sandwich_unfused_step, args.reps),
+                                           "folded": timed(sandwich_fused_step, args.reps)}
     out["forward_ms_fused"] = timed(fused_fwd, args.reps)
     out["forward_backward_ms_fused"] = timed(fused_step, args.reps)
     with torch.no_grad():

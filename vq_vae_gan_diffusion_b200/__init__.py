@@ -17,11 +17,11 @@ from . import _native
 from ._native import VQNativeError, build
 from .codebook import CodeBook, vq_embed_nchw
 from .postconv import FoldedPostQuant
-from .preconv import FoldedQuantConv
+from .preconv import FoldedQuantConv, FoldedVQ
 from .nearest import CodeTable, gaussian_to_indices, nearest_indices
 from .tokens import blend_with_sos, index_to_log_onehot, log_onehot_to_index, mask_and_replace
 
-__all__ = ["CodeBook", "FoldedPostQuant", "FoldedQuantConv", "vq_embed_nchw", "CodeTable", "nearest_indices", "gaussian_to_indices", "index_to_log_onehot", "log_onehot_to_index", "mask_and_replace", "blend_with_sos",
+__all__ = ["CodeBook", "FoldedPostQuant", "FoldedQuantConv", "FoldedVQ", "vq_embed_nchw", "CodeTable", "nearest_indices", "gaussian_to_indices", "index_to_log_onehot", "log_onehot_to_index", "mask_and_replace", "blend_with_sos",
            "VQNativeError", "build", "install"]
 
 REFERENCE_MODULE = "network.vqvae.submodule.codebook"
