@@ -29,9 +29,8 @@ Accuracy note: the reference's ``z_q = fl(z + fl(e - z))`` carries a rounding er
 (relative to |e|) away from e, and so are quantities linear in it (the convolution's weight gradient).  The fold uses e
 itself -- the value the straight-through construction stands for; tests compare both against a float64 evaluation.
 
-The encoder-side ``quant_conv`` (vqvae.py:83,128) is NOT folded: its output z is needed in fp32 by three consumers (operand
-conversion, exact stage / z_q / loss, backward), so fusing it means owning an fp32-accurate 256 x 256 tensor-core
-convolution (split-precision, three passes) inside the operand-preparation kernel -- see DESIGN.md section 9.
+The encoder-side ``quant_conv`` (vqvae.py:83,128) is folded by :class:`~vq_vae_gan_diffusion_b200.preconv.FoldedQuantConv`; both sides
+together: :class:`~vq_vae_gan_diffusion_b200.preconv.FoldedVQ`.
 """
 from __future__ import annotations
 
