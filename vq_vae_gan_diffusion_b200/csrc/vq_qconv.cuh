@@ -46,6 +46,10 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
                  : "memory");
 }
 
+// (Measured and dropped, cfg4-sized call with a one-tile codebook, forward 0.477 ms: a third stage in the source ring -- the bias
+// then read from global memory -- 0.490 ms; the next TMEM load in flight while the current accumulator chunk is processed,
+// 167 registers, 0.482 ms; both, 0.507 ms.  profiles/r2_ab_qconv_variants.jsonl)
+constexpr int kQcHsSlots = 2;             // stages of the fp32 source ring
 constexpr int kQcThreads = 384;
 constexpr int kQcWarpH = 0, kQcWarpW = 1, kQcWarpMma = 2;      // (warp 3 idles: the converter / epilogue groups stay 4-aligned)
 constexpr int kQcWarpConv0 = 4, kQcWarpEpi0 = 8;
@@ -59,11 +63,11 @@ struct QcSmem {
     alignas(1024) uint8_t a_hi[2][kQcBytesA];
     alignas(1024) uint8_t a_lo[2][kQcBytesA];
     alignas(1024) uint8_t b[2][kQcBytesB];
-    alignas(128) float hs[2][kQcStageCh][kRowTile];
+    alignas(128) float hs[kQcHsSlots][kQcStageCh][kRowTile];
     float bias[kD];
     float hinv[2][kRowTile];                                    // 1 / s_h of the tile's rows (by tile parity)
-    alignas(8) uint64_t hs_full[2];
-    uint64_t hs_empty[2];
+    alignas(8) uint64_t hs_full[kQcHsSlots];
+    uint64_t hs_empty[kQcHsSlots];
     uint64_t a_full[2];
     uint64_t a_empty[2];
     uint64_t b_full[2];
@@ -147,9 +151,11 @@ vq_qconv_prep_kernel(const QconvParams p, const __grid_constant__ CUtensorMap tm
     }
 
     if (warp == 0 && lane == 0) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kQcHsSlots; i++) {
             mbar_init(&s.hs_full[i], 1);
             mbar_init(&s.hs_empty[i], 4);
+        }
+        for (int i = 0; i < 2; i++) {
             mbar_init(&s.a_full[i], 4);
             mbar_init(&s.a_empty[i], 1);
             mbar_init(&s.b_full[i], 1);
@@ -174,14 +180,13 @@ vq_qconv_prep_kernel(const QconvParams p, const __grid_constant__ CUtensorMap tm
     if (warp == kQcWarpH) {
         // ------------------------------------------------------------------ h producer
         const uint64_t pol_stream = policy_evict_first();     // second pass: the tile is not needed again
-        uint32_t it = 0;
+        uint32_t slot = 0, ph = 0;                            // ring position of the next stage and its phase
         for (int t = blockIdx.x; t < p.row_tiles; t += gridDim.x) {
             const int64_t n0 = (int64_t)t * kRowTile;
             const int64_t b = n0 / p.HW, hw0 = n0 % p.HW;
             const float* src0 = p.h + (b * kD) * p.HW + hw0;
             for (int pass = 0; pass < 2; pass++) {
-                for (int dc = 0; dc < kNumDChunks; dc++, it++) {
-                    const uint32_t slot = it & 1, ph = (it >> 1) & 1;
+                for (int dc = 0; dc < kNumDChunks; dc++) {
                     mbar_wait(&s.hs_empty[slot], ph ^ 1);
                     if (lane == 0) mbar_expect_tx(&s.hs_full[slot], kQcBytesHs);
                     __syncwarp();
@@ -198,6 +203,7 @@ vq_qconv_prep_kernel(const QconvParams p, const __grid_constant__ CUtensorMap tm
                         }
                     }
                     __syncwarp();
+                    if (++slot == kQcHsSlots) { slot = 0; ph ^= 1; }
                 }
             }
         }
@@ -271,52 +277,53 @@ vq_qconv_prep_kernel(const QconvParams p, const __grid_constant__ CUtensorMap tm
     } else if (warp >= kQcWarpConv0 && warp < kQcWarpEpi0) {
         // ------------------------------------------------------------------ converters: thread <-> latent row of the tile
         const int r = (warp - kQcWarpConv0) * 32 + lane;
-        uint32_t ith = 0, ita = 0, tile_i = 0;
+        uint32_t slot = 0, ph = 0, ita = 0, tile_i = 0;
+        const uint32_t hs_sa = smem_u32(&s.hs[0][0][r]);      // (explicit shared-memory accesses: the manually aligned base is a
+        const uint32_t ahi_sa = smem_u32(s.a_hi[0]) + r * 128, alo_sa = smem_u32(s.a_lo[0]) + r * 128;   // generic pointer to the compiler)
         for (int t = blockIdx.x; t < p.row_tiles; t += gridDim.x, tile_i++) {
             // pass 0: max |h| of the row over all 256 channels (the operand scale must be known before the first conversion)
             float mx = 0.0f;
-            for (int dc = 0; dc < kNumDChunks; dc++, ith++) {
-                const uint32_t slot = ith & 1, ph = (ith >> 1) & 1;
+            for (int dc = 0; dc < kNumDChunks; dc++) {
                 mbar_wait(&s.hs_full[slot], ph);
-                const float* col = &s.hs[slot][0][r];
+                const uint32_t col = hs_sa + slot * kQcBytesHs;
 #pragma unroll 16
-                for (int c = 0; c < kQcStageCh; c++) mx = fmaxf(mx, fabsf(col[c * kRowTile]));
+                for (int c = 0; c < kQcStageCh; c++) mx = fmaxf(mx, fabsf(lds_f32(col + c * (kRowTile * 4))));
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s.hs_empty[slot]);
+                if (++slot == kQcHsSlots) { slot = 0; ph ^= 1; }
             }
             const int ex = exponent_of(mx);
             const float sc = pow2f(kOperandTopExp - ex);
             {
                 const uint32_t par = tile_i & 1, use = tile_i >> 1;
                 mbar_wait(&s.hinv_empty[par], (use & 1) ^ 1);
-                s.hinv[par][r] = pow2f(ex - kOperandTopExp);
+                sts_f32(smem_u32(&s.hinv[par][r]), pow2f(ex - kOperandTopExp));
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&s.hinv_full[par]);
             }
             // pass 1: hi / lo fp16 operand rows of each 64-channel chunk
-            for (int dc = 0; dc < kNumDChunks; dc++, ith++, ita++) {
-                const uint32_t slot = ith & 1, ph = (ith >> 1) & 1;
+            for (int dc = 0; dc < kNumDChunks; dc++, ita++) {
                 const uint32_t as = ita & 1, aph = (ita >> 1) & 1;
                 mbar_wait(&s.hs_full[slot], ph);
                 mbar_wait(&s.a_empty[as], aph ^ 1);
-                const float* col = &s.hs[slot][0][r];
-                uint8_t* hi_row = s.a_hi[as] + r * 128;
-                uint8_t* lo_row = s.a_lo[as] + r * 128;
+                const uint32_t col = hs_sa + slot * kQcBytesHs;
+                const uint32_t hi_row = ahi_sa + as * kQcBytesA, lo_row = alo_sa + as * kQcBytesA;
 #pragma unroll
                 for (int c8 = 0; c8 < 8; c8++) {
                     uint32_t hv[4], lv[4];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const float x0 = col[(8 * c8 + 2 * j) * kRowTile] * sc, x1 = col[(8 * c8 + 2 * j + 1) * kRowTile] * sc;
+                        const float x0 = lds_f32(col + (8 * c8 + 2 * j) * (kRowTile * 4)) * sc;
+                        const float x1 = lds_f32(col + (8 * c8 + 2 * j + 1) * (kRowTile * 4)) * sc;
                         const __half2 hh = __floats2half2_rn(x0, x1);
                         const float2 hf = __half22float2(hh);
                         const __half2 ll = __floats2half2_rn(x0 - hf.x, x1 - hf.y);      // exact differences
                         hv[j] = *reinterpret_cast<const uint32_t*>(&hh);
                         lv[j] = *reinterpret_cast<const uint32_t*>(&ll);
                     }
-                    const int piece = (c8 ^ (r & 7)) << 4;                               // SWIZZLE_128B: 16-byte piece ^ (row & 7)
-                    *reinterpret_cast<uint4*>(hi_row + piece) = make_uint4(hv[0], hv[1], hv[2], hv[3]);
-                    *reinterpret_cast<uint4*>(lo_row + piece) = make_uint4(lv[0], lv[1], lv[2], lv[3]);
+                    const uint32_t piece = (uint32_t)((c8 ^ (r & 7)) << 4);              // SWIZZLE_128B: 16-byte piece ^ (row & 7)
+                    sts128(hi_row + piece, hv[0], hv[1], hv[2], hv[3]);
+                    sts128(lo_row + piece, lv[0], lv[1], lv[2], lv[3]);
                 }
                 fence_proxy_async_smem();                      // generic-proxy stores -> visible to the tensor core's reads
                 __syncwarp();
@@ -324,6 +331,7 @@ vq_qconv_prep_kernel(const QconvParams p, const __grid_constant__ CUtensorMap tm
                     mbar_arrive(&s.a_full[as]);
                     mbar_arrive(&s.hs_empty[slot]);
                 }
+                if (++slot == kQcHsSlots) { slot = 0; ph ^= 1; }
             }
         }
     } else if (warp >= kQcWarpEpi0) {
@@ -331,13 +339,15 @@ vq_qconv_prep_kernel(const QconvParams p, const __grid_constant__ CUtensorMap tm
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;
         const float w_inv = __ldg(p.w_scalars);
+        const uint32_t bias_sa = smem_u32(&s.bias[0]);
+        auto bias_at = [&](int ch) -> float { return lds_f32(bias_sa + ch * 4); };
         uint32_t tile_i = 0;
         for (int t = blockIdx.x; t < p.row_tiles; t += gridDim.x, tile_i++) {
             const uint32_t buf = tile_i & 1, use = tile_i >> 1;
             const int64_t n0 = (int64_t)t * kRowTile;
             const int64_t b = n0 / p.HW, hw0 = n0 % p.HW;
             mbar_wait(&s.hinv_full[buf], use & 1);
-            const float scale = s.hinv[buf][r] * w_inv;       // 1 / (s_h s_W): exact (powers of two)
+            const float scale = lds_f32(smem_u32(&s.hinv[buf][r])) * w_inv;       // 1 / (s_h s_W): exact (powers of two)
             __syncwarp();
             if (lane == 0) mbar_arrive(&s.hinv_empty[buf]);
             mbar_wait(&s.t_full[buf], use & 1);
@@ -347,18 +357,14 @@ vq_qconv_prep_kernel(const QconvParams p, const __grid_constant__ CUtensorMap tm
             // pass A: z = fl(acc * scale + bias) stored NCHW; |z|^2 in the canonical order (partial j over d == j (mod 4),
             // ascending, one fma each -- vq_prep_z_kernel's chains); row maximum
             float p0 = 0.0f, p1 = 0.0f, p2 = 0.0f, p3 = 0.0f, mx = 0.0f;
-#pragma unroll 1
-            for (int c = 0; c < kD / 32; c++) {
-                uint32_t acc[32];
-                tmem_ld32(taddr + 32 * c, acc);
-                tmem_ld_wait();
+            auto pass_a = [&](const uint32_t (&acc)[32], int c) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     const int ch = 32 * c + i;
-                    const float z0 = __fmaf_rn(__uint_as_float(acc[i + 0]), scale, s.bias[ch + 0]);
-                    const float z1 = __fmaf_rn(__uint_as_float(acc[i + 1]), scale, s.bias[ch + 1]);
-                    const float z2v = __fmaf_rn(__uint_as_float(acc[i + 2]), scale, s.bias[ch + 2]);
-                    const float z3 = __fmaf_rn(__uint_as_float(acc[i + 3]), scale, s.bias[ch + 3]);
+                    const float z0 = __fmaf_rn(__uint_as_float(acc[i + 0]), scale, bias_at(ch + 0));
+                    const float z1 = __fmaf_rn(__uint_as_float(acc[i + 1]), scale, bias_at(ch + 1));
+                    const float z2v = __fmaf_rn(__uint_as_float(acc[i + 2]), scale, bias_at(ch + 2));
+                    const float z3 = __fmaf_rn(__uint_as_float(acc[i + 3]), scale, bias_at(ch + 3));
                     zp[(int64_t)(ch + 0) * p.HW] = z0;
                     zp[(int64_t)(ch + 1) * p.HW] = z1;
                     zp[(int64_t)(ch + 2) * p.HW] = z2v;
@@ -367,25 +373,12 @@ vq_qconv_prep_kernel(const QconvParams p, const __grid_constant__ CUtensorMap tm
                     p2 = __fmaf_rn(z2v, z2v, p2); p3 = __fmaf_rn(z3, z3, p3);
                     mx = fmaxf(mx, fmaxf(fmaxf(fabsf(z0), fabsf(z1)), fmaxf(fabsf(z2v), fabsf(z3))));
                 }
-            }
-            const float zz = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
-            const int ex = exponent_of(mx);
-            p.z2[n0 + r] = zz;
-            p.z_inv_scale[n0 + r] = pow2f(ex - kOperandTopExp);
-            const float sc = pow2f(kOperandTopExp - ex);
+            };
             // pass B: the row of the distance GEMM's operand image ([row tile][chunk][128][64] fp16, SWIZZLE_128B), recomputed
             // from the accumulator with the same fma -> the same z, bit for bit
             __half* img = p.z_h + ((int64_t)t * kNumDChunks) * (kRowTile * kDChunk) + r * kDChunk;
-#pragma unroll 1
-            for (int c = 0; c < kD / 32; c++) {
-                uint32_t acc[32];
-                tmem_ld32(taddr + 32 * c, acc);
-                tmem_ld_wait();
-                if (c == kD / 32 - 1) {                       // the accumulator is in registers for the last time: release it
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s.t_empty[buf]);
-                }
+            float sc = 0.0f;
+            auto pass_b = [&](const uint32_t (&acc)[32], int c) {
                 __half* chunk = img + (int64_t)(c >> 1) * (kRowTile * kDChunk);
 #pragma unroll
                 for (int q = 0; q < 4; q++) {
@@ -393,14 +386,42 @@ vq_qconv_prep_kernel(const QconvParams p, const __grid_constant__ CUtensorMap tm
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const int i = 8 * q + 2 * j, ch = 32 * c + i;
-                        const float za = __fmaf_rn(__uint_as_float(acc[i]), scale, s.bias[ch]);
-                        const float zb = __fmaf_rn(__uint_as_float(acc[i + 1]), scale, s.bias[ch + 1]);
+                        const float za = __fmaf_rn(__uint_as_float(acc[i]), scale, bias_at(ch));
+                        const float zb = __fmaf_rn(__uint_as_float(acc[i + 1]), scale, bias_at(ch + 1));
                         const __half2 hh = __floats2half2_rn(za * sc, zb * sc);
                         pk[j] = *reinterpret_cast<const uint32_t*>(&hh);
                     }
                     const int piece = (c & 1) * 4 + q;
                     *reinterpret_cast<uint4*>(chunk + ((piece ^ (r & 7)) << 3)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
                 }
+            };
+            auto finish_a = [&]() {
+                const float zz = __fadd_rn(__fadd_rn(p0, p1), __fadd_rn(p2, p3));
+                const int ex = exponent_of(mx);
+                p.z2[n0 + r] = zz;
+                p.z_inv_scale[n0 + r] = pow2f(ex - kOperandTopExp);
+                sc = pow2f(kOperandTopExp - ex);
+            };
+            auto release = [&]() {                             // the accumulator is in registers for the last time
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&s.t_empty[buf]);
+            };
+#pragma unroll 1
+            for (int c = 0; c < kD / 32; c++) {
+                uint32_t acc[32];
+                tmem_ld32(taddr + 32 * c, acc);
+                tmem_ld_wait();
+                pass_a(acc, c);
+            }
+            finish_a();
+#pragma unroll 1
+            for (int c = 0; c < kD / 32; c++) {
+                uint32_t acc[32];
+                tmem_ld32(taddr + 32 * c, acc);
+                tmem_ld_wait();
+                if (c == kD / 32 - 1) release();
+                pass_b(acc, c);
             }
         }
     }
