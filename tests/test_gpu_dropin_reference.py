@@ -200,3 +200,38 @@ def test_frozen_vqvae_and_state_dict_roundtrip(env):
     assert torch.equal(idx_o, idx_r)
     for p in ours.parameters():
         p.requires_grad = True
+
+
+def test_vqvae_forward_backward_with_both_convolutions_folded(env):
+    """The reference VQVAE's own forward (vqvae.py:116-137) with quant_conv -> CodeBook -> post_quant_conv replaced by the opt-in
+    FoldedVQ: decoded images, indices, q_loss and the gradients of encoder / both 1x1 convolutions / codebook
+    against the unmodified reference model on identical weights and inputs."""
+    vq = env["vq"]
+    ref, ours = env["ref"]["vqvae"], env["ours"]["vqvae"]
+    x = _images(4, seed=41)
+    _plant_codebook(env, x)
+    fused = vq.FoldedVQ(ours.quant_conv, ours.codebook, ours.post_quant_conv)
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False                      # the reference's convolutions in fp32, like the fold's arithmetic
+    try:
+        ref.zero_grad(set_to_none=True)
+        dec_r, idx_r, loss_r = ref(x)
+        (torch.nn.functional.l1_loss(dec_r, x) + loss_r).backward()
+        ours.zero_grad(set_to_none=True)
+        h = ours.encoder(x)
+        assert fused.pre.fusable(h), "16 x 16 latents of 256 channels are what the fused kernel takes"
+        post_quant_x, idx_o, loss_o = fused(h)                   # in place of vqvae.py:128-133
+        dec_o = ours.decoder(post_quant_x)
+        (torch.nn.functional.l1_loss(dec_o, x) + loss_o).backward()
+    finally:
+        torch.backends.cudnn.allow_tf32 = old
+    assert torch.equal(idx_o, idx_r), "planted codebook: every index must agree"
+    assert abs(float(loss_o) - float(loss_r)) <= 1e-5 * abs(float(loss_r))
+    assert rel_err(dec_o.detach().cpu().numpy(), dec_r.detach().cpu().numpy()) <= 1e-4
+    for what, po, pr in (("codebook.weight.grad", ours.codebook.codebook.weight, ref.codebook.codebook.weight),
+                         ("quant_conv.weight.grad", ours.quant_conv.weight, ref.quant_conv.weight),
+                         ("quant_conv.bias.grad", ours.quant_conv.bias, ref.quant_conv.bias),
+                         ("post_quant_conv.weight.grad", ours.post_quant_conv.weight, ref.post_quant_conv.weight),
+                         ("first encoder weight grad", next(ours.encoder.parameters()), next(ref.encoder.parameters()))):
+        err = rel_err(po.grad.cpu().numpy(), pr.grad.cpu().numpy())
+        assert err <= 2e-4, (what, err)                          # cuDNN / cuBLAS kernels in between: not our arithmetic
