@@ -134,3 +134,51 @@ def test_narrow_latent_dim_is_accepted_and_wide_rejected():
         cb(torch.zeros(1, 64, 2, 2))
     with pytest.raises(ValueError):
         vq.CodeBook(8, 512)(torch.zeros(1, 512, 2, 2))
+
+
+def test_folded_quant_conv_entry_points_validate_without_gpu():
+    """vq_forward_qconv / vq_prepare_quant_conv / vq_pack_stats / vq_allreduce_multimem refuse bad arguments before any device
+    work, and the Python modules over them have no CPU path (the CodeBook they end in raises)."""
+    L = _native.lib()
+    one = ctypes.c_void_p(16)                                    # a non-null, 16-byte aligned dummy (never dereferenced)
+    args_tail = (one, one, one, one, 16, 0.25, None, one, one, None, None, one, 1 << 20, None)
+    assert L.vq_forward_qconv(one, 2, 35, 256, one, one, None, one, *args_tail) == -2          # HW % 128 != 0: VQ_E_UNSUPPORTED
+    assert b"HW" in L.vq_last_error()
+    assert L.vq_forward_qconv(one, 2, 128, 64, one, one, None, one, *args_tail) == -2          # only 256 -> 256
+    assert L.vq_forward_qconv(None, 2, 128, 256, one, one, None, one, *args_tail) == -1        # null activations
+    assert L.vq_forward_qconv(ctypes.c_void_p(20), 2, 128, 256, one, one, None, one, *args_tail) == -1   # misaligned
+    assert L.vq_prepare_quant_conv(None, one, one, None) == -1
+    assert L.vq_pack_stats(None, one, 16, one, None) == -1
+    assert L.vq_pack_stats(one, one, 0, one, None) == -1
+    assert L.vq_allreduce_multimem(one, one, 0, 1, 64, one, None) == -1                        # world < 2
+    assert L.vq_allreduce_multimem(one, one, 0, 2, 60, one, None) == -1                        # not a multiple of 4 * world
+    assert L.vq_allreduce_multimem(one, one, 0, 2, 64, None, None) == -1                       # no local_sync words
+    conv = torch.nn.Conv2d(256, 256, 1)
+    cb = vq.CodeBook(32, 256)
+    fused = vq.FoldedQuantConv(conv, cb)
+    h = torch.zeros(1, 256, 8, 16)
+    assert not fused.fusable(h)                                  # CPU tensor: the composition, whose CodeBook refuses it
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fused(h)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        vq.FoldedVQ(conv, cb, torch.nn.Conv2d(256, 256, 1))(h)
+    with pytest.raises(ValueError):
+        vq.FoldedQuantConv(torch.nn.Conv2d(256, 256, 3, padding=1), cb)
+    with pytest.raises(ValueError):
+        vq.FoldedQuantConv(torch.nn.Conv2d(256, 128, 1), cb)
+
+
+def test_conv_oracle_matches_torch_conv2d():
+    """oracle/vq_oracle.py: quant_conv_fp32 restates nn.Conv2d(C, C, 1) (vqvae.py:83) on the CPU."""
+    import numpy as np
+    from oracle.vq_oracle import quant_conv_fp32
+    torch.manual_seed(1)
+    conv = torch.nn.Conv2d(256, 256, 1)
+    h = torch.randn(2, 256, 4, 8)
+    with torch.no_grad():
+        want = conv(h).numpy()
+    got = quant_conv_fp32(h.numpy(), conv.weight.detach().numpy(), conv.bias.detach().numpy())
+    assert got.shape == want.shape and got.dtype == np.float32
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    got_nb = quant_conv_fp32(h.numpy(), conv.weight.detach().numpy().reshape(256, 256))
+    assert np.abs(got_nb + conv.bias.detach().numpy()[None, :, None, None] - want).max() <= 1e-5 * np.abs(want).max()
