@@ -5,7 +5,8 @@
 
 A "step" is one pass of the hot path over one batch of synthetic latents: CodeBook forward (operand prep,
 tcgen05 distance GEMM with fused candidate argmin, exact fp32 select + gather + loss + histogram) followed by the
-backward (straight-through grad_z + scatter-add grad_E), plus -- for N > 1 -- the codebook-gradient all-reduce.
+backward (straight-through grad_z + scatter-add grad_E), plus -- for N > 1 -- the codebook-gradient all-reduce (the library's
+NVLS kernel on symmetric memory where every rank can set it up, NCCL otherwise: --collective auto | nccl | multimem).
 The derived codebook state is rebuilt every step, as it is in training where the optimizer changes the weight.
 
 Default workload = BASELINE.json configs[3] ("cfg4"): K=16384, D=256, batch 256 of 32x32 latents PER GPU (weak
@@ -14,8 +15,8 @@ quoted on.  Inputs (268 MB of z + 268 MB of g_out per GPU) exceed the 126 MB L2,
 
 Prints ONE JSON line (rank 0).  `value` = device-resident throughput, `e2e` = the same step driven from pinned host
 buffers (H2D of z and g_out -- double buffered on a copy stream -- and D2H of loss and indices inside the timed region), `roofline` = the distance-GEMM kernel
-against the measured bf16 tensor peak, `cpu_baseline` = the torch-CPU port of the reference (same ATen ops) timed on this box's
-host cores on a bounded row sample.
+against the measured bf16 tensor peak, `cpu_baseline` = the unmodified reference class (staged under baseline/_ref; the torch-CPU
+port of the oracle only when the staged tree is missing) timed on this box's host cores on a bounded row sample.
 
 --impl reference: the reference arm.  Times the UNMODIFIED reference class (network/vqvae/submodule/codebook.py, staged
 byte for byte under git-ignored baseline/_ref/ by tools/stage_reference.py -- the reference is pure Python, there is
