@@ -15,6 +15,9 @@ for w in cfg3 cfg5 cfg2 cfg1; do python bench.py --workload $w --soak-seconds 0 
 for w in cfg2 cfg1; do python bench.py --workload $w --cuda-graphs --no-cpu-baseline --soak-seconds 0 --steps 200 > $O/${TAG}_bench_${w}_graphs.json 2>> $O/${TAG}_bench.err; done
 python tools/gpu_microbench.py --rows > $O/${TAG}_micro.jsonl 2>> $O/${TAG}_bench.err
 python tools/fold_postconv_bench.py --workload cfg4 > $O/${TAG}_fold_cfg4.json 2>> $O/${TAG}_bench.err
+for w in cfg4 cfg5; do python tools/fold_quantconv_bench.py --workload $w > $O/${TAG}_fold_quantconv_$w.json 2>> $O/${TAG}_bench.err; done
+# (multi-GPU, separately: gpurun --gpus 8 -- 'python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+#   --master-port 29533 tools/dp_overhead.py' -> profiles/r2_dp_overhead_8gpu.json; bench.py --gpus N under the same launcher)
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --soak-seconds 0 > /dev/null 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --soak-seconds 0 > $O/${TAG}_ncu1.log 2>&1
