@@ -182,3 +182,49 @@ def test_conv_oracle_matches_torch_conv2d():
     assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
     got_nb = quant_conv_fp32(h.numpy(), conv.weight.detach().numpy().reshape(256, 256))
     assert np.abs(got_nb + conv.bias.detach().numpy()[None, :, None, None] - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_split_precision_model_of_the_folded_convolution():
+    """The arithmetic vq_qconv_prep_kernel runs, modelled in numpy: operands split hi + lo in fp16 after an exact power-of-two
+    scaling (per row for h, per tensor for W), the three products hi hi + lo hi + hi lo accumulated in fp32 sixteen
+    contraction elements at a time -- pessimistically with TRUNCATION after every accumulation, which is the worst the tensor
+    core's fp32 accumulator is known to do -- then z = fl(acc / (s_h s_W) + b).  The model must sit inside the 1e-5 bar the GPU
+    test holds the kernel to, next to the fp32 CPU convolution (the oracle), for O(1), tiny and large activations."""
+    import numpy as np
+    from oracle.vq_oracle import quant_conv_fp32
+    rng = np.random.default_rng(0)
+    D, N = 256, 512
+
+    def split16(x, sc):
+        xs = (x * sc).astype(np.float32)
+        hi = xs.astype(np.float16)
+        lo = (xs - hi.astype(np.float32)).astype(np.float16)
+        return hi.astype(np.float64), lo.astype(np.float64)
+
+    def trunc32(x):
+        y = x.astype(np.float32)
+        bad = np.abs(y.astype(np.float64)) > np.abs(x)
+        y[bad] = np.nextafter(y[bad], np.float32(0))
+        return y
+
+    for h_scale in (1.0, 1e-4, 3e3):
+        h = (h_scale * rng.standard_normal((N, D))).astype(np.float32)
+        W = (rng.uniform(-1, 1, (D, D)) / 16).astype(np.float32)
+        b = (h_scale * rng.uniform(-1, 1, D) / 16).astype(np.float32)
+        z64 = h.astype(np.float64) @ W.astype(np.float64).T + b
+        s_h = np.ldexp(1.0, 15 - np.frexp(np.abs(h).max(1))[1])[:, None].astype(np.float32)
+        s_w = np.float32(np.ldexp(1.0, 15 - np.frexp(np.abs(W).max())[1]))
+        hh, hl = split16(h, s_h)
+        wh, wl = split16(W, s_w)
+        assert np.abs(hh + hl - (h * s_h).astype(np.float64)).max() <= 2.0 ** -8           # <= 2^-23 of the row's top binade (2^15)
+        acc = np.zeros((N, D), np.float32)
+        for dc in range(4):
+            for A, B in ((hh, wh), (hl, wh), (hh, wl)):
+                for k in range(4):
+                    s = slice(64 * dc + 16 * k, 64 * dc + 16 * k + 16)
+                    acc = trunc32(acc.astype(np.float64) + A[:, s] @ B[:, s].T)
+        z = (acc.astype(np.float64) / s_h.astype(np.float64) / float(s_w) + b).astype(np.float32)
+        err = np.abs(z - z64).max() / np.abs(z64).max()
+        z_cpu = quant_conv_fp32(h.T.reshape(1, D, N, 1).copy(), W, b)[0, :, :, 0].T
+        err_cpu = np.abs(z_cpu - z64).max() / np.abs(z64).max()
+        assert err <= 5e-6 and err_cpu <= 5e-6, (h_scale, err, err_cpu)
